@@ -1,0 +1,1 @@
+"""Minimal stand-in for the absent third-party torch_robotics package (golden generation only)."""

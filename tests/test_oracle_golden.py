@@ -1,0 +1,168 @@
+"""CPU: the oracle restatement against the golden vectors produced by the UNMODIFIED reference
+planners (oracle/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from motion_planning_baselines_b200 import configs
+from oracle import gp_prior, planners
+from oracle.build import TA, oracle_field, oracle_robot
+from oracle.costs import CostSpec
+
+from conftest import load_golden
+
+
+def T(a):
+    return torch.as_tensor(np.asarray(a))
+
+
+def assert_close(a, b, rtol=1e-5, atol=0.0, what=''):
+    a, b = T(a).double(), T(b).double()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    assert bool((err <= tol).all()), f'{what}: max rel err {(err / b.abs().clamp_min(1e-30)).max():.3e}, max abs {err.max():.3e}'
+
+
+@pytest.mark.parametrize('name', ['prior_d2_H16', 'prior_d7_H8'])
+def test_prior_precision_factor_and_samples(name):
+    g = load_golden(name)
+    m = g['meta']
+    d, H = m['d'], m['H']
+    K_s = gp_prior.unary_K(2 * d, m['sig_s'], TA)
+    K_g = gp_prior.unary_K(2 * d, m['sig_g'], TA)
+    Q = gp_prior.gp_Q_inv(d, m['dt'], m['sig_gp'], TA)
+    assert torch.equal(K_s, T(g['K_s'])) and torch.equal(K_g, T(g['K_g'])) and torch.equal(Q, T(g['Q_inv']))
+    Sinv = gp_prior.prior_precision(H, d, m['dt'], K_s, Q, K_g, TA)
+    assert torch.equal(Sinv, T(g['Sigma_inv'])), 'precision must be bit-identical (same fp64 assembly)'
+    L = gp_prior.precision_to_scale_tril(Sinv)
+    assert_close(L, g['scale_tril'], rtol=1e-6, atol=1e-9, what='scale_tril')
+    x = gp_prior.sample_prior(T(g['means']).reshape(m['P'], -1), T(g['scale_tril']), T(g['eps']))
+    assert_close(x.reshape(m['P'], m['S'], H, 2 * d), g['samples'], rtol=1e-5, atol=1e-6, what='samples')
+    cv = gp_prior.const_vel_mean(T(g['start']), T(g['goal'])[0], m['dt'], H, d, TA)
+    assert_close(cv.reshape(1, -1), g['const_vel_mean'], rtol=1e-6, atol=1e-7, what='const-vel mean')
+
+
+def _spec(g, H):
+    m = g['meta']
+    cfg = configs.config(m['cfg'])
+    robot = oracle_robot(cfg['robot'], m['dt'])
+    field = oracle_field(cfg['obstacles'], cfg['robot'])
+    return CostSpec(robot, H, m['dt'], T(g['start']), T(g['goal']), [field],
+                    sigma_start=m['sigma_start'], sigma_gp=m['sigma_gp'], sigma_coll=m['sigma_coll'],
+                    sigma_goal_prior=m['sigma_goal_prior'], tensor_args=TA)
+
+
+STOCH = ['stochgpmp_pm2d_moderate', 'stochgpmp_pm3d_moderate', 'stochgpmp_pm3d_frozen',
+         'stochgpmp_panda_moderate', 'stochgpmp_panda_frozen']
+
+
+@pytest.mark.parametrize('name', STOCH)
+def test_stoch_gpmp_iteration(name):
+    g = load_golden(name)
+    m = g['meta']
+    spec = _spec(g, m['H'])
+    means = T(g['means0'])
+    L, Sinv = T(g['L']), T(g['Sigma_inv'])
+    for it in range(m['iters']):
+        out = planners.stoch_gpmp_iteration(spec, means, L, Sinv, T(g[f'eps{it}']), m['temperature'], m['step_size'])
+        assert_close(out['samples'], g[f'samples{it}'], rtol=1e-5, atol=1e-6, what='samples')
+        # cost terms and totals on the reference's own samples (isolates cost maths from sampling)
+        xs = T(g[f'samples{it}'])
+        terms = torch.stack([t.reshape(-1) for t in spec.terms(xs.reshape(-1, *xs.shape[2:]))])
+        assert_close(terms, g[f'terms{it}'], rtol=2e-6, atol=1e-6, what='cost terms')
+        c = planners.stoch_gpmp_costs(spec, xs, means, Sinv, m['temperature'])
+        assert_close(c, g[f'costs{it}'], rtol=1e-5, what='costs + IS term')
+        w, _, new = planners.softmax_update(T(g[f'costs{it}']), xs, means, m['temperature'], m['step_size'])
+        assert_close(w, g[f'weights{it}'], rtol=1e-5, atol=1e-30, what='weights (reference costs)')
+        assert_close(new, g[f'means{it + 1}'], rtol=1e-5, atol=1e-7, what='updated means')
+        assert int(out['costs'].argmin()) == int(T(g[f'costs{it}']).argmin())
+        means = T(g[f'means{it + 1}'])
+
+
+@pytest.mark.parametrize('name', ['stomp_pm2d', 'stomp_panda'])
+def test_stomp_iteration(name):
+    g = load_golden(name)
+    m = g['meta']
+    cfg = configs.config(m['cfg'])
+    robot = oracle_robot(cfg['robot'], m['dt'])
+    field = oracle_field(cfg['obstacles'], cfg['robot'])
+    spec = CostSpec(robot, m['H'], m['dt'], T(g['start']), None, [field], sigma_coll=m['sigma_coll'], tensor_args=TA)
+    cost = lambda x: spec.collision_cost(x, field)
+    R = planners.stomp_R(m['H'], m['dt'], m['sigma_spectral'], TA)
+    assert_close(R, g['R'], rtol=1e-6, what='R')
+    assert_close(gp_prior.precision_to_scale_tril(R), g['L_R'], rtol=1e-4, atol=1e-9, what='L_R')
+    means = T(g['means0'])
+    for it in range(m['iters']):
+        out = planners.stomp_iteration(cost, means, T(g['L_R']), T(g['Sigma']), T(g[f'eps{it}']),
+                                       m['temperature'], m['step_size'])
+        assert_close(out['samples'], g[f'samples{it}'], rtol=1e-5, atol=1e-6, what='samples')
+        assert_close(out['costs'], g[f'costs{it}'], rtol=1e-4, atol=1e-3, what='costs')
+        w = torch.softmax(-T(g[f'costs{it}']) / m['temperature'], dim=1)
+        assert_close(w, g[f'weights{it}'], rtol=1e-5, atol=1e-30, what='weights')
+        assert_close(out['means'], g[f'means{it + 1}'], rtol=1e-4, atol=1e-5, what='means')
+        means = T(g[f'means{it + 1}'])
+
+
+def test_mppi_iteration():
+    g = load_golden('mppi_pm2d')
+    m = g['meta']
+    cfg = configs.config('C1')
+    robot = oracle_robot(cfg['robot'], m['dt'])
+    field = oracle_field(cfg['obstacles'], cfg['robot'])
+    spec = CostSpec(robot, m['T'], m['dt'], T(g['start']), None, [field], sigma_coll=m['sigma_coll'], tensor_args=TA)
+
+    class Ext:
+        def eval(self, x):
+            return spec.collision_cost(x, field)
+    Cov = planners.mppi_cov(m['T'], [0.15, 0.15], 'const_ctrl', TA)
+    assert_close(Cov, g['Cov'], rtol=1e-6, what='Cov')
+    mean = T(g['mean0'])
+    best = float('inf')
+    for it in range(m['iters']):
+        out = planners.mppi_iteration(mean, T(g['L_ctrl']), T(g['Cov_inv']), T(g[f'eps{it}']), T(g['start']),
+                                      T(g['goal']), m['dt'], torch.tensor([-100., -100.]), torch.tensor([100., 100.]),
+                                      m['c_weights'], 1.0, 1.0, ext_cost=Ext())
+        assert_close(out['controls'], g[f'controls{it}'], rtol=1e-5, atol=1e-6, what='controls')
+        assert_close(out['states'], g[f'states{it}'], rtol=1e-5, atol=1e-6, what='states')
+        assert_close(out['costs'], g[f'costs{it}'], rtol=1e-5, what='costs')
+        assert_close(out['weights'].reshape(-1), g[f'weights{it}'].reshape(-1), rtol=1e-3, atol=1e-7, what='weights')
+        assert_close(out['mean'], g[f'mean{it + 1}'], rtol=1e-3, atol=1e-5, what='mean')
+        best = min(best, float(out['best_cost']))
+        assert_close(best, g[f'best_cost{it}'], rtol=1e-5, what='best cost')
+        mean = T(g[f'mean{it + 1}'])
+
+
+def test_chomp_iterations():
+    g = load_golden('chomp_pm2d')
+    m = g['meta']
+    cfg = configs.config(m['cfg'])
+    robot = oracle_robot(cfg['robot'], m['dt'])
+    field = oracle_field(cfg['obstacles'], cfg['robot'])
+    spec = CostSpec(robot, m['H'], m['dt'], T(g['start']), None, [field], sigma_coll=m['sigma_coll'], tensor_args=TA)
+    cost = lambda x: m['cost_weight'] * spec.collision_cost(x, field)
+    R = planners.chomp_R(m['H'], m['dt'], TA)
+    assert_close(R, g['R'], rtol=1e-6, what='R')
+    x = T(g['x0'])
+    for it in range(m['iters']):
+        out = planners.chomp_iteration(cost, x, R, m['weight_prior_cost'], m['step_size'], m['grad_clip'])
+        assert_close(out['x'], g[f'x{it + 1}'], rtol=1e-5, atol=1e-6, what=f'x after iter {it}')
+        x = T(g[f'x{it + 1}'])
+    assert_close(T(g[f"x{m['iters']}"]), g['x_multi'], rtol=1e-6, atol=1e-7, what='multi-iteration run')
+
+
+@pytest.mark.parametrize('name', ['gpmp2_pm2d', 'gpmp2_panda'])
+def test_gpmp2_steps(name):
+    g = load_golden(name)
+    m = g['meta']
+    spec = _spec(g, m['H'])
+    means = T(g['means0'])
+    for it in range(m['iters']):
+        out = planners.gpmp2_step(spec, means, m['delta'], m['trust_region'], m['step_size'])
+        if it == 0:
+            assert_close(out['A'][:2], g['A0'], rtol=1e-4, atol=1e-6, what='A')
+            assert_close(out['b'], g['b0'], rtol=1e-5, atol=1e-7, what='b')
+            assert_close(torch.diagonal(out['K'], dim1=-2, dim2=-1), g['Kdiag0'], rtol=1e-6, what='K')
+        assert_close(out['costs'], g[f'costs{it}'], rtol=1e-4, what='costs')
+        step = (T(g[f'means{it + 1}']) - means).abs().max()
+        assert_close(out['means'], g[f'means{it + 1}'], rtol=1e-3, atol=float(2e-3 * step), what='means')
+        means = T(g[f'means{it + 1}'])
