@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- trajectory samples cost-evaluated+updated per second (Panda Stoch-GPMP, H=64).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                     (CPU baseline arm: the oracle port)
+
+A step = one Stoch-GPMP iteration over P=512 particles x S=64 samples x H=64 waypoints of the
+7-DoF Panda (BASELINE.json configs[3], "panda_spheres"): sample from the GP prior, forward
+kinematics to 50 collision spheres, collision + GP cost (+ importance-sampling term), softmax
+update.  Independent particles shard across GPUs with no data-path collective (weak scaling:
+512 particles per GPU).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'trajectory samples cost-evaluated+updated/sec (Panda, H=64)'
+UNIT = 'samples/s'
+P_PER_GPU, S, H, DOF = 512, 64, 64, 7
+D, M, NS, NO = 2 * DOF, 64 * 14, 50, 16
+# algorithmic work per sample (SURVEY.md 8d / BASELINE.md section 4, C4 column)
+FLOP_SAMPLING = M * (M + 1)                                   # 803,712  triangular mat-vec
+FLOP_FK = H * (600 + 18 * NS)                                 # 96,000
+FLOP_SDF = (H - 1) * NS * (10 * NO + 3)                       # 513,450
+FLOP_GP = (H - 1) * (10 * DOF + 5) + 4 * D                    # 4,781
+FLOP_IS = 2 * M                                               # 1,792
+FLOP_UPDATE = 2 * M + 10                                      # 1,802
+BYTES_UPDATE = M * 4                                          # K3 reads every sample row once
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p['hbm_gbs'], bf16=p['bf16_tflops'], bf16_sustained=p.get('bf16_tflops_sustained'),
+                    sm_max_mhz=p.get('sm_max_mhz', 1965.0), source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, sm_max_mhz=1965.0,
+                source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock and throttle reasons while the timed region runs."""
+
+    def __init__(self, index, period=0.004):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self._stop_evt = index, period, [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap',
+                 getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
+                 getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+                 getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+                 getattr(nv, 'nvmlClocksEventReasonHwPowerBrakeSlowdown', 0x80): 'hw_power_brake'}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return dict(sm_mhz=med, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), n_samples=len(self.samples))
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+    if vis:
+        try:
+            return int(vis.split(',')[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_setup(P_cpu):
+    """The oracle port of the reference's Stoch-GPMP iteration in its 'faithful' cost model:
+    per-particle scale_tril [P,M,M] re-factorised every iteration + broadcast batched mat-vec sampler
+    (mp_priors_multi.py:100-123), eager-torch cost chain, dense IS term."""
+    from motion_planning_baselines_b200 import configs
+    from oracle import gp_prior
+    from oracle.build import TA, oracle_field, oracle_robot
+    from oracle.costs import CostSpec
+    cfg = configs.config('C4')
+    sig = cfg['params']
+    start, goal = torch.tensor(cfg['start']), torch.tensor(cfg['goal'])
+    spec = CostSpec(oracle_robot(cfg['robot'], cfg['dt']), H, cfg['dt'], start, goal,
+                    [oracle_field(cfg['obstacles'], cfg['robot'])], sigma_start=sig['sigma_start'], sigma_gp=sig['sigma_gp'],
+                    sigma_coll=sig['sigma_coll'], sigma_goal_prior=sig['sigma_goal_prior'], tensor_args=TA)
+    K_s = gp_prior.unary_K(D, sig['sigma_start_sample'], TA)
+    K_g = gp_prior.unary_K(D, sig['sigma_goal_sample'], TA)
+    Q = gp_prior.gp_Q_inv(DOF, cfg['dt'], sig['sigma_gp_sample'], TA)
+    Sinv = gp_prior.prior_precision(H, DOF, cfg['dt'], K_s, Q, K_g, TA)
+    L = gp_prior.precision_to_scale_tril(Sinv)
+    mean = gp_prior.const_vel_mean(torch.cat((start, torch.zeros(DOF))), torch.cat((goal, torch.zeros(DOF))), cfg['dt'], H, DOF, TA)
+    means = mean.unsqueeze(0).repeat(P_cpu, 1, 1)
+    return spec, means, L, Sinv, sig
+
+
+def cpu_reference_run(P_cpu, steps, warmup, faithful=True):
+    from oracle import planners as oplanners
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec, means, L, Sinv, sig = cpu_reference_setup(P_cpu)
+    gen = torch.Generator().manual_seed(0)
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            eps = torch.randn(S, P_cpu, M, generator=gen)
+            t0 = time.perf_counter()
+            out = oplanners.stoch_gpmp_iteration(spec, means, L, Sinv, eps, sig['temperature'], sig['step_size'], faithful=faithful)
+            means = out['means']
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    t = float(np.sum(times))
+    return dict(value=P_cpu * S * steps / t, ms_per_step=1e3 * t / steps)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    P_cpu = args.cpu_particles
+    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    r = cpu_reference_run(P_cpu, steps, warmup, faithful=True)
+    cores = torch.get_num_threads()
+    sample = (f'{P_cpu} particles x {S} samples x {H} waypoints Panda per step (of {P_PER_GPU}); {steps} timed steps, '
+              f'{warmup} warm-up; oracle port in the reference cost model (per-particle scale_tril re-factorised every '
+              f'iteration, batched mat-vec sampler, eager torch fp32)')
+    line = dict(impl='reference', metric=METRIC, value=r['value'], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup,
+                ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', config=workload_config(args.gpus),
+                cpu_baseline=dict(value=r['value'], unit=UNIT, cores=cores, kind='port', sample=sample),
+                e2e=dict(value=r['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return dict(workload='panda_spheres Stoch-GPMP (BASELINE.json configs[3]): 7-DoF Panda FK -> 50 collision spheres vs 16 '
+                         'sphere obstacles, 512 particles x 64 samples x 64 waypoints per GPU',
+                particles_per_gpu=P_PER_GPU, samples=S, waypoints=H, dof=DOF, robot_spheres=NS, obstacles=NO,
+                global_samples_per_step=n * P_PER_GPU * S, sharding=f'particles x{n} (no data-path collective)',
+                noise='injected eps resident in HBM (8 rotating 117 MB buffers)',
+                l2='per-step inputs+outputs (235 MB) exceed the 126 MB L2; eps buffers rotate')
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-particles', type=int, default=32, help='particles per step of the bounded CPU-baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import ctypes as C
+
+    import torch.distributed as dist
+
+    from motion_planning_baselines_b200 import _lib, configs
+    from motion_planning_baselines_b200.fields import CollisionField
+    from motion_planning_baselines_b200.planners import StochGPMP
+    from motion_planning_baselines_b200.robots import Robot
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback for the product path)'
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = dict(device=torch.device('cuda', local_rank), dtype=torch.float32)
+    K, W = args.steps, max(args.warmup, 3)
+
+    cfg = configs.config('C4')
+    torch.manual_seed(1000 + rank)
+    robot = Robot(cfg['robot'], dt=cfg['dt'], tensor_args=dev)
+    field = CollisionField(cfg['obstacles'], tensor_args=dev)
+    P = P_PER_GPU
+    planner = StochGPMP(robot=robot, n_dof=DOF, n_support_points=H, num_particles_per_goal=P, opt_iters=1, dt=cfg['dt'],
+                        start_state=torch.tensor(cfg['start']).to(**dev),
+                        multi_goal_states=torch.tensor(cfg['goal']).to(**dev).unsqueeze(0),
+                        collision_fields=[field], tensor_args=dev, num_samples=S, **cfg['params'])
+    n_buf = 8
+    eps_bufs = [torch.randn(S, P, M, **dev) for _ in range(n_buf)]
+    means0 = planner._particle_means.clone()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ---------------------------------------------------------------------------
+    for i in range(W):
+        planner.step_staged(eps_bufs[i % n_buf])
+    planner._particle_means.copy_(means0)
+
+    # ---- timed region: exactly K steps, per-stage events inside ---------------------------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    barrier()
+    sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(K):
+        planner.step_staged(eps_bufs[i % n_buf], events=ev[i])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    stage_ms = np.array([[ev[i][j].elapsed_time(ev[i][j + 1]) for j in range(4)] for i in range(K)]).mean(0)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev['device'], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * P * S * K / (ms_total * 1e-3)
+    free_frac = float(planner.free_flags.float().mean())
+
+    # ---- e2e through the public API with HOST buffers ------------------------------------------
+    # per step: pinned-host eps -> device (H2D), planner.optimize(opt_iters=1, eps=...), trajectory -> pinned host (D2H)
+    planner._particle_means.copy_(means0)
+    h_eps = [torch.randn(S, P, M).pin_memory() for _ in range(2)]
+    d_eps = [torch.empty(S, P, M, **dev) for _ in range(2)]
+    h_traj = torch.empty(P, H, D).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
+    Ke = max(3, min(K, 20))
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            d_eps[b].copy_(h_eps[b], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_steps(n):
+        for b in range(2):
+            consumed[b].record(main_stream)
+        upload(0)
+        for i in range(n):
+            b = i % 2
+            if i + 1 < n:
+                upload(i + 1)                       # overlaps the next step's upload with this step's kernels
+            main_stream.wait_event(ready[b])
+            traj = planner.optimize(opt_iters=1, eps=[d_eps[b]])
+            consumed[b].record(main_stream)
+            h_traj.copy_(traj, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_steps(2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_steps(Ke)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev['device'], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = world * P * S * Ke / (ms_e2e * 1e-3)
+
+    # e2e with noise drawn on the device by the planner itself (informational)
+    planner._particle_means.copy_(means0)
+    barrier()
+    e0.record()
+    for i in range(Ke):
+        traj = planner.optimize(opt_iters=1)
+        h_traj.copy_(traj, non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e_dev = e0.elapsed_time(e1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    n_samp = P * S
+    sm_mhz_peak = clocks.get('sm_max_mhz') or pk['sm_max_mhz']
+    fp32_peak = 148 * 128 * 2 * sm_mhz_peak * 1e6 / 1e12            # TFLOP/s, nominal FMA rate at clocks.max.sm
+    kernels = []
+    flops = [FLOP_SAMPLING, None, FLOP_FK + FLOP_SDF + FLOP_GP + FLOP_IS, None]
+    names = ['sample_gp_simt_kernel (K1)', 'prior_matvec_kernel', 'cost_eval_kernel (K2)', 'softmax_update_kernel (K3)']
+    for j, nm in enumerate(names):
+        k = dict(kernel=nm, ms=float(stage_ms[j]), share=float(stage_ms[j] / stage_ms.sum()))
+        if flops[j]:
+            a = flops[j] * n_samp / (stage_ms[j] * 1e-3) / 1e12
+            k.update(bound='fp32', achieved=a, peak=fp32_peak, unit='TFLOP/s', frac=a / fp32_peak)
+        elif j == 3:
+            a = BYTES_UPDATE * n_samp / (stage_ms[j] * 1e-3) / 1e9
+            k.update(bound='hbm', achieved=a, peak=pk['hbm'], unit='GB/s', frac=a / pk['hbm'],
+                     note='algorithmic bytes = one read of every sample row; rows with zero weight are skipped, so achieved can exceed peak')
+        kernels.append(k)
+    dom = max((k for k in kernels if 'achieved' in k), key=lambda k: k['ms'])
+    roofline = dict(bound=dom['bound'], achieved=dom['achieved'], peak=dom['peak'], unit=dom['unit'], frac=dom['frac'],
+                    traffic=None, kernel=dom['kernel'], ms_per_launch=dom['ms'],
+                    peak_source=('nominal FP32 FMA rate 148 SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json holds only '
+                                 'HBM and bf16 tensor peaks; this kernel is FP32-issue bound)') if dom['bound'] == 'fp32' else pk['source'],
+                    algorithmic_flop_per_sample=flops[2] if 'K2' in dom['kernel'] else flops[0], kernels=kernels)
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=workload_config(world), clocks=clocks, gpu_launches=4 * K,
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=S * P * M * 4, d2h_bytes_per_step=P * H * D * 4,
+                         steps=Ke, ms_per_step=ms_e2e / Ke,
+                         note='planner.optimize(opt_iters=1, eps=<pinned host noise>) + trajectory read-back; the next '
+                              "step's noise upload overlaps this step's kernels",
+                         device_noise_ms_per_step=ms_e2e_dev / Ke),
+                roofline=roofline, collision_free_fraction_last_step=free_frac)
+    if not args.no_cpu_baseline:
+        torch.cuda.empty_cache()
+        r = cpu_reference_run(args.cpu_particles, steps=3, warmup=1, faithful=True)
+        line['cpu_baseline'] = dict(
+            value=r['value'], unit=UNIT, cores=torch.get_num_threads(), kind='port',
+            sample=(f'{args.cpu_particles} particles x {S} samples x {H} waypoints per step, 3 timed steps + 1 warm-up; oracle '
+                    'port in the reference cost model (per-iteration re-factorisation, batched mat-vec sampler, eager torch fp32)'),
+            ms_per_step=r['ms_per_step'])
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

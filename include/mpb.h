@@ -1,0 +1,145 @@
+/*
+ * mpb.h -- C ABI of libmpb_b200.so: the B200 (sm_100a) batched trajectory
+ * cost-and-update hot path of mp_baselines.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MPB_E* code otherwise;
+ *     mpb_last_error() returns a thread-local message for the last failure.
+ *   - all data pointers are DEVICE pointers on the current CUDA device unless
+ *     the parameter name ends in _host; descriptor structs themselves live on the host.
+ *   - fp32, row-major, contiguous.  The caller owns every buffer; the library
+ *     allocates nothing persistent and keeps no global state (stream-ordered,
+ *     re-entrant: one planner <-> one stream).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *
+ * Symbols used below: P particles, S samples per particle, H waypoints, d dof,
+ * D = 2d state width (position | velocity), M = H*D, B = number of trajectories.
+ *
+ * Each entry point names the reference code it replaces (paths relative to the
+ * reference repo root, anindex/motion_planning_baselines @ 8a50c3c).
+ */
+#ifndef MPB_H_
+#define MPB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPB_OK 0
+#define MPB_EINVAL (-1)     /* bad argument (shape, null pointer, unsupported size) */
+#define MPB_ECUDA (-2)      /* a CUDA runtime call or kernel launch failed */
+#define MPB_EUNSUPPORTED (-3)
+
+#define MPB_MAX_FIELDS 4
+#define MPB_MAX_DOF 8
+#define MPB_ROBOT_POINT 0   /* q is the workspace position (2-D / 3-D point mass) */
+#define MPB_ROBOT_CHAIN 1   /* serial chain of revolute-z joints with a sphere table */
+
+/* Replaces the duck-typed `robot` the reference passes around
+ * (mp_baselines/planners/costs/cost_functions.py:21,50-52: q_dim, get_position,
+ * get_velocity, fk_map_collision). */
+typedef struct mpb_robot_desc {
+    int32_t kind;               /* MPB_ROBOT_POINT | MPB_ROBOT_CHAIN */
+    int32_t q_dim;              /* d: 2|3 for a point, <= MPB_MAX_DOF for a chain */
+    int32_t ws_dim;             /* 2 | 3 */
+    int32_t n_spheres;          /* collision spheres on the robot (1 for a point) */
+    const float* fixed_tf;      /* [q_dim,3,4] parent->joint transforms      (chain) */
+    const int32_t* sphere_link; /* [n_spheres] ascending joint index of the carrying frame (chain) */
+    const float* sphere_off;    /* [n_spheres,3] centre in that frame        (chain) */
+    const float* sphere_r;      /* [n_spheres] radii */
+} mpb_robot_desc;
+
+/* Replaces one entry of `collision_fields` (mp_baselines/planners/gpmp2.py:72-79), i.e. the
+ * object whose compute_cost() FieldFactor calls (costs/factors/field_factor.py:39):
+ * a union of sphere and axis-aligned box primitives, cost = sum over robot spheres of
+ * relu(radius + cutoff_margin - sdf(centre)). */
+typedef struct mpb_field_desc {
+    int32_t n_spheres;
+    int32_t n_boxes;
+    const float* spheres;       /* [n_spheres,4] cx,cy,cz,r          (cz = 0 in 2-D) */
+    const float* boxes;         /* [n_boxes,8]  cx,cy,cz,0,hx,hy,hz,0 (hz = +inf in 2-D) */
+    float cutoff_margin;
+    float weight;               /* CostComposite weight * 1/sigma_coll^2 is applied as
+                                   weight * (inv_sigma2 * sum_t err)  (cost_functions.py:85,185-186) */
+    float inv_sigma2;
+} mpb_field_desc;
+
+/* Replaces CostGP + CostGoalPrior parameters (cost_functions.py:234-289,488-536;
+ * gp_factor.py:34-50; unary_factor.py:19).  All scalars are the fp32 values the reference
+ * stores in its K / Q_inv matrices. */
+typedef struct mpb_gp_desc {
+    int32_t enabled;            /* 0: no start/GP/goal terms (STOMP / CHOMP / MPPI cost objects) */
+    int32_t has_goal;
+    float dt;
+    float k_start;              /* 1/sigma_start^2 */
+    float k_goal;               /* 1/sigma_goal_prior^2 */
+    float q11, q12, q22;        /* Q^-1 = [[q11 I, q12 I],[q12 I, q22 I]] */
+    float w_gp, w_goal;         /* CostComposite weights (1.0 in build_gpmp2_cost_composite) */
+    const float* start_state;   /* [D] start with zero velocity (gpmp2.py:50) */
+    const float* goal_state;    /* [D] goal with zero velocity  (gpmp2.py:60-61), or NULL */
+} mpb_gp_desc;
+
+const char* mpb_last_error(void);
+int mpb_version(void);
+
+/* x[p,s,:] = mu[p,:] + L @ eps[s,p,:]
+ * Replaces MultiMPPrior.sample (costs/factors/mp_priors_multi.py:253-256) =
+ * torch MultivariateNormal.rsample with scale_tril L; L is lower-triangular [M,M].
+ * eps is laid out as torch draws it: [S,P,M]. */
+int mpb_sample_gp(const float* L, const float* mu, const float* eps, float* x,
+                  int P, int S, int M, void* stream);
+
+/* STOMP noise: x[p,s,h,j] = mu[p,h,j] + (h==0||h==H-1 ? 0 : sum_k L_R[h,k] eps[s,j,p,k])
+ * Replaces STOMP.sample (mp_baselines/planners/stomp.py:97-108); eps is [S,D,P,H]. */
+int mpb_sample_stomp(const float* L_R, const float* mu, const float* eps, float* x,
+                     int P, int S, int H, int D, void* stream);
+
+/* y[p,:] = Sigma_inv @ mu[p,:] for a banded (block-tridiagonal) Sigma_inv [M,M] with
+ * half bandwidth half_bw (= 2D-1).  Accumulated in fp64.  First half of the
+ * importance-sampling term of StochGPMP._get_costs (stoch_gpmp.py:239-241). */
+int mpb_prior_matvec(const float* Sigma_inv, const float* mu, float* y,
+                     int P, int M, int half_bw, void* stream);
+
+/* Fused FK + collision + GP/goal cost (+ importance-sampling term) of B trajectories.
+ * Replaces CostComposite.eval over {CostGP, CostGoalPrior, CostCollision...}
+ * (cost_functions.py:70-87,171-189,271-289,523-536), Cost.get_q_pos_vel_and_fk_map (:41-53),
+ * FieldFactor.get_error (field_factor.py:17-39) and, when is_vec != NULL, the second half of
+ * the IS term: cost[b] += is_scale * dot(x[b], is_vec[b / samples_per_particle]).
+ *   x          [B,H,D]
+ *   cost       [B]               total
+ *   terms      [n_terms,B]|NULL  individual weighted terms: (start+GP), goal (if has_goal), one per field
+ *   free_flag  [B]|NULL          1 iff every collision hinge term of the trajectory is exactly 0
+ */
+int mpb_cost_eval(const float* x, int B, int H,
+                  const mpb_robot_desc* robot,
+                  const mpb_field_desc* fields, int n_fields,
+                  const mpb_gp_desc* gp,
+                  const float* is_vec, int samples_per_particle, float is_scale,
+                  float* cost, float* terms, uint8_t* free_flag, void* stream);
+
+/* w = softmax(-cost/temp) over samples; g = sum_s w (x_s - mu); mu += step * (SigmaR @ g if
+ * SigmaR else g).  Replaces StochGPMP._update_distribution (stoch_gpmp.py:267-279) and
+ * STOMP._update_distribution (stomp.py:199-220; SigmaR = inverse(R) [H,H]).
+ *   cost [P,S], x [P,S,H,D], mu [P,H,D] (in place), weights [P,S] out, grad [P,H,D] out|NULL */
+int mpb_softmax_update(const float* cost, const float* x, float* mu, float* weights, float* grad,
+                       float temp, float step, const float* SigmaR,
+                       int P, int S, int H, int D, void* stream);
+
+/* One fused Stoch-GPMP iteration = sample_gp -> prior_matvec -> cost_eval(+IS) -> softmax_update.
+ * Replaces the body of StochGPMP.optimize (stoch_gpmp.py:291-299).
+ * workspace: x [P,S,H,D], cost [P,S], weights [P,S], is_vec [P,M]; free_flag [P*S] may be NULL. */
+int mpb_stoch_gpmp_iter(const float* L, const float* Sigma_inv, const float* eps,
+                        float* mu, float* x, float* cost, float* weights, float* is_vec,
+                        uint8_t* free_flag,
+                        int P, int S, int H,
+                        const mpb_robot_desc* robot,
+                        const mpb_field_desc* fields, int n_fields,
+                        const mpb_gp_desc* gp,
+                        float temp, float step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPB_H_ */

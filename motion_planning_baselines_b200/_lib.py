@@ -1,0 +1,98 @@
+"""ctypes binding of libmpb_b200.so (the C ABI declared in include/mpb.h).
+
+There is NO fallback: if the shared library is missing or a call fails, we raise.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmpb_b200.so')
+
+MPB_MAX_FIELDS = 4
+ROBOT_POINT, ROBOT_CHAIN = 0, 1
+
+
+class MpbError(RuntimeError):
+    pass
+
+
+class RobotDesc(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('q_dim', C.c_int32), ('ws_dim', C.c_int32), ('n_spheres', C.c_int32),
+                ('fixed_tf', C.c_void_p), ('sphere_link', C.c_void_p), ('sphere_off', C.c_void_p),
+                ('sphere_r', C.c_void_p)]
+
+
+class FieldDesc(C.Structure):
+    _fields_ = [('n_spheres', C.c_int32), ('n_boxes', C.c_int32), ('spheres', C.c_void_p), ('boxes', C.c_void_p),
+                ('cutoff_margin', C.c_float), ('weight', C.c_float), ('inv_sigma2', C.c_float)]
+
+
+class GPDesc(C.Structure):
+    _fields_ = [('enabled', C.c_int32), ('has_goal', C.c_int32), ('dt', C.c_float), ('k_start', C.c_float),
+                ('k_goal', C.c_float), ('q11', C.c_float), ('q12', C.c_float), ('q22', C.c_float),
+                ('w_gp', C.c_float), ('w_goal', C.c_float), ('start_state', C.c_void_p), ('goal_state', C.c_void_p)]
+
+
+_lib = None
+
+_vp, _i, _f = C.c_void_p, C.c_int, C.c_float
+_SIGNATURES = {
+    'mpb_last_error': (C.c_char_p, []),
+    'mpb_version': (C.c_int, []),
+    'mpb_sample_gp': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'mpb_sample_stomp': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'mpb_prior_matvec': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    'mpb_cost_eval': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
+                                _vp, _i, _f, _vp, _vp, _vp, _vp]),
+    'mpb_softmax_update': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _vp]),
+    'mpb_stoch_gpmp_iter': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                      C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
+                                      _f, _f, _vp]),
+}
+
+
+def exported_symbols():
+    """Every symbol include/mpb.h declares (checked by the CPU test-suite)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MpbError(f'{LIB_PATH} is missing: run ./build.sh (or __graft_entry__.build()). '
+                           'There is no CPU fallback for the hot path.')
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise MpbError(f'libmpb_b200 error {rc}: {lib().mpb_last_error().decode()}')
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32/int32/uint8 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise MpbError('expected a CUDA tensor: the hot path has no CPU implementation')
+    if not t.is_contiguous():
+        raise MpbError('expected a contiguous tensor')
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_f32(*tensors):
+    for t in tensors:
+        if t is not None and t.dtype != torch.float32:
+            raise MpbError(f'expected float32, got {t.dtype}')

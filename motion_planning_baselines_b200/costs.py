@@ -1,0 +1,193 @@
+"""Cost objects with the reference's names, constructor arguments and call surface
+(mp_baselines/planners/costs/cost_functions.py), evaluated by ONE fused sm_100a kernel
+(mpb_cost_eval, csrc/cost_eval.cu) instead of a chain of eager torch ops.
+
+    Cost.eval(trajs [B,H,D] | [N,B,H,D], **obs) -> [B] (or [N*B])      cost_functions.py:30-35
+    CostComposite(robot, n_support_points, cost_list, weights_cost_l)   cost_functions.py:56-105
+    CostCollision(robot, n_support_points, field=, sigma_coll=)         cost_functions.py:147-189
+    CostGP(robot, n_support_points, start_state, dt, sigma_params)      cost_functions.py:234-289
+    CostGoalPrior(robot, n_support_points, multi_goal_states=, ...)     cost_functions.py:488-536
+    build_gpmp2_cost_composite(...)                                      gpmp2.py:23-89
+
+There is no CPU implementation behind these classes: tensors must live on the CUDA device.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .fields import CollisionField
+
+
+class Cost:
+    def __init__(self, robot, n_support_points, tensor_args=None, **kwargs):
+        self.robot = robot
+        self.n_dof = robot.q_dim
+        self.dim = 2 * self.n_dof
+        self.n_support_points = n_support_points
+        self.tensor_args = tensor_args if tensor_args is not None else robot.tensor_args
+
+    def set_cost_factors(self):
+        pass
+
+    def __call__(self, trajs, **kwargs):
+        return self.eval(trajs, **kwargs)
+
+    def eval(self, trajs, **kwargs):
+        return CostComposite(self.robot, self.n_support_points, [self], tensor_args=self.tensor_args).eval(trajs, **kwargs)
+
+    def get_linear_system(self, trajs, **kwargs):
+        raise NotImplementedError
+
+
+class CostCollision(Cost):
+    def __init__(self, robot, n_support_points, field=None, sigma_coll=None, **kwargs):
+        super().__init__(robot, n_support_points, **kwargs)
+        if field is not None and not isinstance(field, CollisionField):
+            raise _lib.MpbError('CostCollision needs a motion_planning_baselines_b200.CollisionField')
+        self.field = field
+        self.sigma_coll = sigma_coll
+        self.inv_sigma2 = 1. / (sigma_coll ** 2)          # FieldFactor.K (field_factor.py:15)
+
+
+class CostGP(Cost):
+    def __init__(self, robot, n_support_points, start_state, dt, sigma_params, **kwargs):
+        super().__init__(robot, n_support_points, **kwargs)
+        self.start_state = start_state.to(**self.tensor_args).contiguous()
+        assert self.start_state.numel() == self.dim, 'start_state must be [2*dof] (position | zero velocity)'
+        self.dt = dt
+        self.sigma_start = sigma_params['sigma_start']
+        self.sigma_gp = sigma_params['sigma_gp']
+        # fp32 constants exactly as UnaryFactor.K / GPFactor.calc_Q_inv build them
+        one = torch.ones((), dtype=torch.float32)
+        self.k_start = float(one / self.sigma_start ** 2)
+        qc = one / self.sigma_gp ** 2
+        self.q11 = float(12. * (dt ** -3.) * qc)
+        self.q12 = float(-6. * (dt ** -2.) * qc)
+        self.q22 = float(4. * (dt ** -1.) * qc)
+
+
+class CostGoalPrior(Cost):
+    def __init__(self, robot, n_support_points, multi_goal_states=None, num_particles_per_goal=None,
+                 num_samples=None, sigma_goal_prior=None, **kwargs):
+        super().__init__(robot, n_support_points, **kwargs)
+        self.multi_goal_states = multi_goal_states
+        self.num_goals = multi_goal_states.shape[0]
+        if self.num_goals != 1:
+            # the reference reshapes to [num_goals, ...] and breaks for > 1 goal
+            raise NotImplementedError('CostGoalPrior supports a single goal (as the reference effectively does)')
+        self.goal_state = multi_goal_states.reshape(-1)[:self.dim].to(**self.tensor_args).contiguous()
+        self.num_particles_per_goal = num_particles_per_goal
+        self.num_samples = num_samples
+        self.sigma_goal_prior = sigma_goal_prior
+        self.k_goal = float(torch.ones((), dtype=torch.float32) / sigma_goal_prior ** 2)
+
+
+class CostComposite(Cost):
+    def __init__(self, robot, n_support_points, cost_list, weights_cost_l=None, **kwargs):
+        super().__init__(robot, n_support_points, **kwargs)
+        self.cost_l = list(cost_list)
+        self.weight_cost_l = weights_cost_l if weights_cost_l is not None else [1.0] * len(self.cost_l)
+        self._build()
+
+    def _build(self, unit_weights=False):
+        gp = _lib.GPDesc(enabled=0, has_goal=0, w_gp=1.0, w_goal=1.0)
+        fields = []
+        self._keepalive = []
+        order = []                                          # kernel term index of every cost_l entry
+        n_gp = n_goal = 0
+        for cost, w in zip(self.cost_l, self.weight_cost_l):
+            w = 1.0 if unit_weights else float(w)
+            if isinstance(cost, CostGP):
+                assert n_gp == 0, 'one CostGP per composite'
+                n_gp += 1
+                gp.enabled, gp.dt, gp.k_start = 1, cost.dt, cost.k_start
+                gp.q11, gp.q12, gp.q22, gp.w_gp = cost.q11, cost.q12, cost.q22, w
+                gp.start_state = cost.start_state.data_ptr()
+                self._keepalive.append(cost.start_state)
+                order.append(('gp', 0))
+            elif isinstance(cost, CostGoalPrior):
+                assert n_goal == 0, 'one CostGoalPrior per composite'
+                n_goal += 1
+                gp.has_goal, gp.k_goal, gp.w_goal = 1, cost.k_goal, w
+                gp.goal_state = cost.goal_state.data_ptr()
+                self._keepalive.append(cost.goal_state)
+                order.append(('goal', 0))
+            elif isinstance(cost, CostCollision):
+                if cost.field is None:
+                    order.append(('none', 0))
+                    continue
+                order.append(('field', len(fields)))
+                fields.append(cost.field.desc(weight=w, inv_sigma2=cost.inv_sigma2))
+            else:
+                raise NotImplementedError(f'{type(cost).__name__} has no fused implementation yet')
+        if gp.has_goal and not gp.enabled:
+            raise NotImplementedError('CostGoalPrior without CostGP is not supported by the fused kernel')
+        if len(fields) > _lib.MPB_MAX_FIELDS:
+            raise NotImplementedError(f'at most {_lib.MPB_MAX_FIELDS} collision fields per composite')
+        arr = (_lib.FieldDesc * max(1, len(fields)))(*fields)
+        n_head = int(gp.enabled) + int(gp.has_goal)
+        term_index = []
+        for kind, i in order:
+            term_index.append({'gp': 0, 'goal': 1, 'field': n_head + i, 'none': -1}[kind])
+        return gp, arr, len(fields), term_index
+
+    def _flatten(self, trajs):
+        assert trajs.ndim in (3, 4)
+        if trajs.ndim == 4:
+            trajs = trajs.reshape(-1, *trajs.shape[2:])
+        _lib.require_f32(trajs)
+        if trajs.shape[-1] != self.dim or trajs.shape[-2] != self.n_support_points:
+            raise _lib.MpbError(f'trajectories must be [..., {self.n_support_points}, {self.dim}], got {tuple(trajs.shape)}')
+        return trajs.contiguous()
+
+    def eval(self, trajs, trajs_interpolated=None, return_invidual_costs_and_weights=False,
+             is_vec=None, samples_per_particle=1, is_scale=0.0, out=None, free_flag=None, **kwargs):
+        """Reference signature plus optional fused extras (IS term, collision-free flags)."""
+        if trajs_interpolated is not None:
+            raise NotImplementedError('interpolated collision checking is a "next" row (SURVEY.md 8f)')
+        if kwargs.get('obstacle_spheres') is not None:
+            raise NotImplementedError('per-call obstacle_spheres are not supported')
+        x = self._flatten(trajs)
+        B = x.shape[0]
+        gp, fields, nf, term_index = self._build(unit_weights=return_invidual_costs_and_weights)
+        cost = out if out is not None else torch.empty(B, device=x.device, dtype=torch.float32)
+        n_terms = int(gp.enabled) + int(gp.has_goal) + nf
+        terms = torch.empty(n_terms, B, device=x.device, dtype=torch.float32) if return_invidual_costs_and_weights else None
+        _lib.check(_lib.lib().mpb_cost_eval(
+            _lib.ptr(x), B, self.n_support_points, C.byref(self.robot.desc), fields, nf, C.byref(gp),
+            _lib.ptr(is_vec), samples_per_particle, is_scale,
+            _lib.ptr(cost), _lib.ptr(terms), _lib.ptr(free_flag), _lib.stream_ptr()))
+        if return_invidual_costs_and_weights:
+            zero = torch.zeros(B, device=x.device, dtype=torch.float32)
+            return [terms[i] if i >= 0 else zero for i in term_index], self.weight_cost_l
+        return cost
+
+    def collision_free(self, trajs):
+        """bool [B]: every collision hinge term of the trajectory (waypoints 1..H-1) is exactly 0."""
+        x = self._flatten(trajs)
+        flags = torch.empty(x.shape[0], device=x.device, dtype=torch.uint8)
+        self.eval(x, free_flag=flags)
+        return flags.bool()
+
+
+def build_gpmp2_cost_composite(robot=None, n_support_points=None, dt=None, start_state=None, multi_goal_states=None,
+                               num_particles_per_goal=None, collision_fields=None, extra_costs=[],
+                               sigma_start=1e-5, sigma_gp=1e-2, sigma_coll=1e-5, sigma_goal_prior=1e-5,
+                               num_samples: int = 64, tensor_args=None, **kwargs):
+    """Same defaults and wiring as mp_baselines/planners/gpmp2.py:23-89."""
+    cost_func_list = []
+    start_state_zero_vel = torch.cat((start_state, torch.zeros(start_state.nelement(), **tensor_args)))
+    cost_func_list.append(CostGP(robot, n_support_points, start_state_zero_vel, dt,
+                                 dict(sigma_start=sigma_start, sigma_gp=sigma_gp), tensor_args=tensor_args))
+    if multi_goal_states is not None:
+        goal_zero_vel = torch.cat((multi_goal_states, torch.zeros_like(multi_goal_states)), dim=-1).unsqueeze(0)
+        cost_func_list.append(CostGoalPrior(robot, n_support_points, multi_goal_states=goal_zero_vel.reshape(-1, goal_zero_vel.shape[-1]),
+                                            num_particles_per_goal=num_particles_per_goal, num_samples=num_samples,
+                                            sigma_goal_prior=sigma_goal_prior, tensor_args=tensor_args))
+    for field in (collision_fields or []):
+        cost_func_list.append(CostCollision(robot, n_support_points, field=field, sigma_coll=sigma_coll,
+                                            tensor_args=tensor_args))
+    if extra_costs:
+        cost_func_list.extend(extra_costs)
+    return CostComposite(robot, n_support_points, cost_func_list, tensor_args=tensor_args)

@@ -1,0 +1,61 @@
+// C-ABI glue of libmpb_b200.so: error reporting, device queries and the fused iteration drivers.
+#include <cstdarg>
+#include <cstdio>
+
+#include "mpb_common.cuh"
+
+namespace mpb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+        return MPB_ECUDA;
+    }
+    return MPB_OK;
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+}  // namespace mpb
+
+extern "C" const char* mpb_last_error(void) { return mpb::g_err; }
+extern "C" int mpb_version(void) { return 100; }
+
+// One Stoch-GPMP iteration (mp_baselines/planners/stoch_gpmp.py:291-299): K1 -> matvec -> K2 -> K3,
+// all enqueued on `stream` with no host synchronisation.  The prior factor L never changes, so the
+// reference's per-iteration re-factorisation (mp_priors_multi.py:120-123) has no counterpart here.
+extern "C" int mpb_stoch_gpmp_iter(const float* L, const float* Sigma_inv, const float* eps, float* mu, float* x,
+                                   float* cost, float* weights, float* is_vec, uint8_t* free_flag, int P, int S,
+                                   int H, const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
+                                   const mpb_gp_desc* gp, float temp, float step, void* stream) {
+    MPB_REQUIRE(robot, "mpb_stoch_gpmp_iter: robot is null");
+    const int D = 2 * robot->q_dim, M = H * D;
+    int rc = mpb_sample_gp(L, mu, eps, x, P, S, M, stream);
+    if (rc) return rc;
+    rc = mpb_prior_matvec(Sigma_inv, mu, is_vec, P, M, 2 * D - 1, stream);
+    if (rc) return rc;
+    rc = mpb_cost_eval(x, P * S, H, robot, fields, n_fields, gp, is_vec, S, temp, cost, nullptr, free_flag, stream);
+    if (rc) return rc;
+    return mpb_softmax_update(cost, x, mu, weights, nullptr, temp, step, nullptr, P, S, H, D, stream);
+}

@@ -1,0 +1,287 @@
+// K2: fused forward kinematics + collision hinge + GP/start/goal cost (+ importance-sampling dot).
+//
+// Replaces CostComposite.eval over {CostGP, CostGoalPrior, CostCollision...} and everything below it
+// (mp_baselines/planners/costs/cost_functions.py:41-53,70-87,171-189,271-289,523-536;
+// costs/factors/field_factor.py:17-39; gp_factor.py:52-56; unary_factor.py:22-29) and the second
+// half of the IS term of stoch_gpmp.py:239-241.
+//
+// Mapping: one warp per trajectory, lanes over waypoints (t = lane, lane+32, ...).  The trajectory
+// row [H*D] is staged once in shared memory with coalesced 128-bit loads (the GP factor needs the
+// neighbouring waypoint, FK needs the joint vector).  Link frames live in registers; sphere centres
+// are produced in register blocks of G and tested against obstacle primitives broadcast from shared
+// memory (collision.cuh).  Per-trajectory sums are reduced with warp shuffles; nothing but the
+// [B] cost (and optional terms / flags) is written.  Bound: FP32 issue rate.
+#include "collision.cuh"
+
+namespace mpb {
+
+struct CostArgs {
+    const float* x;
+    int B, H, D, d, M;
+    mpb_robot_desc robot;
+    FieldArgs fields;
+    mpb_gp_desc gp;
+    const float* is_vec;
+    int S;
+    float is_scale;
+    float* cost;
+    float* terms;
+    unsigned char* free_flag;
+    unsigned field_off, robot_off, rows_off;   // byte offsets into dynamic shared memory
+    int row_stride;                            // floats
+};
+
+constexpr int kWarps = 8;
+
+template <int G>
+__device__ __forceinline__ void collide_block(const FieldSmem* sf, int nf, const float (&cx)[G], const float (&cy)[G],
+                                              const float (&cz)[G], const float (&rad)[G],
+                                              float (&hs)[MPB_MAX_FIELDS], bool& is_free) {
+#pragma unroll
+    for (int f = 0; f < MPB_MAX_FIELDS; ++f) {
+        if (f < nf) {
+            float b[G];
+#pragma unroll
+            for (int k = 0; k < G; ++k) b[k] = __fadd_rn(rad[k], sf[f].margin);
+            const unsigned cand = cull_block<G>(sf[f], cx, cy, cz, b);
+            const unsigned any = __reduce_or_sync(MPB_FULL_MASK, cand);
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                if (any & (1u << k)) {
+                    const float h = exact_hinge(sf[f], cx[k], cy[k], cz[k], b[k]);
+                    hs[f] = __fadd_rn(hs[f], h);
+                    is_free = is_free && (h == 0.f);
+                }
+            }
+        }
+    }
+}
+
+template <int KIND, int G>
+__global__ void __launch_bounds__(kWarps * 32) cost_eval_kernel(const __grid_constant__ CostArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ FieldSmem s_fields[MPB_MAX_FIELDS];
+    __shared__ RobotSmem s_robot;
+
+    stage_fields(a.fields, smem + a.field_off, s_fields);
+    if (KIND == MPB_ROBOT_CHAIN) stage_robot(a.robot, smem + a.robot_off, &s_robot);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* xs = reinterpret_cast<float*>(smem + a.rows_off) + (size_t)warp * a.row_stride;
+    const int nf = a.fields.n_fields;
+    const int H = a.H, D = a.D, d = a.d, M = a.M;
+    const bool vec_ok = ((M & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+
+    for (int b = blockIdx.x * kWarps + warp; b < a.B; b += gridDim.x * kWarps) {
+        // ---- stage the trajectory row ------------------------------------------------------
+        const float* xb = a.x + (size_t)b * M;
+        if (vec_ok) {
+            const float4* src = reinterpret_cast<const float4*>(xb);
+            float4* dst = reinterpret_cast<float4*>(xs);
+            for (int i = lane; i < (M >> 2); i += 32) dst[i] = __ldg(src + i);
+        } else {
+            for (int i = lane; i < M; i += 32) xs[i] = __ldg(xb + i);
+        }
+        __syncwarp();
+
+        double acc_gp = 0.0, acc_goal = 0.0, acc_is = 0.0;
+        float acc_coll[MPB_MAX_FIELDS];
+#pragma unroll
+        for (int f = 0; f < MPB_MAX_FIELDS; ++f) acc_coll[f] = 0.f;
+        bool is_free = true;
+        const float* isv = a.is_vec ? a.is_vec + (size_t)(b / a.S) * M : nullptr;
+
+        for (int t0 = 0; t0 < H; t0 += 32) {
+            const int t = t0 + lane;
+            const bool valid = t < H;
+            const int tc = valid ? t : H - 1;
+            const float* xt = xs + tc * D;
+
+            // ---- start / GP / goal Mahalanobis terms -------------------------------------
+            if (a.gp.enabled && valid) {
+                if (t == 0) {
+                    float c = 0.f;
+                    for (int k = 0; k < D; ++k) {
+                        const float e = __ldg(a.gp.start_state + k) - xt[k];
+                        c = fmaf(e * a.gp.k_start, e, c);
+                    }
+                    acc_gp += (double)c;
+                }
+                if (t < H - 1) {
+                    const float* xn = xt + D;
+                    float c = 0.f;
+                    for (int k = 0; k < d; ++k) {
+                        const float ep = xn[k] - fmaf(a.gp.dt, xt[d + k], xt[k]);
+                        const float ev = xn[d + k] - xt[d + k];
+                        c = fmaf(fmaf(a.gp.q11, ep, a.gp.q12 * ev), ep, c);
+                        c = fmaf(fmaf(a.gp.q12, ep, a.gp.q22 * ev), ev, c);
+                    }
+                    acc_gp += (double)c;
+                }
+                if (t == H - 1 && a.gp.has_goal) {
+                    float c = 0.f;
+                    for (int k = 0; k < D; ++k) {
+                        const float e = __ldg(a.gp.goal_state + k) - xt[k];
+                        c = fmaf(e * a.gp.k_goal, e, c);
+                    }
+                    acc_goal += (double)c;
+                }
+            }
+            // ---- importance-sampling dot  x . (Sigma^-1 mu_p) ---------------------------
+            if (isv && valid) {
+                const float* yv = isv + t * D;
+                double s = 0.0;
+                for (int k = 0; k < D; ++k) s = fma((double)xt[k], (double)__ldg(yv + k), s);
+                acc_is += s;
+            }
+            // ---- collision (warp-synchronous: every lane takes part, results masked) -------
+            if (nf > 0) {
+                float hs[MPB_MAX_FIELDS];
+#pragma unroll
+                for (int f = 0; f < MPB_MAX_FIELDS; ++f) hs[f] = 0.f;
+                bool wp_free = true;
+                if (KIND == MPB_ROBOT_POINT) {
+                    float cx[1], cy[1], cz[1], rad[1];
+                    cx[0] = xt[0];
+                    cy[0] = xt[1];
+                    cz[0] = (a.robot.ws_dim == 3) ? xt[2] : 0.f;
+                    rad[0] = __ldg(a.robot.sphere_r);
+                    collide_block<1>(s_fields, nf, cx, cy, cz, rad, hs, wp_free);
+                } else {
+                    Frame T;
+                    frame_identity(T);
+                    int cur = -1;
+                    const int ns = s_robot.n_spheres;
+                    for (int s0 = 0; s0 < ns; s0 += G) {
+                        float cx[G], cy[G], cz[G], rad[G];
+#pragma unroll
+                        for (int k = 0; k < G; ++k) {
+                            const int s = s0 + k;
+                            if (s < ns) {
+                                const int l = s_robot.link[s];
+                                while (cur < l) {
+                                    ++cur;
+                                    frame_advance(T, s_robot.fixed_tf + cur * 12, xt[cur]);
+                                }
+                                const float4 o = s_robot.sphere[s];
+                                cx[k] = fmaf(T.r00, o.x, fmaf(T.r01, o.y, fmaf(T.r02, o.z, T.tx)));
+                                cy[k] = fmaf(T.r10, o.x, fmaf(T.r11, o.y, fmaf(T.r12, o.z, T.ty)));
+                                cz[k] = fmaf(T.r20, o.x, fmaf(T.r21, o.y, fmaf(T.r22, o.z, T.tz)));
+                                rad[k] = o.w;
+                            } else {
+                                cx[k] = cy[k] = cz[k] = 1e18f;     // padding slot: never a candidate
+                                rad[k] = 0.f;
+                            }
+                        }
+                        collide_block<G>(s_fields, nf, cx, cy, cz, rad, hs, wp_free);
+                    }
+                }
+                if (valid && t >= 1) {      // waypoint 0 is skipped (cost_functions.py:165-169)
+#pragma unroll
+                    for (int f = 0; f < MPB_MAX_FIELDS; ++f) acc_coll[f] += hs[f];
+                    is_free = is_free && wp_free;
+                }
+            }
+        }
+
+        // ---- per-trajectory reductions ------------------------------------------------------
+        float total = 0.f;
+        int term = 0;
+        if (a.gp.enabled) {
+            const float c0 = a.gp.w_gp * (float)warp_sum(acc_gp);
+            total += c0;
+            if (a.terms && lane == 0) a.terms[(size_t)term * a.B + b] = c0;
+            ++term;
+            if (a.gp.has_goal) {
+                const float c1 = a.gp.w_goal * (float)warp_sum(acc_goal);
+                total += c1;
+                if (a.terms && lane == 0) a.terms[(size_t)term * a.B + b] = c1;
+                ++term;
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < MPB_MAX_FIELDS; ++f) {
+            if (f < nf) {
+                const float e = (float)warp_sum((double)acc_coll[f]);
+                const float c = s_fields[f].weight * (s_fields[f].inv_sigma2 * e);
+                total += c;
+                if (a.terms && lane == 0) a.terms[(size_t)term * a.B + b] = c;
+                ++term;
+            }
+        }
+        if (isv) total += a.is_scale * (float)warp_sum(acc_is);
+        const int all_free = __all_sync(MPB_FULL_MASK, is_free);
+        if (lane == 0) {
+            a.cost[b] = total;
+            if (a.free_flag) a.free_flag[b] = (unsigned char)(all_free ? 1 : 0);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace mpb
+
+extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc* robot,
+                             const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp,
+                             const float* is_vec, int samples_per_particle, float is_scale,
+                             float* cost, float* terms, uint8_t* free_flag, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(x && cost && robot, "mpb_cost_eval: null x/cost/robot");
+    MPB_REQUIRE(B >= 0 && H >= 2, "mpb_cost_eval: need B >= 0 and H >= 2 (got B=%d H=%d)", B, H);
+    MPB_REQUIRE(n_fields >= 0 && n_fields <= MPB_MAX_FIELDS, "mpb_cost_eval: n_fields=%d not in [0,%d]", n_fields, MPB_MAX_FIELDS);
+    MPB_REQUIRE(n_fields == 0 || fields, "mpb_cost_eval: fields is null");
+    MPB_REQUIRE(robot->kind == MPB_ROBOT_POINT || robot->kind == MPB_ROBOT_CHAIN, "mpb_cost_eval: unknown robot kind %d", robot->kind);
+    MPB_REQUIRE(robot->ws_dim == 2 || robot->ws_dim == 3, "mpb_cost_eval: ws_dim must be 2 or 3");
+    if (robot->kind == MPB_ROBOT_POINT)
+        MPB_REQUIRE(robot->q_dim == robot->ws_dim && robot->n_spheres == 1 && robot->sphere_r, "mpb_cost_eval: point robot needs q_dim == ws_dim, one sphere");
+    else
+        MPB_REQUIRE(robot->q_dim >= 1 && robot->q_dim <= MPB_MAX_DOF && robot->ws_dim == 3 && robot->n_spheres >= 1 &&
+                    robot->fixed_tf && robot->sphere_link && robot->sphere_off && robot->sphere_r,
+                    "mpb_cost_eval: chain robot needs 1..%d joints, ws_dim 3 and a sphere table", MPB_MAX_DOF);
+    MPB_REQUIRE(!is_vec || samples_per_particle >= 1, "mpb_cost_eval: samples_per_particle must be >= 1 with is_vec");
+    if (B == 0) return MPB_OK;
+
+    CostArgs a{};
+    a.x = x; a.B = B; a.H = H; a.d = robot->q_dim; a.D = 2 * robot->q_dim; a.M = H * a.D;
+    a.robot = *robot;
+    a.fields.n_fields = n_fields;
+    for (int i = 0; i < n_fields; ++i) {
+        MPB_REQUIRE(fields[i].n_spheres >= 0 && fields[i].n_boxes >= 0 &&
+                    (fields[i].n_spheres == 0 || fields[i].spheres) && (fields[i].n_boxes == 0 || fields[i].boxes),
+                    "mpb_cost_eval: field %d has inconsistent primitive arrays", i);
+        a.fields.f[i] = fields[i];
+    }
+    if (gp && gp->enabled) {
+        MPB_REQUIRE(gp->start_state && (!gp->has_goal || gp->goal_state), "mpb_cost_eval: gp start/goal state is null");
+        a.gp = *gp;
+    } else {
+        a.gp.enabled = 0;
+    }
+    a.is_vec = is_vec; a.S = is_vec ? samples_per_particle : 1; a.is_scale = is_scale;
+    a.cost = cost; a.terms = terms; a.free_flag = free_flag;
+
+    const size_t fb = field_smem_bytes(fields, n_fields);
+    const size_t rb = robot_smem_bytes(*robot);
+    a.row_stride = (a.M + 3) & ~3;
+    a.field_off = 0; a.robot_off = (unsigned)fb; a.rows_off = (unsigned)(fb + rb);
+    const size_t smem = fb + rb + (size_t)kWarps * a.row_stride * sizeof(float);
+    MPB_REQUIRE(smem <= 227 * 1024, "mpb_cost_eval: %zu bytes of shared memory needed (H*D too large or too many primitives)", smem);
+
+    const int blocks_needed = (B + kWarps - 1) / kWarps;
+    const int grid = blocks_needed < sm_count() * 8 ? blocks_needed : sm_count() * 8;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (robot->kind == MPB_ROBOT_POINT) {
+        e = cudaFuncSetAttribute(cost_eval_kernel<MPB_ROBOT_POINT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) cost_eval_kernel<MPB_ROBOT_POINT, 1><<<grid, kWarps * 32, smem, st>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(cost_eval_kernel<MPB_ROBOT_CHAIN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) cost_eval_kernel<MPB_ROBOT_CHAIN, 4><<<grid, kWarps * 32, smem, st>>>(a);
+    }
+    if (e != cudaSuccess) {
+        set_error("mpb_cost_eval: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return MPB_ECUDA;
+    }
+    return check_launch("mpb_cost_eval");
+}

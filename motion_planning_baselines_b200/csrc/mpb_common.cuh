@@ -1,0 +1,42 @@
+// Shared helpers for the sm_100a kernels of libmpb_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math_constants.h>
+
+#include "../../include/mpb.h"
+
+#define MPB_FULL_MASK 0xffffffffu
+
+namespace mpb {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);     // cudaGetLastError() -> MPB_OK / MPB_ECUDA
+int sm_count();                         // SMs of the current device (cached per device)
+
+#define MPB_REQUIRE(cond, ...)                       \
+    do {                                             \
+        if (!(cond)) {                               \
+            mpb::set_error(__VA_ARGS__);             \
+            return MPB_EINVAL;                       \
+        }                                            \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MPB_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MPB_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(MPB_FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_and(int v) { return __all_sync(MPB_FULL_MASK, v); }
+
+}  // namespace mpb

@@ -1,0 +1,223 @@
+// K1 (FP32 SIMT variant): GP-prior sampling  x[p,s,:] = mu[p,:] + L @ eps[s,p,:].
+//
+// Replaces MultiMPPrior.sample (mp_baselines/planners/costs/factors/mp_priors_multi.py:253-256), i.e.
+// torch MultivariateNormal.rsample's broadcast batched mat-vec against a per-particle [P,M,M]
+// scale_tril, by ONE triangular GEMM  X[N,M] = E[N,M] * L^T  (N = P*S rows) that reads the single
+// [M,M] factor: k-tiles above the diagonal are skipped, the epilogue adds mu_p and writes the
+// sample-major reference layout [S,P,M] back as particle-major [P,S,M].
+//
+// 128x128x16 tiles, 256 threads, 8x8 register micro-tile split 4+4 so that the 128-bit shared-memory
+// reads are bank-conflict free; global->shared prefetch is double buffered through registers.
+// Bound: FP32 FMA.  (The tcgen05 3xTF32 variant lives in sample_gp_tc.cu.)
+#include "mpb_common.cuh"
+
+namespace mpb {
+
+constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+
+__global__ void __launch_bounds__(256) sample_gp_simt_kernel(const float* __restrict__ L, const float* __restrict__ mu,
+                                                             const float* __restrict__ eps, float* __restrict__ x,
+                                                             int P, int S, int M) {
+    __shared__ __align__(16) float As[2][BK][BM + PAD];   // eps tile, k-major
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];   // L tile,   k-major
+    const int N = P * S;
+    const int n0 = blockIdx.x * BM, i0 = blockIdx.y * BN;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const bool vec = (M & 3) == 0;
+
+    // each thread moves two 4-float k-segments of A and of B per k-tile
+    int lrow[2], lk[2];
+    const float* asrc[2];
+    const float* bsrc[2];
+    bool aok[2], bok[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int idx = tid * 2 + j;
+        lrow[j] = idx >> 2;
+        lk[j] = (idx & 3) * 4;
+        const int n = n0 + lrow[j];
+        aok[j] = n < N;
+        const int p = aok[j] ? n / S : 0, s = aok[j] ? n - p * S : 0;
+        asrc[j] = eps + ((size_t)s * P + p) * M;
+        const int i = i0 + lrow[j];
+        bok[j] = i < M;
+        bsrc[j] = L + (size_t)(bok[j] ? i : 0) * M;
+    }
+    const int k_end = min(M, i0 + BN);                  // L[i,k] = 0 for k > i
+    const int n_kt = (k_end + BK - 1) / BK;
+
+    float4 ra[2], rb[2];
+    auto gload = [&](int kt) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int k = kt * BK + lk[j];
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+            if (vec) {
+                if (aok[j] && k < M) va = __ldg(reinterpret_cast<const float4*>(asrc[j] + k));
+                if (bok[j] && k < M) vb = __ldg(reinterpret_cast<const float4*>(bsrc[j] + k));
+            } else {
+                float ta[4] = {0.f, 0.f, 0.f, 0.f}, tb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (aok[j] && k + c < M) ta[c] = __ldg(asrc[j] + k + c);
+                    if (bok[j] && k + c < M) tb[c] = __ldg(bsrc[j] + k + c);
+                }
+                va = make_float4(ta[0], ta[1], ta[2], ta[3]);
+                vb = make_float4(tb[0], tb[1], tb[2], tb[3]);
+            }
+            ra[j] = va;
+            rb[j] = vb;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            As[buf][lk[j] + 0][lrow[j]] = ra[j].x; As[buf][lk[j] + 1][lrow[j]] = ra[j].y;
+            As[buf][lk[j] + 2][lrow[j]] = ra[j].z; As[buf][lk[j] + 3][lrow[j]] = ra[j].w;
+            Bs[buf][lk[j] + 0][lrow[j]] = rb[j].x; Bs[buf][lk[j] + 1][lrow[j]] = rb[j].y;
+            Bs[buf][lk[j] + 2][lrow[j]] = rb[j].z; Bs[buf][lk[j] + 3][lrow[j]] = rb[j].w;
+        }
+    };
+
+    float acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < n_kt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < n_kt) gload(kt + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+        }
+        if (kt + 1 < n_kt) {
+            sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    // epilogue: + mu_p, particle-major store
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int n = n0 + (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
+        if (n >= N) continue;
+        const int p = n / S;
+        const float* mrow = mu + (size_t)p * M;
+        float* xrow = x + (size_t)n * M;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = i0 + h * 64 + tx * 4;
+            if (vec && i + 3 < M) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow + i));
+                float4 o;
+                o.x = m4.x + acc[r][h * 4 + 0]; o.y = m4.y + acc[r][h * 4 + 1];
+                o.z = m4.z + acc[r][h * 4 + 2]; o.w = m4.w + acc[r][h * 4 + 3];
+                *reinterpret_cast<float4*>(xrow + i) = o;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (i + c < M) xrow[i + c] = __ldg(mrow + i + c) + acc[r][h * 4 + c];
+            }
+        }
+    }
+}
+
+// STOMP noise: x[p,s,h,j] = mu[p,h,j] + (endpoint ? 0 : sum_{k<=h} L_R[h,k] eps[s,j,p,k])
+// (mp_baselines/planners/stomp.py:97-108).  One CTA stages L_R once and loops over (p,s) pairs.
+__global__ void __launch_bounds__(256) sample_stomp_kernel(const float* __restrict__ LR, const float* __restrict__ mu,
+                                                           const float* __restrict__ eps, float* __restrict__ x,
+                                                           int P, int S, int H, int D) {
+    extern __shared__ __align__(16) float sm[];
+    float* Ls = sm;                         // [H][H+1]
+    float* es = sm + H * (H + 1);           // [D][H+1]
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) Ls[(i / H) * (H + 1) + (i % H)] = LR[i];
+    const int M = H * D;
+    for (int ps = blockIdx.x; ps < P * S; ps += gridDim.x) {
+        const int p = ps / S, s = ps - p * S;
+        __syncthreads();
+        for (int i = threadIdx.x; i < M; i += blockDim.x) {      // i = j*H + k
+            const int j = i / H, k = i - j * H;
+            es[j * (H + 1) + k] = __ldg(eps + (((size_t)s * D + j) * P + p) * H + k);
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < M; o += blockDim.x) {      // o = h*D + j
+            const int h = o / D, j = o - h * D;
+            float acc = 0.f;
+            if (h != 0 && h != H - 1) {
+                const float* lrow = Ls + h * (H + 1);
+                const float* erow = es + j * (H + 1);
+                for (int k = 0; k <= h; ++k) acc = fmaf(lrow[k], erow[k], acc);
+            }
+            x[(size_t)ps * M + o] = __ldg(mu + (size_t)p * M + o) + acc;
+        }
+    }
+}
+
+// y[p,:] = Sigma_inv @ mu[p,:] for banded Sigma_inv, fp64 accumulation.
+__global__ void prior_matvec_kernel(const float* __restrict__ Sinv, const float* __restrict__ mu, float* __restrict__ y,
+                                    int P, int M, int hbw) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P * M) return;
+    const int p = idx / M, i = idx - p * M;
+    const int j0 = max(0, i - hbw), j1 = min(M - 1, i + hbw);
+    const float* row = Sinv + (size_t)i * M;
+    const float* m = mu + (size_t)p * M;
+    double acc = 0.0;
+    for (int j = j0; j <= j1; ++j) acc = fma((double)__ldg(row + j), (double)__ldg(m + j), acc);
+    y[idx] = (float)acc;
+}
+
+}  // namespace mpb
+
+extern "C" int mpb_sample_gp(const float* L, const float* mu, const float* eps, float* x, int P, int S, int M,
+                             void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(L && mu && eps && x, "mpb_sample_gp: null pointer");
+    MPB_REQUIRE(P >= 0 && S >= 0 && M >= 1, "mpb_sample_gp: bad sizes P=%d S=%d M=%d", P, S, M);
+    if (P == 0 || S == 0) return MPB_OK;
+    MPB_REQUIRE((long long)P * S <= 0x7fffffffLL / 2, "mpb_sample_gp: P*S too large");
+    dim3 grid((P * S + BM - 1) / BM, (M + BN - 1) / BN);
+    sample_gp_simt_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, mu, eps, x, P, S, M);
+    return check_launch("mpb_sample_gp");
+}
+
+extern "C" int mpb_sample_stomp(const float* L_R, const float* mu, const float* eps, float* x, int P, int S, int H,
+                                int D, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(L_R && mu && eps && x, "mpb_sample_stomp: null pointer");
+    MPB_REQUIRE(P >= 0 && S >= 0 && H >= 2 && D >= 1, "mpb_sample_stomp: bad sizes");
+    if (P == 0 || S == 0) return MPB_OK;
+    const size_t smem = (size_t)(H + D) * (H + 1) * sizeof(float);
+    MPB_REQUIRE(smem <= 200 * 1024, "mpb_sample_stomp: H=%d too large for shared memory", H);
+    cudaError_t e = cudaFuncSetAttribute(sample_stomp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("mpb_sample_stomp: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+    const long long work = (long long)P * S;
+    const int grid = (int)(work < (long long)sm_count() * 4 ? work : (long long)sm_count() * 4);
+    sample_stomp_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(L_R, mu, eps, x, P, S, H, D);
+    return check_launch("mpb_sample_stomp");
+}
+
+extern "C" int mpb_prior_matvec(const float* Sigma_inv, const float* mu, float* y, int P, int M, int half_bw,
+                                void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(Sigma_inv && mu && y, "mpb_prior_matvec: null pointer");
+    MPB_REQUIRE(P >= 0 && M >= 1 && half_bw >= 0, "mpb_prior_matvec: bad sizes");
+    if (P == 0) return MPB_OK;
+    const int n = P * M;
+    prior_matvec_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(Sigma_inv, mu, y, P, M, half_bw);
+    return check_launch("mpb_prior_matvec");
+}

@@ -1,0 +1,129 @@
+"""GP / unary factors and the GP trajectory prior with the reference's names and signatures
+(mp_baselines/planners/costs/factors/{gp_factor,unary_factor,mp_priors_multi}.py).
+
+Construction is one-off host-side setup: the precision is assembled in fp64
+on the CPU exactly like the reference does, and the sampling factor ``scale_tril`` comes from the
+very routine the reference uses (torch.distributions.MultivariateNormal(precision_matrix=...) on the
+CPU in the working dtype), so that the fused sampler multiplies by bit-identical numbers.  The hot
+part -- drawing samples every iteration -- runs in the mpb_sample_gp kernel, and ``set_mean`` only
+swaps the mean: the factor of an unchanged precision is never recomputed (reference quirk B4).
+"""
+import torch
+import torch.distributions as dist
+
+from . import _lib
+
+_CPU32 = dict(device='cpu', dtype=torch.float32)
+
+
+class UnaryFactor:
+    """K = I / sigma^2, error = mean - x (unary_factor.py:6-32)."""
+
+    def __init__(self, dim, sigma, mean=None, tensor_args=None):
+        self.sigma, self.dim, self.tensor_args = sigma, dim, tensor_args
+        self.mean = torch.zeros(dim, **tensor_args) if mean is None else mean
+        self.K = (torch.eye(dim, **_CPU32) / sigma ** 2).to(**tensor_args)
+
+    def set_mean(self, x):
+        self.mean = x.clone().detach()
+
+
+class GPFactor:
+    """Constant-velocity GP factor: Phi and Q^-1 (gp_factor.py:4-50)."""
+
+    def __init__(self, dim, sigma, d_t, num_factors, tensor_args=None, Q_c_inv=None):
+        self.dim, self.d_t, self.tensor_args = dim, d_t, tensor_args
+        self.state_dim = 2 * dim
+        self.num_factors = num_factors
+        eye = torch.eye(dim, **_CPU32)
+        Qc = eye / sigma ** 2 if Q_c_inv is None else Q_c_inv.to(**_CPU32)
+        a, b, c = 12. * (d_t ** -3.) * Qc, -6. * (d_t ** -2.) * Qc, 4. * (d_t ** -1.) * Qc
+        Q = torch.cat((torch.cat((a, b), dim=-1), torch.cat((b, c), dim=-1)), dim=-2)
+        self.Q_c_inv = Qc.to(**tensor_args)
+        self.Q_inv = Q.unsqueeze(0).to(**tensor_args)           # [1,D,D]; the reference repeats it num_factors times
+        Phi = torch.eye(2 * dim, **_CPU32)
+        Phi[:dim, dim:] = eye * d_t
+        self.phi = Phi.to(**tensor_args)
+
+
+def _precision(num_steps, dt, state_dim, dof, K_s_inv, K_gp_inv, K_g_inv):
+    """Sigma^-1 = A^T Q^-1 A in fp64 on the CPU (mp_priors_multi.py:213-251)."""
+    H, D, M = num_steps + 1, state_dim, state_dim * (num_steps + 1)
+    f64 = dict(device='cpu', dtype=torch.float64)
+    Phi = torch.eye(D, **f64)
+    Phi[:dof, dof:] = torch.eye(dof, **f64) * dt
+    A = torch.eye(M, **f64)
+    A[D:, :-D] -= torch.kron(torch.eye(H - 1, **f64), Phi)
+    blocks = [K_s_inv.to(**f64)] + [K_gp_inv.to(**f64)] * (H - 1)
+    if K_g_inv is not None:
+        tail = torch.zeros(D, M, **f64)
+        tail[:, -D:] = torch.eye(D, **f64)
+        A = torch.cat((A, tail))
+        blocks.append(K_g_inv.to(**f64))
+    return A.t() @ torch.block_diag(*blocks) @ A
+
+
+class MultiMPPrior:
+    """Gaussian trajectory prior N(means, Sigma) with Sigma^-1 block-tridiagonal
+    (mp_priors_multi.py:15-259).  ``sample`` runs on the GPU (csrc/sample_gp.cu)."""
+
+    def __init__(self, num_steps, dt, state_dim, dof, K_s_inv, K_gp_inv, start_state, means=None, K_g_inv=None,
+                 goal_states=None, use_numpy=False, tensor_args=None):
+        self.state_dim, self.dof, self.num_steps = state_dim, dof, num_steps
+        self.M = state_dim * (num_steps + 1)
+        self.tensor_args = tensor_args
+        self.goal_directed = goal_states is not None
+        if means is None:
+            self.num_modes = goal_states.shape[0] if self.goal_directed else 1
+            means = self.get_const_vel_mean(start_state, goal_states, dt, num_steps, dof)
+        else:
+            self.num_modes = means.shape[0]
+        self.means = means.reshape(self.num_modes, -1).to(**tensor_args).contiguous()
+
+        Sinv64 = _precision(num_steps, dt, state_dim, dof, K_s_inv, K_gp_inv, K_g_inv if self.goal_directed else None)
+        Sinv_cpu = Sinv64.to(torch.float32)
+        # the reference's own factorisation routine, once, on the CPU, in the working dtype
+        self.scale_tril = dist.MultivariateNormal(torch.zeros(self.M), precision_matrix=Sinv_cpu).scale_tril \
+            .to(**tensor_args).contiguous()
+        self.Sigma_inv = Sinv_cpu.to(**tensor_args).contiguous()
+
+    @classmethod
+    def const_vel_trajectory(cls, start_state, goal_state, dt, num_steps, dof, set_initial_final_vel_to_zero=True,
+                             tensor_args=None):
+        """Straight line, constant velocity, zero velocity at both ends (mp_priors_multi.py:130-151)."""
+        w = torch.arange(num_steps + 1, **tensor_args).unsqueeze(-1)
+        traj = torch.zeros(num_steps + 1, 2 * dof, **tensor_args)
+        traj[:, :dof] = start_state[:dof] * (num_steps - w) * 1. / num_steps + goal_state[:dof] * w * 1. / num_steps
+        vel = (goal_state[:dof] - start_state[:dof]) / (num_steps * dt)
+        if set_initial_final_vel_to_zero:
+            traj[1:-1, dof:] = vel
+        else:
+            traj[:, dof:] = vel
+        return traj
+
+    def get_const_vel_mean(self, start_state, goal_states, dt, num_steps, dof):
+        if self.goal_directed:
+            return torch.stack([self.const_vel_trajectory(start_state, g, dt, num_steps, dof, tensor_args=self.tensor_args)
+                                for g in goal_states], dim=0)
+        return start_state.repeat(num_steps + 1, 1)
+
+    def get_mean(self, reshape=True):
+        m = self.means.clone().detach()
+        return m.reshape(self.num_modes, self.num_steps + 1, self.state_dim) if reshape else m
+
+    def set_mean(self, means_new):
+        assert means_new.shape == self.means.shape
+        self.means = means_new.clone().detach().contiguous()
+
+    def sample(self, num_samples, eps=None, out=None):
+        """-> [num_modes, num_samples, H, state_dim].  ``eps`` ([S,P,M], the layout torch draws) can be
+        injected for parity runs; otherwise it is drawn on the device."""
+        P, S, M = self.num_modes, num_samples, self.M
+        if eps is None:
+            eps = torch.randn(S, P, M, **self.tensor_args)
+        _lib.require_f32(eps)
+        assert eps.shape == (S, P, M)
+        x = out if out is not None else torch.empty(P, S, M, **self.tensor_args)
+        _lib.check(_lib.lib().mpb_sample_gp(_lib.ptr(self.scale_tril), _lib.ptr(self.means), _lib.ptr(eps.contiguous()),
+                                            _lib.ptr(x), P, S, M, _lib.stream_ptr()))
+        return x.view(P, S, self.num_steps + 1, self.state_dim)

@@ -1,0 +1,200 @@
+"""Stoch-GPMP with the reference's constructor, attributes and return values
+(mp_baselines/planners/stoch_gpmp.py), its iteration body replaced by the fused kernels:
+
+    sample_and_eval        stoch_gpmp.py:244-265  ->  mpb_sample_gp + mpb_prior_matvec + mpb_cost_eval
+    _update_distribution   stoch_gpmp.py:267-279  ->  mpb_softmax_update
+    optimize               stoch_gpmp.py:281-309  ->  mpb_stoch_gpmp_iter per iteration (no host sync)
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from ..costs import build_gpmp2_cost_composite
+from ..factors import GPFactor, MultiMPPrior, UnaryFactor
+from .base import OptimizationPlanner
+
+
+class StochGPMP(OptimizationPlanner):
+
+    def __init__(self, robot=None, n_dof=None, n_support_points=None, num_particles_per_goal=None, opt_iters=None,
+                 dt=None, start_state=None, step_size=1., multi_goal_states=None, initial_particle_means=None,
+                 sigma_start_init=None, sigma_start_sample=None, sigma_goal_init=None, sigma_goal_sample=None,
+                 sigma_gp_init=None, sigma_gp_sample=None, num_samples=2, temperature=1., **kwargs):
+        super().__init__(name='StochGPMP', n_dof=n_dof, n_support_points=n_support_points,
+                         num_particles_per_goal=num_particles_per_goal, opt_iters=opt_iters, dt=dt,
+                         start_state=start_state, initial_particle_means=initial_particle_means,
+                         multi_goal_states=multi_goal_states, sigma_start_init=sigma_start_init,
+                         sigma_goal_init=sigma_goal_init, sigma_gp_init=sigma_gp_init, pos_only=False, **kwargs)
+        self.robot = robot
+        self.goal_directed = multi_goal_states is not None
+        if self.goal_directed and self.num_goals != 1:
+            raise NotImplementedError('Stoch-GPMP is single-goal (the reference cost breaks for > 1 goal, quirk B3)')
+        self.num_samples = num_samples
+        self.step_size = step_size
+        self.temperature = temperature
+        self.sigma_start_sample = sigma_start_sample
+        self.sigma_goal_sample = sigma_goal_sample
+        self.sigma_gp_sample = sigma_gp_sample
+        self._mean = None
+        self._weights = None
+        self._sample_dist = None
+        self.costs = None
+        self.free_flags = None
+
+        self.cost = build_gpmp2_cost_composite(
+            robot=robot, n_support_points=n_support_points, dt=dt, start_state=start_state.to(**self.tensor_args),
+            multi_goal_states=None if multi_goal_states is None else multi_goal_states.to(**self.tensor_args),
+            num_particles_per_goal=num_particles_per_goal, num_samples=num_samples, **kwargs)
+        self.reset(initial_particle_means=initial_particle_means)
+
+    # ------------------------------------------------------------------ setup (one-off, host side)
+    def set_prior_factors(self):
+        D, ta = self.d_state_opt, self.tensor_args
+        self.start_prior_init = UnaryFactor(D, self.sigma_start_init, self.start_state, ta)
+        self.gp_prior_init = GPFactor(self.n_dof, self.sigma_gp_init, self.dt, self.n_support_points - 1, ta)
+        self.multi_goal_prior_init = [UnaryFactor(D, self.sigma_goal_init, g, ta) for g in self.multi_goal_states] \
+            if self.goal_directed else []
+        self.start_prior_sample = UnaryFactor(D, self.sigma_start_sample, self.start_state, ta)
+        self.gp_prior_sample = GPFactor(self.n_dof, self.sigma_gp_sample, self.dt, self.n_support_points - 1, ta)
+        self.multi_goal_prior_sample = [UnaryFactor(D, self.sigma_goal_sample, g, ta) for g in self.multi_goal_states] \
+            if self.goal_directed else []
+
+    def get_prior_dist(self, start_K, gp_K, goal_K, state_init, particle_means=None, goal_states=None):
+        return MultiMPPrior(self.n_support_points - 1, self.dt, 2 * self.n_dof, self.n_dof, start_K, gp_K, state_init,
+                            K_g_inv=goal_K, means=particle_means, goal_states=goal_states, tensor_args=self.tensor_args)
+
+    def const_vel_trajectories(self, start_state, multi_goal_states):
+        H, d = self.n_support_points, self.n_dof
+        w = torch.arange(H, **self.tensor_args).view(1, H, 1)
+        traj = torch.zeros(multi_goal_states.shape[0], self.num_particles_per_goal, H, self.d_state_opt, **self.tensor_args)
+        pos = start_state[:d] * (H - w - 1) / (H - 1) + multi_goal_states[:, None, :d] * w / (H - 1)
+        traj[..., :d] = pos.unsqueeze(1)
+        traj[..., d:] = ((multi_goal_states[:, :d] - start_state[:d]) / (H * self.dt))[:, None, None, :]
+        return traj
+
+    def reset(self, start_state=None, multi_goal_states=None, initial_particle_means=None, eps_init=None):
+        if start_state is not None:
+            self.start_state = start_state.detach().clone().to(**self.tensor_args)
+        if multi_goal_states is not None:
+            self.multi_goal_states = multi_goal_states.detach().clone().to(**self.tensor_args)
+        self.set_prior_factors()
+        goal_K_init = self.multi_goal_prior_init[0].K if self.goal_directed else None
+        goal_K_sample = self.multi_goal_prior_sample[0].K if self.goal_directed else None
+        if initial_particle_means is not None:
+            if isinstance(initial_particle_means, str) and initial_particle_means == 'const_vel':
+                means = self.const_vel_trajectories(self.start_state, self.multi_goal_states)
+            else:
+                means = initial_particle_means.to(**self.tensor_args)
+        else:
+            init = self.get_prior_dist(self.start_prior_init.K, self.gp_prior_init.Q_inv[0], goal_K_init,
+                                       self.start_state, goal_states=self.multi_goal_states)
+            means = init.sample(self.num_particles_per_goal, eps=eps_init)
+            del init
+        self._particle_means = means.flatten(0, 1).contiguous().clone() if means.ndim == 4 else means.contiguous().clone()
+        self._sample_dist = self.get_prior_dist(self.start_prior_sample.K, self.gp_prior_sample.Q_inv[0], goal_K_sample,
+                                                self.start_state, particle_means=self._particle_means,
+                                                goal_states=self.multi_goal_states)
+        self.Sigma_inv = self._sample_dist.Sigma_inv
+        P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
+        ta = self.tensor_args
+        self.state_samples = torch.empty(P, S, H, D, **ta)
+        self.costs = torch.empty(P, S, **ta)
+        self._w_buf = torch.empty(P, S, **ta)
+        self._is_vec = torch.empty(P, H * D, **ta)
+        self.free_flags = torch.empty(P * S, device=ta['device'], dtype=torch.uint8)
+        self.state_samples = self._sample_dist.sample(S, out=self.state_samples.view(P, S, H * D))
+
+    # ------------------------------------------------------------------ hot path
+    def _get_costs(self, **observation):
+        """cost.eval + importance-sampling ratio term (stoch_gpmp.py:235-242) on self.state_samples."""
+        P, S, M = self.num_particles, self.num_samples, self.n_support_points * self.d_state_opt
+        _lib.check(_lib.lib().mpb_prior_matvec(_lib.ptr(self.Sigma_inv), _lib.ptr(self._particle_means),
+                                               _lib.ptr(self._is_vec), P, M, 2 * self.d_state_opt - 1, _lib.stream_ptr()))
+        self.cost.eval(self.state_samples, is_vec=self._is_vec, samples_per_particle=S, is_scale=self.temperature,
+                       out=self.costs.view(-1), free_flag=self.free_flags, **observation)
+        return self.costs
+
+    def sample_and_eval(self, eps=None, **observation):
+        P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
+        self._sample_dist.means = self._particle_means.view(P, -1)
+        self.state_samples = self._sample_dist.sample(S, eps=eps, out=self.state_samples.view(P, S, H * D))
+        costs = self._get_costs(**observation)
+        d = self.n_dof
+        return (self.state_samples[..., -d:], self.state_samples[..., :d],
+                self._particle_means[..., -d:].clone(), self._particle_means[..., :d].clone(), costs)
+
+    def _update_distribution(self, costs, traj_samples):
+        P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
+        grad = torch.empty(P, H, D, **self.tensor_args)
+        _lib.check(_lib.lib().mpb_softmax_update(_lib.ptr(costs.contiguous()), _lib.ptr(traj_samples.contiguous()),
+                                                 _lib.ptr(self._particle_means), _lib.ptr(self._w_buf), _lib.ptr(grad),
+                                                 self.temperature, self.step_size, None, P, S, H, D, _lib.stream_ptr()))
+        self._weights = self._w_buf.view(P, S, 1, 1)
+        self._sample_dist.means = self._particle_means.view(P, -1)
+        return grad
+
+    def optimize(self, opt_iters=None, debug=False, eps=None, **observation):
+        """``eps``: optional injected noise, [opt_iters,S,P,M] or a list of [S,P,M] (parity runs)."""
+        if opt_iters is None:
+            opt_iters = self.opt_iters
+        if observation.get('obstacle_spheres') is not None:
+            raise NotImplementedError('per-call obstacle_spheres are not supported')
+        P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
+        M = H * D
+        gp, fields, nf, _ = self.cost._build()
+        lib = _lib.lib()
+        pos_mean = vel_mean = None
+        for it in range(opt_iters):
+            e = eps[it] if eps is not None else torch.randn(S, P, M, **self.tensor_args)
+            _lib.require_f32(e)
+            assert e.shape == (S, P, M) and e.is_contiguous()
+            if it == opt_iters - 1:     # the reference returns the pre-update particle means of the last iteration
+                pos_mean = self._particle_means[..., :self.n_dof].clone()
+                vel_mean = self._particle_means[..., -self.n_dof:].clone()
+            _lib.check(lib.mpb_stoch_gpmp_iter(
+                _lib.ptr(self._sample_dist.scale_tril), _lib.ptr(self.Sigma_inv), _lib.ptr(e),
+                _lib.ptr(self._particle_means), _lib.ptr(self.state_samples), _lib.ptr(self.costs), _lib.ptr(self._w_buf),
+                _lib.ptr(self._is_vec), _lib.ptr(self.free_flags), P, S, H,
+                C.byref(self.robot.desc), fields, nf, C.byref(gp), self.temperature, self.step_size, _lib.stream_ptr()))
+        self._weights = self._w_buf.view(P, S, 1, 1)
+        self._sample_dist.means = self._particle_means.view(P, -1)
+        self._recent_control_samples = self.state_samples[..., -self.n_dof:]
+        self._recent_state_trajectories = self.state_samples[..., :self.n_dof]
+        self._recent_control_particles = vel_mean
+        self._recent_state_particles = pos_mean
+        self._recent_weights = self._weights
+        return self._get_traj()
+
+    def step_staged(self, eps, events=None):
+        """One iteration as four separate C-ABI calls (same kernels as mpb_stoch_gpmp_iter); ``events`` is an
+        optional list of 5 torch.cuda.Event recorded around the stages (bench.py per-kernel timing)."""
+        P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
+        M = H * D
+        lib, st = _lib.lib(), _lib.stream_ptr()
+        gp, fields, nf, _ = self.cost._build()
+        rec = (lambda i: events[i].record()) if events is not None else (lambda i: None)
+        rec(0)
+        _lib.check(lib.mpb_sample_gp(_lib.ptr(self._sample_dist.scale_tril), _lib.ptr(self._particle_means), _lib.ptr(eps),
+                                     _lib.ptr(self.state_samples), P, S, M, st))
+        rec(1)
+        _lib.check(lib.mpb_prior_matvec(_lib.ptr(self.Sigma_inv), _lib.ptr(self._particle_means), _lib.ptr(self._is_vec),
+                                        P, M, 2 * D - 1, st))
+        rec(2)
+        _lib.check(lib.mpb_cost_eval(_lib.ptr(self.state_samples), P * S, H, C.byref(self.robot.desc), fields, nf,
+                                     C.byref(gp), _lib.ptr(self._is_vec), S, self.temperature, _lib.ptr(self.costs), None,
+                                     _lib.ptr(self.free_flags), st))
+        rec(3)
+        _lib.check(lib.mpb_softmax_update(_lib.ptr(self.costs), _lib.ptr(self.state_samples), _lib.ptr(self._particle_means),
+                                          _lib.ptr(self._w_buf), None, self.temperature, self.step_size, None, P, S, H, D, st))
+        rec(4)
+
+    def get_recent_samples(self):
+        return (self._recent_state_trajectories.detach().clone(), self._recent_state_particles.detach().clone(),
+                self._recent_control_samples.detach().clone(), self._recent_control_particles.detach().clone(),
+                self._recent_weights.detach().clone())
+
+    def sample_trajectories(self, num_samples_per_particle):
+        self._sample_dist.means = self._particle_means.view(self.num_particles, -1)
+        samples = self._sample_dist.sample(num_samples_per_particle)
+        return samples[..., :self.n_dof], samples[..., -self.n_dof:]
