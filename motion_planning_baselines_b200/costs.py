@@ -150,6 +150,8 @@ class CostComposite(Cost):
             raise NotImplementedError('per-call obstacle_spheres are not supported')
         x = self._flatten(trajs)
         B = x.shape[0]
+        if B == 0 and not return_invidual_costs_and_weights:
+            return out if out is not None else torch.empty(0, device=x.device, dtype=torch.float32)
         gp, fields, nf, term_index = self._build(unit_weights=return_invidual_costs_and_weights)
         cost = out if out is not None else torch.empty(B, device=x.device, dtype=torch.float32)
         n_terms = int(gp.enabled) + int(gp.has_goal) + nf

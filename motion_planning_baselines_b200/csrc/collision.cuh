@@ -6,55 +6,60 @@
 //
 // Two passes per robot sphere:
 //   1. cull pass  -- branch-free FMA arithmetic, 8 issue slots per sphere/sphere pair and 9 per
-//      sphere/box pair, obstacle primitives broadcast from shared memory and amortised over a
-//      register block of G robot spheres.  It only decides "could the hinge be non-zero?"
-//      with a conservative slack, so its rounding never reaches the result.
-//   2. exact pass -- only for robot spheres some lane of the warp flagged: every operation is a
-//      separately rounded IEEE op in the oracle's order (__fmul_rn/__fadd_rn/__fsqrt_rn cannot be
-//      contracted into FMAs), which makes hinge values and collision-free flags bit-identical to
-//      the oracle for the same sphere centre.
+//      sphere/box pair, obstacle primitives broadcast from shared memory (LDS.128 + LDS.64) and
+//      amortised over a register block of G robot spheres.  It only decides "could the hinge be
+//      non-zero?" with a conservative slack, so its rounding never reaches the result.
+//   2. exact pass -- only for flagged spheres: every operation is a separately rounded IEEE op in the
+//      oracle's order (__fmul_rn/__fadd_rn/__fsqrt_rn cannot be contracted into FMAs), which makes
+//      hinge values and collision-free flags bit-identical to the oracle for the same sphere centre.
+//      Flagged spheres of a warp are compacted into a shared-memory queue and drained 32 at a time,
+//      so the (expensive, divergent) exact pass always runs with full lanes.
 #pragma once
 #include "mpb_common.cuh"
 
 namespace mpb {
 
-struct FieldSmem {
-    const float4* sph;    // cx, cy, cz, r
-    const float2* sphx;   // -r^2, -2r            (cull pass)
-    const float4* boxc;   // cx, cy, cz, 0
-    const float4* boxh;   // hx, hy, hz, 0        (hz = +inf in 2-D)
+// Byte offsets (from the dynamic shared-memory base) of one staged field + its scalars.
+struct FieldLayout {
+    unsigned sph, sphx, boxc, boxh;   // float4[n_sph], float2[n_sph], float4[n_box], float4[n_box]
     int n_sph, n_box;
-    float margin;
-    float weight, inv_sigma2;
+    float margin, weight, inv_sigma2;
 };
-
-// Bytes of shared memory needed to stage the obstacle primitives of `n` fields.
-inline size_t field_smem_bytes(const mpb_field_desc* f, int n) {
-    size_t b = 0;
-    for (int i = 0; i < n; ++i) b += (size_t)f[i].n_spheres * 24 + (size_t)f[i].n_boxes * 32;
-    return (b + 15) & ~(size_t)15;
-}
 
 struct FieldArgs {              // by-value kernel argument
     int n_fields;
     mpb_field_desc f[MPB_MAX_FIELDS];
+    FieldLayout l[MPB_MAX_FIELDS];
 };
 
-// Cooperative staging by the whole CTA.  `base` must be 16-byte aligned.  Caller syncs afterwards.
-__device__ __forceinline__ void stage_fields(const FieldArgs& fa, unsigned char* base, FieldSmem* out) {
-    unsigned char* p = base;
+// Fills fa.l[] starting at byte offset `base` (16-byte aligned); returns the end offset.
+inline unsigned layout_fields(FieldArgs& fa, unsigned base) {
+    unsigned p = base;
     for (int i = 0; i < fa.n_fields; ++i) {
         const mpb_field_desc& d = fa.f[i];
-        float4* sph = reinterpret_cast<float4*>(p);
-        p += (size_t)d.n_spheres * 16;
-        float4* boxc = reinterpret_cast<float4*>(p);
-        p += (size_t)d.n_boxes * 16;
-        float4* boxh = reinterpret_cast<float4*>(p);
-        p += (size_t)d.n_boxes * 16;
-        float2* sphx = reinterpret_cast<float2*>(p);
-        p += (size_t)d.n_spheres * 8;
+        FieldLayout& l = fa.l[i];
+        l.sph = p;  p += (unsigned)d.n_spheres * 16;
+        l.boxc = p; p += (unsigned)d.n_boxes * 16;
+        l.boxh = p; p += (unsigned)d.n_boxes * 16;
+        l.sphx = p; p += (unsigned)d.n_spheres * 8;
+        p = (p + 15u) & ~15u;
+        l.n_sph = d.n_spheres; l.n_box = d.n_boxes;
+        l.margin = d.cutoff_margin; l.weight = d.weight; l.inv_sigma2 = d.inv_sigma2;
+    }
+    return p;
+}
+
+// Cooperative staging by the whole CTA (caller syncs afterwards).
+__device__ __forceinline__ void stage_fields(const FieldArgs& fa, unsigned char* smem) {
+    for (int i = 0; i < fa.n_fields; ++i) {
+        const mpb_field_desc& d = fa.f[i];
+        const FieldLayout& l = fa.l[i];
+        float4* sph = reinterpret_cast<float4*>(smem + l.sph);
+        float2* sphx = reinterpret_cast<float2*>(smem + l.sphx);
+        float4* boxc = reinterpret_cast<float4*>(smem + l.boxc);
+        float4* boxh = reinterpret_cast<float4*>(smem + l.boxh);
         for (int o = threadIdx.x; o < d.n_spheres; o += blockDim.x) {
-            float4 s = reinterpret_cast<const float4*>(d.spheres)[o];
+            const float4 s = reinterpret_cast<const float4*>(d.spheres)[o];
             sph[o] = s;
             sphx[o] = make_float2(-s.w * s.w, -2.f * s.w);
         }
@@ -62,27 +67,23 @@ __device__ __forceinline__ void stage_fields(const FieldArgs& fa, unsigned char*
             boxc[o] = reinterpret_cast<const float4*>(d.boxes)[2 * o];
             boxh[o] = reinterpret_cast<const float4*>(d.boxes)[2 * o + 1];
         }
-        if (threadIdx.x == 0) {
-            FieldSmem fs;
-            fs.sph = sph; fs.sphx = sphx; fs.boxc = boxc; fs.boxh = boxh;
-            fs.n_sph = d.n_spheres; fs.n_box = d.n_boxes;
-            fs.margin = d.cutoff_margin; fs.weight = d.weight; fs.inv_sigma2 = d.inv_sigma2;
-            out[i] = fs;
-        }
     }
 }
 
 // ---- pass 1: conservative candidate test for a register block of G sphere centres -------------
+// `smem` must be the kernel's extern __shared__ array so that the loads compile to LDS.
 template <int G>
-__device__ __forceinline__ unsigned cull_block(const FieldSmem& f, const float (&cx)[G], const float (&cy)[G],
-                                               const float (&cz)[G], const float (&b)[G]) {
+__device__ __forceinline__ unsigned cull_block(const unsigned char* smem, const FieldLayout& f, const float (&cx)[G],
+                                               const float (&cy)[G], const float (&cz)[G], const float (&b)[G]) {
     float ms[G], mb[G];
 #pragma unroll
     for (int k = 0; k < G; ++k) { ms[k] = CUDART_INF_F; mb[k] = CUDART_INF_F; }
+    const float4* sph = reinterpret_cast<const float4*>(smem + f.sph);
+    const float2* sphx = reinterpret_cast<const float2*>(smem + f.sphx);
 #pragma unroll 2
     for (int o = 0; o < f.n_sph; ++o) {
-        const float4 s = f.sph[o];
-        const float2 e = f.sphx[o];
+        const float4 s = sph[o];
+        const float2 e = sphx[o];
 #pragma unroll
         for (int k = 0; k < G; ++k) {
             const float dx = cx[k] - s.x, dy = cy[k] - s.y, dz = cz[k] - s.z;
@@ -93,10 +94,12 @@ __device__ __forceinline__ unsigned cull_block(const FieldSmem& f, const float (
             ms[k] = fminf(ms[k], a);
         }
     }
+    const float4* boxc = reinterpret_cast<const float4*>(smem + f.boxc);
+    const float4* boxh = reinterpret_cast<const float4*>(smem + f.boxh);
 #pragma unroll 2
     for (int o = 0; o < f.n_box; ++o) {
-        const float4 c = f.boxc[o];
-        const float4 h = f.boxh[o];
+        const float4 c = boxc[o];
+        const float4 h = boxh[o];
 #pragma unroll
         for (int k = 0; k < G; ++k) {
             const float qx = fabsf(cx[k] - c.x) - h.x;
@@ -118,12 +121,13 @@ __device__ __forceinline__ unsigned cull_block(const FieldSmem& f, const float (
 // Returns min over the primitives that can possibly be closer than b (all others have sdf >= b and
 // cannot change relu(b - min sdf)).  If GRAD, also returns the unit gradient of the active primitive.
 template <bool GRAD>
-__device__ __forceinline__ float exact_sdf(const FieldSmem& f, float cx, float cy, float cz, float b,
-                                           float* gx, float* gy, float* gz) {
+__device__ __forceinline__ float exact_sdf(const unsigned char* smem, const FieldLayout& f, float cx, float cy, float cz,
+                                           float b, float* gx, float* gy, float* gz) {
     float best = CUDART_INF_F;
     float bgx = 0.f, bgy = 0.f, bgz = 0.f;
+    const float4* sph = reinterpret_cast<const float4*>(smem + f.sph);
     for (int o = 0; o < f.n_sph; ++o) {
-        const float4 s = f.sph[o];
+        const float4 s = sph[o];
         const float dx = __fsub_rn(cx, s.x), dy = __fsub_rn(cy, s.y), dz = __fsub_rn(cz, s.z);
         const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
         const float t = b + s.w;
@@ -136,9 +140,11 @@ __device__ __forceinline__ float exact_sdf(const FieldSmem& f, float cx, float c
             }
         }
     }
+    const float4* boxc = reinterpret_cast<const float4*>(smem + f.boxc);
+    const float4* boxh = reinterpret_cast<const float4*>(smem + f.boxh);
     for (int o = 0; o < f.n_box; ++o) {
-        const float4 c = f.boxc[o];
-        const float4 h = f.boxh[o];
+        const float4 c = boxc[o];
+        const float4 h = boxh[o];
         const float dx = __fsub_rn(cx, c.x), dy = __fsub_rn(cy, c.y), dz = __fsub_rn(cz, c.z);
         const float qx = __fsub_rn(fabsf(dx), h.x), qy = __fsub_rn(fabsf(dy), h.y), qz = __fsub_rn(fabsf(dz), h.z);
         const float m = fmaxf(fmaxf(qx, qy), qz);
@@ -168,39 +174,39 @@ __device__ __forceinline__ float exact_sdf(const FieldSmem& f, float cx, float c
 }
 
 // hinge of one robot sphere against one field, exact arithmetic.
-__device__ __forceinline__ float exact_hinge(const FieldSmem& f, float cx, float cy, float cz, float b) {
-    const float sd = exact_sdf<false>(f, cx, cy, cz, b, nullptr, nullptr, nullptr);
+__device__ __forceinline__ float exact_hinge(const unsigned char* smem, const FieldLayout& f, float cx, float cy, float cz,
+                                             float b) {
+    const float sd = exact_sdf<false>(smem, f, cx, cy, cz, b, nullptr, nullptr, nullptr);
     return fmaxf(__fsub_rn(b, sd), 0.f);
 }
 
 // ---- robot tables in shared memory ---------------------------------------------------------------
-struct RobotSmem {
-    const float* fixed_tf;     // [dof*12]
-    const float4* sphere;      // [n] ox, oy, oz, radius
-    const int* link;           // [n] ascending
+struct RobotLayout {
+    unsigned sphere;      // float4[n]  ox, oy, oz, radius
+    unsigned tf;          // float[dof*12]
+    unsigned link;        // int[n]     ascending joint index
     int n_spheres, dof;
 };
 
-inline size_t robot_smem_bytes(const mpb_robot_desc& r) {
-    if (r.kind != MPB_ROBOT_CHAIN) return 0;
-    size_t b = (size_t)r.n_spheres * 16 + (size_t)r.q_dim * 48 + (size_t)r.n_spheres * 4;
-    return (b + 15) & ~(size_t)15;
+inline unsigned layout_robot(const mpb_robot_desc& r, RobotLayout& l, unsigned base) {
+    l.n_spheres = r.n_spheres; l.dof = r.q_dim;
+    if (r.kind != MPB_ROBOT_CHAIN) { l.sphere = l.tf = l.link = base; return base; }
+    unsigned p = base;
+    l.sphere = p; p += (unsigned)r.n_spheres * 16;
+    l.tf = p;     p += (unsigned)r.q_dim * 48;
+    l.link = p;   p += (unsigned)r.n_spheres * 4;
+    return (p + 15u) & ~15u;
 }
 
-__device__ __forceinline__ void stage_robot(const mpb_robot_desc& r, unsigned char* base, RobotSmem* out) {
-    float4* sp = reinterpret_cast<float4*>(base);
-    float* tf = reinterpret_cast<float*>(base + (size_t)r.n_spheres * 16);
-    int* lk = reinterpret_cast<int*>(base + (size_t)r.n_spheres * 16 + (size_t)r.q_dim * 48);
+__device__ __forceinline__ void stage_robot(const mpb_robot_desc& r, const RobotLayout& l, unsigned char* smem) {
+    float4* sp = reinterpret_cast<float4*>(smem + l.sphere);
+    float* tf = reinterpret_cast<float*>(smem + l.tf);
+    int* lk = reinterpret_cast<int*>(smem + l.link);
     for (int s = threadIdx.x; s < r.n_spheres; s += blockDim.x) {
         sp[s] = make_float4(r.sphere_off[3 * s], r.sphere_off[3 * s + 1], r.sphere_off[3 * s + 2], r.sphere_r[s]);
         lk[s] = r.sphere_link[s];
     }
     for (int i = threadIdx.x; i < r.q_dim * 12; i += blockDim.x) tf[i] = r.fixed_tf[i];
-    if (threadIdx.x == 0) {
-        RobotSmem rs;
-        rs.fixed_tf = tf; rs.sphere = sp; rs.link = lk; rs.n_spheres = r.n_spheres; rs.dof = r.q_dim;
-        *out = rs;
-    }
 }
 
 // One step of the serial chain:  T <- T * F_j * Rz(q_j)   (oracle/robots.py SerialChainRobot.link_frames)
@@ -213,25 +219,26 @@ __device__ __forceinline__ void frame_identity(Frame& T) {
     T.r20 = 0.f; T.r21 = 0.f; T.r22 = 1.f; T.tx = T.ty = T.tz = 0.f;
 }
 
-__device__ __forceinline__ void frame_advance(Frame& T, const float* F, float q) {
+// F: 12 floats (row-major 3x4) in shared memory; (cs, sn) = cos / sin of the joint angle.
+__device__ __forceinline__ void frame_advance(Frame& T, const float* F, float cs, float sn) {
+    const float4 f0 = *reinterpret_cast<const float4*>(F);
+    const float4 f1 = *reinterpret_cast<const float4*>(F + 4);
+    const float4 f2 = *reinterpret_cast<const float4*>(F + 8);
     // translation: t += R * Ft
-    const float ftx = F[3], fty = F[7], ftz = F[11];
-    T.tx = fmaf(T.r00, ftx, fmaf(T.r01, fty, fmaf(T.r02, ftz, T.tx)));
-    T.ty = fmaf(T.r10, ftx, fmaf(T.r11, fty, fmaf(T.r12, ftz, T.ty)));
-    T.tz = fmaf(T.r20, ftx, fmaf(T.r21, fty, fmaf(T.r22, ftz, T.tz)));
+    T.tx = fmaf(T.r00, f0.w, fmaf(T.r01, f1.w, fmaf(T.r02, f2.w, T.tx)));
+    T.ty = fmaf(T.r10, f0.w, fmaf(T.r11, f1.w, fmaf(T.r12, f2.w, T.ty)));
+    T.tz = fmaf(T.r20, f0.w, fmaf(T.r21, f1.w, fmaf(T.r22, f2.w, T.tz)));
     // rotation: R <- R * Fr
-    const float a00 = fmaf(T.r00, F[0], fmaf(T.r01, F[4], T.r02 * F[8]));
-    const float a01 = fmaf(T.r00, F[1], fmaf(T.r01, F[5], T.r02 * F[9]));
-    const float a02 = fmaf(T.r00, F[2], fmaf(T.r01, F[6], T.r02 * F[10]));
-    const float a10 = fmaf(T.r10, F[0], fmaf(T.r11, F[4], T.r12 * F[8]));
-    const float a11 = fmaf(T.r10, F[1], fmaf(T.r11, F[5], T.r12 * F[9]));
-    const float a12 = fmaf(T.r10, F[2], fmaf(T.r11, F[6], T.r12 * F[10]));
-    const float a20 = fmaf(T.r20, F[0], fmaf(T.r21, F[4], T.r22 * F[8]));
-    const float a21 = fmaf(T.r20, F[1], fmaf(T.r21, F[5], T.r22 * F[9]));
-    const float a22 = fmaf(T.r20, F[2], fmaf(T.r21, F[6], T.r22 * F[10]));
+    const float a00 = fmaf(T.r00, f0.x, fmaf(T.r01, f1.x, T.r02 * f2.x));
+    const float a01 = fmaf(T.r00, f0.y, fmaf(T.r01, f1.y, T.r02 * f2.y));
+    const float a02 = fmaf(T.r00, f0.z, fmaf(T.r01, f1.z, T.r02 * f2.z));
+    const float a10 = fmaf(T.r10, f0.x, fmaf(T.r11, f1.x, T.r12 * f2.x));
+    const float a11 = fmaf(T.r10, f0.y, fmaf(T.r11, f1.y, T.r12 * f2.y));
+    const float a12 = fmaf(T.r10, f0.z, fmaf(T.r11, f1.z, T.r12 * f2.z));
+    const float a20 = fmaf(T.r20, f0.x, fmaf(T.r21, f1.x, T.r22 * f2.x));
+    const float a21 = fmaf(T.r20, f0.y, fmaf(T.r21, f1.y, T.r22 * f2.y));
+    const float a22 = fmaf(T.r20, f0.z, fmaf(T.r21, f1.z, T.r22 * f2.z));
     // joint rotation about local z
-    float sn, cs;
-    sincosf(q, &sn, &cs);
     T.r00 = fmaf(a00, cs, a01 * sn); T.r01 = fmaf(a01, cs, -a00 * sn); T.r02 = a02;
     T.r10 = fmaf(a10, cs, a11 * sn); T.r11 = fmaf(a11, cs, -a10 * sn); T.r12 = a12;
     T.r20 = fmaf(a20, cs, a21 * sn); T.r21 = fmaf(a21, cs, -a20 * sn); T.r22 = a22;

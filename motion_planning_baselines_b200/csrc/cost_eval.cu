@@ -8,17 +8,23 @@
 // Mapping: one warp per trajectory, lanes over waypoints (t = lane, lane+32, ...).  The trajectory
 // row [H*D] is staged once in shared memory with coalesced 128-bit loads (the GP factor needs the
 // neighbouring waypoint, FK needs the joint vector).  Link frames live in registers; sphere centres
-// are produced in register blocks of G and tested against obstacle primitives broadcast from shared
-// memory (collision.cuh).  Per-trajectory sums are reduced with warp shuffles; nothing but the
-// [B] cost (and optional terms / flags) is written.  Bound: FP32 issue rate.
+// are produced in register blocks of G and run through the branch-free cull pass against obstacle
+// primitives broadcast from shared memory (collision.cuh).  Flagged spheres are compacted into a
+// per-warp queue and evaluated exactly 32 at a time.  Per-trajectory sums are reduced with warp
+// shuffles; nothing but the [B] cost (and optional terms / flags) is written.
+// Bound: FP32 issue rate.
 #include "collision.cuh"
 
 namespace mpb {
+
+constexpr int kWarps = 8;
+constexpr int kQCap = 64;            // queue entries per warp (>= 2 * 32)
 
 struct CostArgs {
     const float* x;
     int B, H, D, d, M;
     mpb_robot_desc robot;
+    RobotLayout rl;
     FieldArgs fields;
     mpb_gp_desc gp;
     const float* is_vec;
@@ -27,51 +33,97 @@ struct CostArgs {
     float* cost;
     float* terms;
     unsigned char* free_flag;
-    unsigned field_off, robot_off, rows_off;   // byte offsets into dynamic shared memory
-    int row_stride;                            // floats
+    unsigned rows_off, queue_off;      // byte offsets into dynamic shared memory
+    int row_stride;                    // floats
 };
 
-constexpr int kWarps = 8;
+// Per-warp queue of flagged spheres (structure of arrays in shared memory).
+struct WarpQueue {
+    float* x; float* y; float* z; float* b; int* f;
+    int n;
+};
+
+struct HingeAcc {
+    float h[MPB_MAX_FIELDS];
+    bool all_zero;
+};
+
+// Exact pass over `count` (<= 32) queue entries starting at `first`, one entry per lane.  Deliberately NOT
+// inlined: it is the rare path, and keeping one copy keeps the hot cull loop resident in the instruction cache.
+__device__ __noinline__ void drain(const FieldArgs& fa, WarpQueue q, int first, int count, int lane, HingeAcc& acc) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    if (lane < count) {
+        const int i = first + lane;
+        const int f = q.f[i];
+        const float h = exact_hinge(smem, fa.l[f], q.x[i], q.y[i], q.z[i], q.b[i]);
+        acc.all_zero = acc.all_zero && (h == 0.f);
+#pragma unroll
+        for (int k = 0; k < MPB_MAX_FIELDS; ++k)
+            if (k == f) acc.h[k] += h;
+    }
+    __syncwarp();
+}
+
+// Append the lanes whose `pred` is set; drain a full batch of 32 when available.
+__device__ __forceinline__ void enqueue(const unsigned char* smem, const FieldArgs& fa, WarpQueue& q, bool pred, float cx,
+                                        float cy, float cz, float b, int f, int lane, HingeAcc& acc) {
+    const unsigned bal = __ballot_sync(MPB_FULL_MASK, pred);
+    if (bal == 0u) return;
+    if (pred) {
+        const int pos = q.n + __popc(bal & ((1u << lane) - 1u));
+        q.x[pos] = cx; q.y[pos] = cy; q.z[pos] = cz; q.b[pos] = b; q.f[pos] = f;
+    }
+    q.n += __popc(bal);
+    __syncwarp();
+    if (q.n >= 32) {
+        q.n -= 32;
+        drain(fa, q, q.n, 32, lane, acc);
+    }
+}
 
 template <int G>
-__device__ __forceinline__ void collide_block(const FieldSmem* sf, int nf, const float (&cx)[G], const float (&cy)[G],
-                                              const float (&cz)[G], const float (&rad)[G],
-                                              float (&hs)[MPB_MAX_FIELDS], bool& is_free) {
+__device__ __forceinline__ void collide_block(const unsigned char* smem, const FieldArgs& fa, WarpQueue& q,
+                                              const float (&cx)[G], const float (&cy)[G], const float (&cz)[G],
+                                              const float (&rad)[G], bool active, int lane, HingeAcc& acc) {
+    for (int f = 0; f < fa.n_fields; ++f) {
+        const FieldLayout& fl = fa.l[f];
+        float b[G];
 #pragma unroll
-    for (int f = 0; f < MPB_MAX_FIELDS; ++f) {
-        if (f < nf) {
-            float b[G];
+        for (int k = 0; k < G; ++k) b[k] = __fadd_rn(rad[k], fl.margin);
+        unsigned cand = cull_block<G>(smem, fl, cx, cy, cz, b);
+        if (!active) cand = 0u;
+        const unsigned any = __reduce_or_sync(MPB_FULL_MASK, cand);
+        if (any) {
 #pragma unroll
-            for (int k = 0; k < G; ++k) b[k] = __fadd_rn(rad[k], sf[f].margin);
-            const unsigned cand = cull_block<G>(sf[f], cx, cy, cz, b);
-            const unsigned any = __reduce_or_sync(MPB_FULL_MASK, cand);
-#pragma unroll
-            for (int k = 0; k < G; ++k) {
-                if (any & (1u << k)) {
-                    const float h = exact_hinge(sf[f], cx[k], cy[k], cz[k], b[k]);
-                    hs[f] = __fadd_rn(hs[f], h);
-                    is_free = is_free && (h == 0.f);
-                }
-            }
+            for (int k = 0; k < G; ++k)
+                if (any & (1u << k)) enqueue(smem, fa, q, (cand >> k) & 1u, cx[k], cy[k], cz[k], b[k], f, lane, acc);
         }
     }
 }
 
 template <int KIND, int G>
-__global__ void __launch_bounds__(kWarps * 32) cost_eval_kernel(const __grid_constant__ CostArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, 2) cost_eval_kernel(const __grid_constant__ CostArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ FieldSmem s_fields[MPB_MAX_FIELDS];
-    __shared__ RobotSmem s_robot;
 
-    stage_fields(a.fields, smem + a.field_off, s_fields);
-    if (KIND == MPB_ROBOT_CHAIN) stage_robot(a.robot, smem + a.robot_off, &s_robot);
+    stage_fields(a.fields, smem);
+    if (KIND == MPB_ROBOT_CHAIN) stage_robot(a.robot, a.rl, smem);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* xs = reinterpret_cast<float*>(smem + a.rows_off) + (size_t)warp * a.row_stride;
+    WarpQueue q;
+    {
+        float* qb = reinterpret_cast<float*>(smem + a.queue_off) + (size_t)warp * kQCap * 5;
+        q.x = qb; q.y = qb + kQCap; q.z = qb + 2 * kQCap; q.b = qb + 3 * kQCap;
+        q.f = reinterpret_cast<int*>(qb + 4 * kQCap);
+    }
     const int nf = a.fields.n_fields;
     const int H = a.H, D = a.D, d = a.d, M = a.M;
     const bool vec_ok = ((M & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+    const float4* rsphere = reinterpret_cast<const float4*>(smem + a.rl.sphere);
+    const float* rtf = reinterpret_cast<const float*>(smem + a.rl.tf);
+    const int* rlink = reinterpret_cast<const int*>(smem + a.rl.link);
+    const float point_r = (KIND == MPB_ROBOT_POINT) ? __ldg(a.robot.sphere_r) : 0.f;
 
     for (int b = blockIdx.x * kWarps + warp; b < a.B; b += gridDim.x * kWarps) {
         // ---- stage the trajectory row ------------------------------------------------------
@@ -79,29 +131,33 @@ __global__ void __launch_bounds__(kWarps * 32) cost_eval_kernel(const __grid_con
         if (vec_ok) {
             const float4* src = reinterpret_cast<const float4*>(xb);
             float4* dst = reinterpret_cast<float4*>(xs);
+#pragma unroll 2
             for (int i = lane; i < (M >> 2); i += 32) dst[i] = __ldg(src + i);
         } else {
+#pragma unroll 1
             for (int i = lane; i < M; i += 32) xs[i] = __ldg(xb + i);
         }
         __syncwarp();
 
         double acc_gp = 0.0, acc_goal = 0.0, acc_is = 0.0;
-        float acc_coll[MPB_MAX_FIELDS];
+        HingeAcc hacc;
 #pragma unroll
-        for (int f = 0; f < MPB_MAX_FIELDS; ++f) acc_coll[f] = 0.f;
-        bool is_free = true;
+        for (int f = 0; f < MPB_MAX_FIELDS; ++f) hacc.h[f] = 0.f;
+        hacc.all_zero = true;
+        q.n = 0;
         const float* isv = a.is_vec ? a.is_vec + (size_t)(b / a.S) * M : nullptr;
 
         for (int t0 = 0; t0 < H; t0 += 32) {
             const int t = t0 + lane;
             const bool valid = t < H;
             const int tc = valid ? t : H - 1;
-            const float* xt = xs + tc * D;
+            float* xt = xs + tc * D;
 
             // ---- start / GP / goal Mahalanobis terms -------------------------------------
             if (a.gp.enabled && valid) {
                 if (t == 0) {
                     float c = 0.f;
+#pragma unroll 1
                     for (int k = 0; k < D; ++k) {
                         const float e = __ldg(a.gp.start_state + k) - xt[k];
                         c = fmaf(e * a.gp.k_start, e, c);
@@ -111,6 +167,7 @@ __global__ void __launch_bounds__(kWarps * 32) cost_eval_kernel(const __grid_con
                 if (t < H - 1) {
                     const float* xn = xt + D;
                     float c = 0.f;
+#pragma unroll 1
                     for (int k = 0; k < d; ++k) {
                         const float ep = xn[k] - fmaf(a.gp.dt, xt[d + k], xt[k]);
                         const float ev = xn[d + k] - xt[d + k];
@@ -121,6 +178,7 @@ __global__ void __launch_bounds__(kWarps * 32) cost_eval_kernel(const __grid_con
                 }
                 if (t == H - 1 && a.gp.has_goal) {
                     float c = 0.f;
+#pragma unroll 1
                     for (int k = 0; k < D; ++k) {
                         const float e = __ldg(a.gp.goal_state + k) - xt[k];
                         c = fmaf(e * a.gp.k_goal, e, c);
@@ -132,39 +190,49 @@ __global__ void __launch_bounds__(kWarps * 32) cost_eval_kernel(const __grid_con
             if (isv && valid) {
                 const float* yv = isv + t * D;
                 double s = 0.0;
+#pragma unroll 2
                 for (int k = 0; k < D; ++k) s = fma((double)xt[k], (double)__ldg(yv + k), s);
                 acc_is += s;
             }
             // ---- collision (warp-synchronous: every lane takes part, results masked) -------
             if (nf > 0) {
-                float hs[MPB_MAX_FIELDS];
-#pragma unroll
-                for (int f = 0; f < MPB_MAX_FIELDS; ++f) hs[f] = 0.f;
-                bool wp_free = true;
+                const bool active = valid && t >= 1;    // waypoint 0 is skipped (cost_functions.py:165-169)
                 if (KIND == MPB_ROBOT_POINT) {
                     float cx[1], cy[1], cz[1], rad[1];
                     cx[0] = xt[0];
                     cy[0] = xt[1];
                     cz[0] = (a.robot.ws_dim == 3) ? xt[2] : 0.f;
-                    rad[0] = __ldg(a.robot.sphere_r);
-                    collide_block<1>(s_fields, nf, cx, cy, cz, rad, hs, wp_free);
+                    rad[0] = point_r;
+                    collide_block<1>(smem, a.fields, q, cx, cy, cz, rad, active, lane, hacc);
                 } else {
+                    // every neighbour has consumed this batch of rows: turn (q | qdot) into (cos q | sin q) in place
+                    __syncwarp();
+                    if (valid) {
+#pragma unroll 1
+                        for (int j = 0; j < d; ++j) {
+                            float sn, cs;
+                            sincosf(xt[j], &sn, &cs);
+                            xt[j] = cs;
+                            xt[d + j] = sn;
+                        }
+                    }
+                    __syncwarp();
                     Frame T;
                     frame_identity(T);
                     int cur = -1;
-                    const int ns = s_robot.n_spheres;
+                    const int ns = a.rl.n_spheres;
                     for (int s0 = 0; s0 < ns; s0 += G) {
                         float cx[G], cy[G], cz[G], rad[G];
 #pragma unroll
                         for (int k = 0; k < G; ++k) {
                             const int s = s0 + k;
                             if (s < ns) {
-                                const int l = s_robot.link[s];
+                                const int l = rlink[s];
                                 while (cur < l) {
                                     ++cur;
-                                    frame_advance(T, s_robot.fixed_tf + cur * 12, xt[cur]);
+                                    frame_advance(T, rtf + cur * 12, xt[cur], xt[d + cur]);
                                 }
-                                const float4 o = s_robot.sphere[s];
+                                const float4 o = rsphere[s];
                                 cx[k] = fmaf(T.r00, o.x, fmaf(T.r01, o.y, fmaf(T.r02, o.z, T.tx)));
                                 cy[k] = fmaf(T.r10, o.x, fmaf(T.r11, o.y, fmaf(T.r12, o.z, T.ty)));
                                 cz[k] = fmaf(T.r20, o.x, fmaf(T.r21, o.y, fmaf(T.r22, o.z, T.tz)));
@@ -174,15 +242,14 @@ __global__ void __launch_bounds__(kWarps * 32) cost_eval_kernel(const __grid_con
                                 rad[k] = 0.f;
                             }
                         }
-                        collide_block<G>(s_fields, nf, cx, cy, cz, rad, hs, wp_free);
+                        collide_block<G>(smem, a.fields, q, cx, cy, cz, rad, active, lane, hacc);
                     }
                 }
-                if (valid && t >= 1) {      // waypoint 0 is skipped (cost_functions.py:165-169)
-#pragma unroll
-                    for (int f = 0; f < MPB_MAX_FIELDS; ++f) acc_coll[f] += hs[f];
-                    is_free = is_free && wp_free;
-                }
             }
+        }
+        if (q.n > 0) {
+            drain(a.fields, q, 0, q.n, lane, hacc);
+            q.n = 0;
         }
 
         // ---- per-trajectory reductions ------------------------------------------------------
@@ -203,21 +270,32 @@ __global__ void __launch_bounds__(kWarps * 32) cost_eval_kernel(const __grid_con
 #pragma unroll
         for (int f = 0; f < MPB_MAX_FIELDS; ++f) {
             if (f < nf) {
-                const float e = (float)warp_sum((double)acc_coll[f]);
-                const float c = s_fields[f].weight * (s_fields[f].inv_sigma2 * e);
+                const float e = (float)warp_sum((double)hacc.h[f]);
+                const float c = a.fields.l[f].weight * (a.fields.l[f].inv_sigma2 * e);
                 total += c;
                 if (a.terms && lane == 0) a.terms[(size_t)term * a.B + b] = c;
                 ++term;
             }
         }
         if (isv) total += a.is_scale * (float)warp_sum(acc_is);
-        const int all_free = __all_sync(MPB_FULL_MASK, is_free);
+        const int all_free = __all_sync(MPB_FULL_MASK, hacc.all_zero);
         if (lane == 0) {
             a.cost[b] = total;
             if (a.free_flag) a.free_flag[b] = (unsigned char)(all_free ? 1 : 0);
         }
         __syncwarp();
     }
+}
+
+template <int KIND, int G>
+static cudaError_t launch(const CostArgs& a, int grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(cost_eval_kernel<KIND, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(cost_eval_kernel<KIND, G>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    cost_eval_kernel<KIND, G><<<grid, kWarps * 32, smem, st>>>(a);
+    return cudaSuccess;
 }
 
 }  // namespace mpb
@@ -227,8 +305,10 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
                              const float* is_vec, int samples_per_particle, float is_scale,
                              float* cost, float* terms, uint8_t* free_flag, void* stream) {
     using namespace mpb;
+    MPB_REQUIRE(B >= 0, "mpb_cost_eval: negative batch size %d", B);
+    if (B == 0) return MPB_OK;
     MPB_REQUIRE(x && cost && robot, "mpb_cost_eval: null x/cost/robot");
-    MPB_REQUIRE(B >= 0 && H >= 2, "mpb_cost_eval: need B >= 0 and H >= 2 (got B=%d H=%d)", B, H);
+    MPB_REQUIRE(H >= 2, "mpb_cost_eval: need B >= 0 and H >= 2 (got B=%d H=%d)", B, H);
     MPB_REQUIRE(n_fields >= 0 && n_fields <= MPB_MAX_FIELDS, "mpb_cost_eval: n_fields=%d not in [0,%d]", n_fields, MPB_MAX_FIELDS);
     MPB_REQUIRE(n_fields == 0 || fields, "mpb_cost_eval: fields is null");
     MPB_REQUIRE(robot->kind == MPB_ROBOT_POINT || robot->kind == MPB_ROBOT_CHAIN, "mpb_cost_eval: unknown robot kind %d", robot->kind);
@@ -240,7 +320,6 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
                     robot->fixed_tf && robot->sphere_link && robot->sphere_off && robot->sphere_r,
                     "mpb_cost_eval: chain robot needs 1..%d joints, ws_dim 3 and a sphere table", MPB_MAX_DOF);
     MPB_REQUIRE(!is_vec || samples_per_particle >= 1, "mpb_cost_eval: samples_per_particle must be >= 1 with is_vec");
-    if (B == 0) return MPB_OK;
 
     CostArgs a{};
     a.x = x; a.B = B; a.H = H; a.d = robot->q_dim; a.D = 2 * robot->q_dim; a.M = H * a.D;
@@ -261,24 +340,21 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
     a.is_vec = is_vec; a.S = is_vec ? samples_per_particle : 1; a.is_scale = is_scale;
     a.cost = cost; a.terms = terms; a.free_flag = free_flag;
 
-    const size_t fb = field_smem_bytes(fields, n_fields);
-    const size_t rb = robot_smem_bytes(*robot);
+    unsigned off = layout_fields(a.fields, 0);
+    off = layout_robot(*robot, a.rl, off);
     a.row_stride = (a.M + 3) & ~3;
-    a.field_off = 0; a.robot_off = (unsigned)fb; a.rows_off = (unsigned)(fb + rb);
-    const size_t smem = fb + rb + (size_t)kWarps * a.row_stride * sizeof(float);
+    a.rows_off = off;
+    off += (unsigned)(kWarps * a.row_stride * sizeof(float));
+    a.queue_off = off;
+    off += (unsigned)(kWarps * kQCap * 5 * sizeof(float));
+    const size_t smem = off;
     MPB_REQUIRE(smem <= 227 * 1024, "mpb_cost_eval: %zu bytes of shared memory needed (H*D too large or too many primitives)", smem);
 
     const int blocks_needed = (B + kWarps - 1) / kWarps;
     const int grid = blocks_needed < sm_count() * 8 ? blocks_needed : sm_count() * 8;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e;
-    if (robot->kind == MPB_ROBOT_POINT) {
-        e = cudaFuncSetAttribute(cost_eval_kernel<MPB_ROBOT_POINT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) cost_eval_kernel<MPB_ROBOT_POINT, 1><<<grid, kWarps * 32, smem, st>>>(a);
-    } else {
-        e = cudaFuncSetAttribute(cost_eval_kernel<MPB_ROBOT_CHAIN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) cost_eval_kernel<MPB_ROBOT_CHAIN, 4><<<grid, kWarps * 32, smem, st>>>(a);
-    }
+    cudaError_t e = (robot->kind == MPB_ROBOT_POINT) ? launch<MPB_ROBOT_POINT, 1>(a, grid, smem, st)
+                                                     : launch<MPB_ROBOT_CHAIN, 4>(a, grid, smem, st);
     if (e != cudaSuccess) {
         set_error("mpb_cost_eval: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         return MPB_ECUDA;
