@@ -117,6 +117,124 @@ __device__ __forceinline__ unsigned cull_block(const unsigned char* smem, const 
     return cand;
 }
 
+// Same test restricted to the primitives named in an index list (the output of the per-link broad phase).
+template <int G>
+__device__ __forceinline__ unsigned cull_list(const unsigned char* smem, const FieldLayout& f, const unsigned short* ls,
+                                              int n_ls, const unsigned short* lb, int n_lb, const float (&cx)[G],
+                                              const float (&cy)[G], const float (&cz)[G], const float (&b)[G]) {
+    float ms[G], mb[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) { ms[k] = CUDART_INF_F; mb[k] = CUDART_INF_F; }
+    const float4* sph = reinterpret_cast<const float4*>(smem + f.sph);
+    const float2* sphx = reinterpret_cast<const float2*>(smem + f.sphx);
+#pragma unroll 1
+    for (int i = 0; i < n_ls; ++i) {
+        const int o = ls[i];
+        const float4 s = sph[o];
+        const float2 e = sphx[o];
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const float dx = cx[k] - s.x, dy = cy[k] - s.y, dz = cz[k] - s.z;
+            float a = fmaf(dx, dx, e.x);
+            a = fmaf(dy, dy, a);
+            a = fmaf(dz, dz, a);
+            a = fmaf(e.y, b[k], a);
+            ms[k] = fminf(ms[k], a);
+        }
+    }
+    const float4* boxc = reinterpret_cast<const float4*>(smem + f.boxc);
+    const float4* boxh = reinterpret_cast<const float4*>(smem + f.boxh);
+#pragma unroll 1
+    for (int i = 0; i < n_lb; ++i) {
+        const int o = lb[i];
+        const float4 c = boxc[o];
+        const float4 h = boxh[o];
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const float qx = fabsf(cx[k] - c.x) - h.x;
+            const float qy = fabsf(cy[k] - c.y) - h.y;
+            const float qz = fabsf(cz[k] - c.z) - h.z;
+            mb[k] = fminf(mb[k], fmaxf(fmaxf(qx, qy), qz));
+        }
+    }
+    unsigned cand = 0;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const bool c = (ms[k] < fmaf(b[k] * b[k], 1.0001f, 1e-6f)) || (mb[k] < fmaf(fabsf(b[k]), 1e-5f, b[k] + 1e-6f));
+        cand |= (c ? 1u : 0u) << k;
+    }
+    return cand;
+}
+
+// Order-preserving float <-> uint map so that REDUX.MIN/MAX (integer only) can reduce floats in one instruction.
+__device__ __forceinline__ unsigned f2ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ float warp_min_f(float f) { return ord2f(__reduce_min_sync(MPB_FULL_MASK, f2ord(f))); }
+__device__ __forceinline__ float warp_max_f(float f) { return ord2f(__reduce_max_sync(MPB_FULL_MASK, f2ord(f))); }
+
+// Warp-cooperative broad phase for one link: which primitives of field f can touch ANY collision sphere of
+// the link for ANY lane (= waypoint) of the warp?
+//   1. the lanes' bounding-sphere centres (bx,by,bz) are reduced to one axis-aligned box [lo,hi] (6 REDUX);
+//   2. lane o tests primitive o against that box inflated by Rm = link bounding radius + field margin, so a
+//      whole chunk of 32 primitives costs one pass; survivors are compacted into index lists by ballot.
+// Conservative: a robot sphere s of the link with a non-zero hinge against primitive o has
+// |c_s - o| < r_s + margin + r_o, hence dist(bc, o) < R + margin + r_o (triangle inequality; box SDFs are
+// 1-Lipschitz) and bc lies in [lo,hi], so dist([lo,hi], o) < R + margin + r_o: a primitive rejected here
+// contributes exactly 0 for every sphere of the link at every waypoint of the warp.
+// The caller issues __syncwarp() before reading the lists.
+__device__ __forceinline__ void broad_phase(const unsigned char* smem, const FieldLayout& f, float bx, float by, float bz,
+                                            float Rm, bool active, int lane, unsigned short* ls, int& n_ls,
+                                            unsigned short* lb, int& n_lb) {
+    const float lox = warp_min_f(active ? bx : CUDART_INF_F), hix = warp_max_f(active ? bx : -CUDART_INF_F);
+    const float loy = warp_min_f(active ? by : CUDART_INF_F), hiy = warp_max_f(active ? by : -CUDART_INF_F);
+    const float loz = warp_min_f(active ? bz : CUDART_INF_F), hiz = warp_max_f(active ? bz : -CUDART_INF_F);
+    const unsigned lt = (1u << lane) - 1u;
+    const float4* sph = reinterpret_cast<const float4*>(smem + f.sph);
+    n_ls = 0;
+#pragma unroll 1
+    for (int o0 = 0; o0 < f.n_sph; o0 += 32) {
+        const int o = o0 + lane;
+        bool near = false;
+        if (o < f.n_sph) {
+            const float4 s = sph[o];
+            const float dx = fmaxf(fmaxf(lox - s.x, s.x - hix), 0.f);
+            const float dy = fmaxf(fmaxf(loy - s.y, s.y - hiy), 0.f);
+            const float dz = fmaxf(fmaxf(loz - s.z, s.z - hiz), 0.f);
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const float t = Rm + s.w;
+            near = d2 < fmaf(t * t, 1.001f, 1e-5f);
+        }
+        const unsigned m = __ballot_sync(MPB_FULL_MASK, near);
+        if (near) ls[n_ls + __popc(m & lt)] = (unsigned short)o;
+        n_ls += __popc(m);
+    }
+    const float4* boxc = reinterpret_cast<const float4*>(smem + f.boxc);
+    const float4* boxh = reinterpret_cast<const float4*>(smem + f.boxh);
+    n_lb = 0;
+    const float tb = fmaf(fabsf(Rm), 1e-3f, Rm + 1e-5f);
+#pragma unroll 1
+    for (int o0 = 0; o0 < f.n_box; o0 += 32) {
+        const int o = o0 + lane;
+        bool near = false;
+        if (o < f.n_box) {
+            const float4 c = boxc[o];
+            const float4 h = boxh[o];
+            const float gx = fmaxf(lox - (c.x + h.x), (c.x - h.x) - hix);     // gap between the two boxes per axis
+            const float gy = fmaxf(loy - (c.y + h.y), (c.y - h.y) - hiy);
+            const float gz = fmaxf(loz - (c.z + h.z), (c.z - h.z) - hiz);
+            near = fmaxf(fmaxf(gx, gy), gz) < tb;
+        }
+        const unsigned m = __ballot_sync(MPB_FULL_MASK, near);
+        if (near) lb[n_lb + __popc(m & lt)] = (unsigned short)o;
+        n_lb += __popc(m);
+    }
+}
+
 // ---- pass 2: exact signed distance in the oracle's operation order -----------------------------
 // Returns min over the primitives that can possibly be closer than b (all others have sdf >= b and
 // cannot change relu(b - min sdf)).  If GRAD, also returns the unit gradient of the active primitive.
@@ -185,16 +303,20 @@ struct RobotLayout {
     unsigned sphere;      // float4[n]  ox, oy, oz, radius
     unsigned tf;          // float[dof*12]
     unsigned link;        // int[n]     ascending joint index
+    unsigned bound;       // float4[dof] bounding sphere of each link's collision spheres (link frame): mx,my,mz,R
+    unsigned link_end;    // int[dof]   one past the last sphere of each link
     int n_spheres, dof;
 };
 
 inline unsigned layout_robot(const mpb_robot_desc& r, RobotLayout& l, unsigned base) {
     l.n_spheres = r.n_spheres; l.dof = r.q_dim;
-    if (r.kind != MPB_ROBOT_CHAIN) { l.sphere = l.tf = l.link = base; return base; }
+    if (r.kind != MPB_ROBOT_CHAIN) { l.sphere = l.tf = l.link = l.bound = l.link_end = base; return base; }
     unsigned p = base;
     l.sphere = p; p += (unsigned)r.n_spheres * 16;
     l.tf = p;     p += (unsigned)r.q_dim * 48;
+    l.bound = p;  p += (unsigned)r.q_dim * 16;
     l.link = p;   p += (unsigned)r.n_spheres * 4;
+    l.link_end = p; p += (unsigned)r.q_dim * 4;
     return (p + 15u) & ~15u;
 }
 
@@ -207,6 +329,28 @@ __device__ __forceinline__ void stage_robot(const mpb_robot_desc& r, const Robot
         lk[s] = r.sphere_link[s];
     }
     for (int i = threadIdx.x; i < r.q_dim * 12; i += blockDim.x) tf[i] = r.fixed_tf[i];
+    // per-link bounding spheres straight from global memory (tiny; one thread per link)
+    if ((int)threadIdx.x < r.q_dim) {
+        const int j = threadIdx.x;
+        float mx = 0.f, my = 0.f, mz = 0.f;
+        int n = 0, end = 0;
+        for (int s = 0; s < r.n_spheres; ++s) {
+            const int ls = r.sphere_link[s];
+            if (ls == j) { mx += r.sphere_off[3 * s]; my += r.sphere_off[3 * s + 1]; mz += r.sphere_off[3 * s + 2]; ++n; }
+            if (ls <= j) end = s + 1;
+        }
+        float R = 0.f;
+        if (n > 0) {
+            mx /= n; my /= n; mz /= n;
+            for (int s = 0; s < r.n_spheres; ++s) {
+                if (r.sphere_link[s] != j) continue;
+                const float dx = r.sphere_off[3 * s] - mx, dy = r.sphere_off[3 * s + 1] - my, dz = r.sphere_off[3 * s + 2] - mz;
+                R = fmaxf(R, sqrtf(dx * dx + dy * dy + dz * dz) + r.sphere_r[s]);
+            }
+        }
+        reinterpret_cast<float4*>(smem + l.bound)[j] = make_float4(mx, my, mz, fmaf(R, 1.0001f, 1e-6f));
+        reinterpret_cast<int*>(smem + l.link_end)[j] = end;
+    }
 }
 
 // One step of the serial chain:  T <- T * F_j * Rz(q_j)   (oracle/robots.py SerialChainRobot.link_frames)

@@ -33,13 +33,15 @@ struct CostArgs {
     float* cost;
     float* terms;
     unsigned char* free_flag;
-    unsigned rows_off, queue_off;      // byte offsets into dynamic shared memory
+    unsigned rows_off, queue_off, list_off;   // byte offsets into dynamic shared memory
     int row_stride;                    // floats
+    int list_cap;                      // broad-phase list entries per warp (max primitives of one field)
 };
 
-// Per-warp queue of flagged spheres (structure of arrays in shared memory).
+// Per-warp queue of flagged spheres: structure of arrays in shared memory at byte offset `base`
+// (x[kQCap] y[kQCap] z[kQCap] b[kQCap] f[kQCap]); offsets instead of pointers keep it at two registers.
 struct WarpQueue {
-    float* x; float* y; float* z; float* b; int* f;
+    unsigned base;
     int n;
 };
 
@@ -49,13 +51,14 @@ struct HingeAcc {
 };
 
 // Exact pass over `count` (<= 32) queue entries starting at `first`, one entry per lane.  Deliberately NOT
-// inlined: it is the rare path, and keeping one copy keeps the hot cull loop resident in the instruction cache.
-__device__ __noinline__ void drain(const FieldArgs& fa, WarpQueue q, int first, int count, int lane, HingeAcc& acc) {
+// inlined: it is the rare path, and keeping one copy keeps the hot loops resident in the instruction cache.
+__device__ __noinline__ void drain(const FieldArgs& fa, unsigned qbase, int first, int count, int lane, HingeAcc& acc) {
     extern __shared__ __align__(16) unsigned char smem[];
     if (lane < count) {
         const int i = first + lane;
-        const int f = q.f[i];
-        const float h = exact_hinge(smem, fa.l[f], q.x[i], q.y[i], q.z[i], q.b[i]);
+        const float* qb = reinterpret_cast<const float*>(smem + qbase);
+        const int f = __float_as_int(qb[4 * kQCap + i]);
+        const float h = exact_hinge(smem, fa.l[f], qb[i], qb[kQCap + i], qb[2 * kQCap + i], qb[3 * kQCap + i]);
         acc.all_zero = acc.all_zero && (h == 0.f);
 #pragma unroll
         for (int k = 0; k < MPB_MAX_FIELDS; ++k)
@@ -65,24 +68,24 @@ __device__ __noinline__ void drain(const FieldArgs& fa, WarpQueue q, int first, 
 }
 
 // Append the lanes whose `pred` is set; drain a full batch of 32 when available.
-__device__ __forceinline__ void enqueue(const unsigned char* smem, const FieldArgs& fa, WarpQueue& q, bool pred, float cx,
+__device__ __forceinline__ void enqueue(unsigned char* smem, const FieldArgs& fa, WarpQueue& q, bool pred, float cx,
                                         float cy, float cz, float b, int f, int lane, HingeAcc& acc) {
     const unsigned bal = __ballot_sync(MPB_FULL_MASK, pred);
     if (bal == 0u) return;
     if (pred) {
-        const int pos = q.n + __popc(bal & ((1u << lane) - 1u));
-        q.x[pos] = cx; q.y[pos] = cy; q.z[pos] = cz; q.b[pos] = b; q.f[pos] = f;
+        float* qb = reinterpret_cast<float*>(smem + q.base) + q.n + __popc(bal & ((1u << lane) - 1u));
+        qb[0] = cx; qb[kQCap] = cy; qb[2 * kQCap] = cz; qb[3 * kQCap] = b; qb[4 * kQCap] = __int_as_float(f);
     }
     q.n += __popc(bal);
     __syncwarp();
     if (q.n >= 32) {
         q.n -= 32;
-        drain(fa, q, q.n, 32, lane, acc);
+        drain(fa, q.base, q.n, 32, lane, acc);
     }
 }
 
 template <int G>
-__device__ __forceinline__ void collide_block(const unsigned char* smem, const FieldArgs& fa, WarpQueue& q,
+__device__ __forceinline__ void collide_block(unsigned char* smem, const FieldArgs& fa, WarpQueue& q,
                                               const float (&cx)[G], const float (&cy)[G], const float (&cz)[G],
                                               const float (&rad)[G], bool active, int lane, HingeAcc& acc) {
     for (int f = 0; f < fa.n_fields; ++f) {
@@ -102,7 +105,7 @@ __device__ __forceinline__ void collide_block(const unsigned char* smem, const F
 }
 
 template <int KIND, int G>
-__global__ void __launch_bounds__(kWarps * 32, 2) cost_eval_kernel(const __grid_constant__ CostArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_constant__ CostArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
 
     stage_fields(a.fields, smem);
@@ -112,17 +115,15 @@ __global__ void __launch_bounds__(kWarps * 32, 2) cost_eval_kernel(const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* xs = reinterpret_cast<float*>(smem + a.rows_off) + (size_t)warp * a.row_stride;
     WarpQueue q;
-    {
-        float* qb = reinterpret_cast<float*>(smem + a.queue_off) + (size_t)warp * kQCap * 5;
-        q.x = qb; q.y = qb + kQCap; q.z = qb + 2 * kQCap; q.b = qb + 3 * kQCap;
-        q.f = reinterpret_cast<int*>(qb + 4 * kQCap);
-    }
+    q.base = a.queue_off + (unsigned)(warp * kQCap * 5 * sizeof(float));
+    q.n = 0;
     const int nf = a.fields.n_fields;
     const int H = a.H, D = a.D, d = a.d, M = a.M;
     const bool vec_ok = ((M & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
     const float4* rsphere = reinterpret_cast<const float4*>(smem + a.rl.sphere);
     const float* rtf = reinterpret_cast<const float*>(smem + a.rl.tf);
-    const int* rlink = reinterpret_cast<const int*>(smem + a.rl.link);
+    unsigned short* lsph = reinterpret_cast<unsigned short*>(smem + a.list_off) + (size_t)warp * 2 * a.list_cap;
+    unsigned short* lbox = lsph + a.list_cap;
     const float point_r = (KIND == MPB_ROBOT_POINT) ? __ldg(a.robot.sphere_r) : 0.f;
 
     for (int b = blockIdx.x * kWarps + warp; b < a.B; b += gridDim.x * kWarps) {
@@ -219,36 +220,60 @@ __global__ void __launch_bounds__(kWarps * 32, 2) cost_eval_kernel(const __grid_
                     __syncwarp();
                     Frame T;
                     frame_identity(T);
-                    int cur = -1;
-                    const int ns = a.rl.n_spheres;
-                    for (int s0 = 0; s0 < ns; s0 += G) {
-                        float cx[G], cy[G], cz[G], rad[G];
+                    int s_begin = 0;
+                    const float4* rbound = reinterpret_cast<const float4*>(smem + a.rl.bound);
+                    const int* rlend = reinterpret_cast<const int*>(smem + a.rl.link_end);
+#pragma unroll 1
+                    for (int j = 0; j < d; ++j) {
+                        frame_advance(T, rtf + j * 12, xt[j], xt[d + j]);
+                        const int s_end = rlend[j];
+                        if (s_end == s_begin) continue;
+                        const float4 bs = rbound[j];
+                        const float bx = fmaf(T.r00, bs.x, fmaf(T.r01, bs.y, fmaf(T.r02, bs.z, T.tx)));
+                        const float by = fmaf(T.r10, bs.x, fmaf(T.r11, bs.y, fmaf(T.r12, bs.z, T.ty)));
+                        const float bz = fmaf(T.r20, bs.x, fmaf(T.r21, bs.y, fmaf(T.r22, bs.z, T.tz)));
+#pragma unroll 1
+                        for (int f = 0; f < nf; ++f) {
+                            const FieldLayout& fl = a.fields.l[f];
+                            int n_ls, n_lb;
+                            __syncwarp();
+                            broad_phase(smem, fl, bx, by, bz, bs.w + fl.margin, active, lane, lsph, n_ls, lbox, n_lb);
+                            if (n_ls + n_lb == 0) continue;
+                            __syncwarp();
+#pragma unroll 1
+                            for (int s0 = s_begin; s0 < s_end; s0 += G) {
+                                float cx[G], cy[G], cz[G], bb[G];
 #pragma unroll
-                        for (int k = 0; k < G; ++k) {
-                            const int s = s0 + k;
-                            if (s < ns) {
-                                const int l = rlink[s];
-                                while (cur < l) {
-                                    ++cur;
-                                    frame_advance(T, rtf + cur * 12, xt[cur], xt[d + cur]);
+                                for (int k = 0; k < G; ++k) {
+                                    if (s0 + k < s_end) {
+                                        const float4 o = rsphere[s0 + k];
+                                        cx[k] = fmaf(T.r00, o.x, fmaf(T.r01, o.y, fmaf(T.r02, o.z, T.tx)));
+                                        cy[k] = fmaf(T.r10, o.x, fmaf(T.r11, o.y, fmaf(T.r12, o.z, T.ty)));
+                                        cz[k] = fmaf(T.r20, o.x, fmaf(T.r21, o.y, fmaf(T.r22, o.z, T.tz)));
+                                        bb[k] = __fadd_rn(o.w, fl.margin);
+                                    } else {
+                                        cx[k] = cy[k] = cz[k] = 1e18f;     // padding slot: never a candidate
+                                        bb[k] = 0.f;
+                                    }
                                 }
-                                const float4 o = rsphere[s];
-                                cx[k] = fmaf(T.r00, o.x, fmaf(T.r01, o.y, fmaf(T.r02, o.z, T.tx)));
-                                cy[k] = fmaf(T.r10, o.x, fmaf(T.r11, o.y, fmaf(T.r12, o.z, T.ty)));
-                                cz[k] = fmaf(T.r20, o.x, fmaf(T.r21, o.y, fmaf(T.r22, o.z, T.tz)));
-                                rad[k] = o.w;
-                            } else {
-                                cx[k] = cy[k] = cz[k] = 1e18f;     // padding slot: never a candidate
-                                rad[k] = 0.f;
+                                unsigned cand = cull_list<G>(smem, fl, lsph, n_ls, lbox, n_lb, cx, cy, cz, bb);
+                                if (!active) cand = 0u;
+                                const unsigned any = __reduce_or_sync(MPB_FULL_MASK, cand);
+                                if (any) {
+#pragma unroll
+                                    for (int k = 0; k < G; ++k)
+                                        if (any & (1u << k))
+                                            enqueue(smem, a.fields, q, (cand >> k) & 1u, cx[k], cy[k], cz[k], bb[k], f, lane, hacc);
+                                }
                             }
                         }
-                        collide_block<G>(smem, a.fields, q, cx, cy, cz, rad, active, lane, hacc);
+                        s_begin = s_end;
                     }
                 }
             }
         }
         if (q.n > 0) {
-            drain(a.fields, q, 0, q.n, lane, hacc);
+            drain(a.fields, q.base, 0, q.n, lane, hacc);
             q.n = 0;
         }
 
@@ -347,6 +372,14 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
     off += (unsigned)(kWarps * a.row_stride * sizeof(float));
     a.queue_off = off;
     off += (unsigned)(kWarps * kQCap * 5 * sizeof(float));
+    a.list_cap = 8;
+    for (int i = 0; i < n_fields; ++i) {
+        MPB_REQUIRE(fields[i].n_spheres < 65536 && fields[i].n_boxes < 65536, "mpb_cost_eval: too many primitives in field %d", i);
+        const int m = fields[i].n_spheres > fields[i].n_boxes ? fields[i].n_spheres : fields[i].n_boxes;
+        if (m > a.list_cap) a.list_cap = (m + 7) & ~7;
+    }
+    a.list_off = off;
+    off += (unsigned)(kWarps * 2 * a.list_cap * sizeof(unsigned short));
     const size_t smem = off;
     MPB_REQUIRE(smem <= 227 * 1024, "mpb_cost_eval: %zu bytes of shared memory needed (H*D too large or too many primitives)", smem);
 
