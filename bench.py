@@ -319,10 +319,17 @@ def main():
     fp32_peak = 148 * 128 * 2 * sm_mhz_peak * 1e6 / 1e12            # TFLOP/s, nominal FMA rate at clocks.max.sm
     kernels = []
     flops = [FLOP_SAMPLING, None, FLOP_FK + FLOP_SDF + FLOP_GP + FLOP_IS, None]
-    names = ['sample_gp_simt_kernel (K1)', 'prior_matvec_kernel', 'cost_eval_kernel (K2)', 'softmax_update_kernel (K3)']
+    names = ['sample_gp_tc_kernel (K1, tcgen05 3xTF32)' if planner._sample_dist.scale_tril_split is not None else 'sample_gp_simt_kernel (K1)', 'prior_matvec_kernel', 'cost_eval_kernel (K2)', 'softmax_update_kernel (K3)']
     for j, nm in enumerate(names):
         k = dict(kernel=nm, ms=float(stage_ms[j]), share=float(stage_ms[j] / stage_ms.sum()))
-        if flops[j]:
+        if flops[j] and j == 0 and 'tcgen05' in nm:
+            a = flops[j] * n_samp / (stage_ms[j] * 1e-3) / 1e12
+            tf32_peak = pk['bf16'] / 2.0
+            k.update(bound='tensor', achieved=a, peak=tf32_peak, unit='TFLOP/s', frac=a / tf32_peak,
+                     note='algorithmic flops M(M+1) per sample; peak = TF32 dense = measured bf16 peak / 2 (' + pk['source'] +
+                          '); fp32 parity needs the 3xTF32 split, i.e. 3 tensor-core flops per algorithmic flop, so the '
+                          'ceiling for this ratio is 1/3 (times the triangular-tile granularity)')
+        elif flops[j]:
             a = flops[j] * n_samp / (stage_ms[j] * 1e-3) / 1e12
             k.update(bound='fp32', achieved=a, peak=fp32_peak, unit='TFLOP/s', frac=a / fp32_peak)
         elif j == 3:
@@ -334,7 +341,7 @@ def main():
     roofline = dict(bound=dom['bound'], achieved=dom['achieved'], peak=dom['peak'], unit=dom['unit'], frac=dom['frac'],
                     traffic=None, kernel=dom['kernel'], ms_per_launch=dom['ms'],
                     peak_source=('nominal FP32 FMA rate 148 SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json holds only '
-                                 'HBM and bf16 tensor peaks; this kernel is FP32-issue bound)') if dom['bound'] == 'fp32' else pk['source'],
+                                 'HBM and bf16 tensor peaks; this kernel is FP32-issue bound)') if dom['bound'] == 'fp32' else dom.get('note', pk['source']),
                     algorithmic_flop_per_sample=flops[2] if 'K2' in dom['kernel'] else flops[0], kernels=kernels)
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,

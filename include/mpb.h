@@ -91,6 +91,15 @@ int mpb_version(void);
 int mpb_sample_gp(const float* L, const float* mu, const float* eps, float* x,
                   int P, int S, int M, void* stream);
 
+/* Tensor-core variant of mpb_sample_gp (tcgen05 3xTF32, fp32 accumulation in TMEM; csrc/sample_gp_tc.cu).
+ * The factor is pre-split once with mpb_split_tf32 into L_hi (upper 11 mantissa bits) and L_lo (next 11 bits);
+ * eps is split on the fly.  Requires M % 16 == 0, M >= 32 and 16-byte aligned pointers
+ * (mpb_sample_gp_tc_supported() != 0); same result as mpb_sample_gp to ~1e-7 absolute. */
+int mpb_split_tf32(const float* src, float* hi, float* lo, long long n, void* stream);
+int mpb_sample_gp_tc_supported(int P, int S, int M);
+int mpb_sample_gp_tc(const float* L_hi, const float* L_lo, const float* mu, const float* eps, float* x,
+                     int P, int S, int M, void* stream);
+
 /* STOMP noise: x[p,s,h,j] = mu[p,h,j] + (h==0||h==H-1 ? 0 : sum_k L_R[h,k] eps[s,j,p,k])
  * Replaces STOMP.sample (mp_baselines/planners/stomp.py:97-108); eps is [S,D,P,H]. */
 int mpb_sample_stomp(const float* L_R, const float* mu, const float* eps, float* x,
@@ -129,8 +138,9 @@ int mpb_softmax_update(const float* cost, const float* x, float* mu, float* weig
 
 /* One fused Stoch-GPMP iteration = sample_gp -> prior_matvec -> cost_eval(+IS) -> softmax_update.
  * Replaces the body of StochGPMP.optimize (stoch_gpmp.py:291-299).
+ * L_split: NULL (FP32 SIMT sampler) or the [2,M,M] output of mpb_split_tf32 (tensor-core sampler).
  * workspace: x [P,S,H,D], cost [P,S], weights [P,S], is_vec [P,M]; free_flag [P*S] may be NULL. */
-int mpb_stoch_gpmp_iter(const float* L, const float* Sigma_inv, const float* eps,
+int mpb_stoch_gpmp_iter(const float* L, const float* L_split, const float* Sigma_inv, const float* eps,
                         float* mu, float* x, float* cost, float* weights, float* is_vec,
                         uint8_t* free_flag,
                         int P, int S, int H,

@@ -45,13 +45,14 @@ extern "C" int mpb_version(void) { return 100; }
 // One Stoch-GPMP iteration (mp_baselines/planners/stoch_gpmp.py:291-299): K1 -> matvec -> K2 -> K3,
 // all enqueued on `stream` with no host synchronisation.  The prior factor L never changes, so the
 // reference's per-iteration re-factorisation (mp_priors_multi.py:120-123) has no counterpart here.
-extern "C" int mpb_stoch_gpmp_iter(const float* L, const float* Sigma_inv, const float* eps, float* mu, float* x,
+extern "C" int mpb_stoch_gpmp_iter(const float* L, const float* L_split, const float* Sigma_inv, const float* eps, float* mu, float* x,
                                    float* cost, float* weights, float* is_vec, uint8_t* free_flag, int P, int S,
                                    int H, const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
                                    const mpb_gp_desc* gp, float temp, float step, void* stream) {
     MPB_REQUIRE(robot, "mpb_stoch_gpmp_iter: robot is null");
     const int D = 2 * robot->q_dim, M = H * D;
-    int rc = mpb_sample_gp(L, mu, eps, x, P, S, M, stream);
+    int rc = L_split ? mpb_sample_gp_tc(L_split, L_split + (size_t)M * M, mu, eps, x, P, S, M, stream)
+                     : mpb_sample_gp(L, mu, eps, x, P, S, M, stream);
     if (rc) return rc;
     rc = mpb_prior_matvec(Sigma_inv, mu, is_vec, P, M, 2 * D - 1, stream);
     if (rc) return rc;

@@ -1,0 +1,385 @@
+// K1 (tensor-core variant): GP-prior sampling  x[p,s,:] = mu[p,:] + L @ eps[s,p,:]  on tcgen05.
+//
+// Replaces MultiMPPrior.sample (mp_baselines/planners/costs/factors/mp_priors_multi.py:253-256).  The shape
+// is a real dense contraction -- X[N,M] = E[N,M] * L^T with N = P*S = 32768 rows and M = K = 896 at the
+// BASELINE.json C4 shape -- so it runs on the 5th-generation tensor cores.  fp32 parity (1e-5) rules out
+// plain TF32 (10-bit mantissa); we use the error-compensated 3xTF32 split
+//        E*L^T  ~=  E_hi*L_hi^T + E_lo*L_hi^T + E_hi*L_lo^T        (fp32 accumulation in TMEM)
+// whose dropped term E_lo*L_lo is O(2^-22) relative.
+//
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor loads of the raw eps tile [128 x 32] and of the pre-split
+//               factor tiles L_hi / L_lo [256 x 32] (128-byte swizzle) into a 2-stage shared-memory ring
+//   warps 4-7   transform: split the eps tile in place into hi (low 13 mantissa bits cleared) and lo = e - hi
+//   warp 1      MMA issuer: one elected thread issues 12 tcgen05.mma.kind::tf32 per stage (4 k-steps x 3
+//               products), accumulators [128 x 256] fp32 in TMEM, double buffered (2 x 256 columns)
+//   warps 8-11  epilogue: tcgen05.ld the accumulator, add mu_p, store the row of x (particle-major)
+// L is lower triangular, so k-blocks right of the diagonal block are never loaded or multiplied.
+// Pipelines: smem full/empty mbarriers (TMA -> transform -> MMA -> TMA) and TMEM full/empty (MMA <-> epilogue).
+#include <cuda.h>
+
+#include "mpb_common.cuh"
+
+namespace mpb {
+
+constexpr int TC_BM = 128;          // rows of eps per tile  (UMMA M)
+constexpr int TC_BN = 256;          // columns of x per tile (UMMA N, rows of L)
+constexpr int TC_BK = 32;           // k per stage: 32 fp32 = one 128-byte swizzle row
+constexpr int TC_STAGES = 2;
+constexpr int TC_THREADS = 384;
+constexpr uint32_t A_TILE_BYTES = TC_BM * TC_BK * 4;      // 16 KiB
+constexpr uint32_t B_TILE_BYTES = TC_BN * TC_BK * 4;      // 32 KiB
+constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;     // A_hi | A_lo | B_hi | B_lo
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile with 128-byte swizzle: rows of 128 B, 8-row (1024 B) swizzle atoms stacked along M/N.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address
+    d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+    return d;
+}
+// kind::tf32, fp32 accumulate, both operands K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcArgs {
+    const float* mu;
+    float* x;
+    int P, S, M, N;             // N = P*S rows
+    int n_row_tiles, n_col_tiles;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+sample_gp_tc_kernel(const __grid_constant__ CUtensorMap map_eps, const __grid_constant__ CUtensorMap map_lhi,
+                    const __grid_constant__ CUtensorMap map_llo, const TcArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * STAGE_BYTES);
+    uint64_t* full_raw = bars;                      // [2] TMA landed
+    uint64_t* full_xf = bars + 2;                   // [2] eps split done
+    uint64_t* empty = bars + 4;                     // [2] MMAs that read the stage completed
+    uint64_t* tmem_full = bars + 6;                 // [2] accumulator ready
+    uint64_t* tmem_empty = bars + 8;                // [2] accumulator drained
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full_raw[s], 1);
+            mbar_init(&full_xf[s], 4);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_base_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    const int n_tiles = a.n_row_tiles * a.n_col_tiles;
+    // tile t -> (column tile jc, row tile r); column tiles are visited from the right (longest k range) first
+    auto tile_coords = [&](int t, int& r, int& jc, int& n_cols, int& n_kb) {
+        const int jj = t / a.n_row_tiles;
+        r = t - jj * a.n_row_tiles;
+        jc = a.n_col_tiles - 1 - jj;
+        const int c0 = jc * TC_BN;
+        n_cols = min(TC_BN, a.M - c0);
+        const int k_end = min(a.M, c0 + TC_BN);          // L[i,k] = 0 for k > i
+        n_kb = (k_end + TC_BK - 1) / TC_BK;
+    };
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                int r, jc, n_cols, n_kb;
+                tile_coords(t, r, jc, n_cols, n_kb);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* st = tiles + stage * STAGE_BYTES;
+                    mbar_expect_tx(&full_raw[stage], A_TILE_BYTES + 2 * B_TILE_BYTES);
+                    tma_load_2d(&map_eps, &full_raw[stage], st, kb * TC_BK, r * TC_BM);
+                    tma_load_2d(&map_lhi, &full_raw[stage], st + 2 * A_TILE_BYTES, kb * TC_BK, jc * TC_BN);
+                    tma_load_2d(&map_llo, &full_raw[stage], st + 2 * A_TILE_BYTES + B_TILE_BYTES, kb * TC_BK, jc * TC_BN);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                int r, jc, n_cols, n_kb;
+                tile_coords(t, r, jc, n_cols, n_kb);
+                const uint32_t idesc = make_idesc_tf32(TC_BM, (n_cols + 15) & ~15);
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&full_xf[stage], phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(tiles + stage * STAGE_BYTES);
+                    const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + A_TILE_BYTES);
+                    const uint64_t b_hi = make_sw128_desc(st + 2 * A_TILE_BYTES);
+                    const uint64_t b_lo = make_sw128_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);      // +32 B per k-step inside the swizzle row
+                        umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, (kb | k) ? 1u : 0u);   // small terms first
+                        umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                        umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================================ transform: eps -> hi | lo =====================
+        const int tid = threadIdx.x - 128;          // 0..127
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            int r, jc, n_cols, n_kb;
+            tile_coords(t, r, jc, n_cols, n_kb);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(&full_raw[stage], phase);
+                float4* hi = reinterpret_cast<float4*>(tiles + stage * STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(tiles + stage * STAGE_BYTES + A_TILE_BYTES);
+#pragma unroll
+                for (int i = 0; i < (int)(A_TILE_BYTES / 16 / 128); ++i) {       // 8 x float4 per thread
+                    const int idx = i * 128 + tid;
+                    const float4 v = hi[idx];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+                    hi[idx] = h;
+                    lo[idx] = l;
+                }
+                fence_async_proxy();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_xf[stage]);
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 8) {
+        // ================================ epilogue ====================================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            int r, jc, n_cols, n_kb;
+            tile_coords(t, r, jc, n_cols, n_kb);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int m = r * TC_BM + q * 32 + lane;            // row of eps: m = s*P + p
+            const bool row_ok = m < a.N;
+            const int s = row_ok ? m / a.P : 0, p = row_ok ? m - s * a.P : 0;
+            const float* mrow = a.mu + (size_t)p * a.M + jc * TC_BN;
+            float* xrow = a.x + ((size_t)p * a.S + s) * a.M + jc * TC_BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN);
+            for (int c = 0; c < n_cols; c += 32) {
+                float v[32];
+                tmem_ld32(taddr + (uint32_t)c, v);
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (c + i + 3 < n_cols) {
+                            const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow + c + i));
+                            float4 o;
+                            o.x = m4.x + v[i]; o.y = m4.y + v[i + 1]; o.z = m4.z + v[i + 2]; o.w = m4.w + v[i + 3];
+                            *reinterpret_cast<float4*>(xrow + c + i) = o;
+                        } else {
+                            for (int e = 0; e < 4; ++e)
+                                if (c + i + e < n_cols) xrow[c + i + e] = __ldg(mrow + c + i + e) + v[i + e];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// L -> L_hi (low 13 mantissa bits cleared) and L_lo = tf32-truncated (L - L_hi); both exactly representable in TF32.
+__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = src[i];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = __uint_as_float(__float_as_uint(v - h) & 0xffffe000u);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] tensor, box [box_rows, 32 floats], 128-byte swizzle, zero fill out of bounds.
+static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace mpb
+
+extern "C" int mpb_split_tf32(const float* src, float* hi, float* lo, long long n, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(src && hi && lo && n >= 0, "mpb_split_tf32: bad arguments");
+    if (n == 0) return MPB_OK;
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, hi, lo, (size_t)n);
+    return check_launch("mpb_split_tf32");
+}
+
+extern "C" int mpb_sample_gp_tc_supported(int P, int S, int M) {
+    return (M % 16 == 0) && M >= 32 && (long long)P * S >= 1 && mpb::get_encode() != nullptr;
+}
+
+extern "C" int mpb_sample_gp_tc(const float* L_hi, const float* L_lo, const float* mu, const float* eps, float* x, int P,
+                                int S, int M, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(L_hi && L_lo && mu && eps && x, "mpb_sample_gp_tc: null pointer");
+    MPB_REQUIRE(P >= 0 && S >= 0 && M >= 32 && M % 16 == 0, "mpb_sample_gp_tc: M=%d must be a multiple of 16 and >= 32", M);
+    if (P == 0 || S == 0) return MPB_OK;
+    MPB_REQUIRE((reinterpret_cast<uintptr_t>(eps) & 15) == 0 && (reinterpret_cast<uintptr_t>(L_hi) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(L_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(mu) & 15) == 0,
+                "mpb_sample_gp_tc: pointers must be 16-byte aligned");
+    const int N = P * S;
+    CUtensorMap m_eps, m_hi, m_lo;
+    if (!make_map(&m_eps, eps, N, M, TC_BM) || !make_map(&m_hi, L_hi, M, M, TC_BN) || !make_map(&m_lo, L_lo, M, M, TC_BN)) {
+        set_error("mpb_sample_gp_tc: cuTensorMapEncodeTiled failed");
+        return MPB_ECUDA;
+    }
+    TcArgs a;
+    a.mu = mu; a.x = x; a.P = P; a.S = S; a.M = M; a.N = N;
+    a.n_row_tiles = (N + TC_BM - 1) / TC_BM;
+    a.n_col_tiles = (M + TC_BN - 1) / TC_BN;
+    cudaError_t e = cudaFuncSetAttribute(sample_gp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("mpb_sample_gp_tc: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+    const int n_tiles = a.n_row_tiles * a.n_col_tiles;
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    sample_gp_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(m_eps, m_hi, m_lo, a);
+    return check_launch("mpb_sample_gp_tc");
+}

@@ -8,6 +8,8 @@ CPU in the working dtype), so that the fused sampler multiplies by bit-identical
 part -- drawing samples every iteration -- runs in the mpb_sample_gp kernel, and ``set_mean`` only
 swaps the mean: the factor of an unchanged precision is never recomputed (reference quirk B4).
 """
+import os
+
 import torch
 import torch.distributions as dist
 
@@ -86,6 +88,12 @@ class MultiMPPrior:
         self.scale_tril = dist.MultivariateNormal(torch.zeros(self.M), precision_matrix=Sinv_cpu).scale_tril \
             .to(**tensor_args).contiguous()
         self.Sigma_inv = Sinv_cpu.to(**tensor_args).contiguous()
+        # tensor-core sampler operands: L pre-split into two TF32-representable parts (3xTF32 scheme)
+        self.scale_tril_split = None
+        if os.environ.get('MPB_SAMPLE_GP', 'tc') != 'simt' and _lib.lib().mpb_sample_gp_tc_supported(1, 1, self.M):
+            self.scale_tril_split = torch.empty(2, self.M, self.M, **tensor_args)
+            _lib.check(_lib.lib().mpb_split_tf32(_lib.ptr(self.scale_tril), _lib.ptr(self.scale_tril_split[0]),
+                                                 _lib.ptr(self.scale_tril_split[1]), self.M * self.M, _lib.stream_ptr()))
 
     @classmethod
     def const_vel_trajectory(cls, start_state, goal_state, dt, num_steps, dof, set_initial_final_vel_to_zero=True,
@@ -124,6 +132,11 @@ class MultiMPPrior:
         _lib.require_f32(eps)
         assert eps.shape == (S, P, M)
         x = out if out is not None else torch.empty(P, S, M, **self.tensor_args)
-        _lib.check(_lib.lib().mpb_sample_gp(_lib.ptr(self.scale_tril), _lib.ptr(self.means), _lib.ptr(eps.contiguous()),
-                                            _lib.ptr(x), P, S, M, _lib.stream_ptr()))
+        eps = eps.contiguous()
+        if self.scale_tril_split is not None:
+            _lib.check(_lib.lib().mpb_sample_gp_tc(_lib.ptr(self.scale_tril_split[0]), _lib.ptr(self.scale_tril_split[1]),
+                                                   _lib.ptr(self.means), _lib.ptr(eps), _lib.ptr(x), P, S, M, _lib.stream_ptr()))
+        else:
+            _lib.check(_lib.lib().mpb_sample_gp(_lib.ptr(self.scale_tril), _lib.ptr(self.means), _lib.ptr(eps),
+                                                _lib.ptr(x), P, S, M, _lib.stream_ptr()))
         return x.view(P, S, self.num_steps + 1, self.state_dim)
