@@ -149,6 +149,43 @@ int mpb_stoch_gpmp_iter(const float* L, const float* L_split, const float* Sigma
                         const mpb_gp_desc* gp,
                         float temp, float step, void* stream);
 
+/* The whole CHOMP loop (n_iters gradient steps) in one launch, x [P,H,D] updated in place.
+ * Replaces CHOMP._run_optimization / _eval (mp_baselines/planners/chomp.py:127-169):
+ *   g = d/dx [ sum_f weight_f * inv_sigma2_f * sum_{t>=1} err_f(x_t) ] + smooth_scale * 2 R x
+ *   g = clamp(g, +-grad_clip); g[:,0] = g[:,H-1] = 0; x -= lr * g
+ * The collision gradient is analytic (the reference uses autograd through FK + SDF).  R [H,H] is the
+ * tridiagonal precision of chomp.py:81-101.  smooth_scale = P_global * weight_prior_cost: the reference adds
+ * the smoothness cost summed over ALL particles to every particle (quirk B1), so when particles are sharded
+ * over GPUs the caller passes the global particle count. */
+int mpb_chomp_run(float* x, int P, int H,
+                  const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
+                  const float* R, float smooth_scale, float lr, float grad_clip, int n_iters, void* stream);
+
+/* GPMP2 step, part 1: collision errors and Jacobians of every waypoint.
+ * Replaces FieldFactor.get_error(calc_jacobian=True) (costs/factors/field_factor.py:41-57) as used by
+ * CostCollision.get_linear_system (cost_functions.py:191-231):
+ *   err  [n_fields,B,H]     err[f,b,t] = sum_s relu(r_s + margin - sdf(c_s)),  0 at t = 0 (no collision factor there)
+ *   hobs [n_fields,B,H,d]   H_obst = -d err / d q_t
+ *   diag_mean [H*d] (fp64) | NULL: (1/B) sum_b sum_f inv_sigma2_f * hobs^2 -- the collision part of
+ *   mean_batch diag(A^T K A) that the trust-region variant needs (gpmp2.py:366); a deterministic reduction. */
+int mpb_gpmp2_linearize(const float* x, int B, int H,
+                        const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
+                        float* err, float* hobs, double* diag_mean, void* stream);
+
+/* GPMP2 step, part 2: assemble the block-tridiagonal normal equations (never materialising A, K, J^T J),
+ * block-Cholesky solve, update x += step * dtheta.  Replaces CostGP/CostGoalPrior.get_linear_system
+ * (cost_functions.py:291-314,538-554), GPMP2._get_grad_terms + get_torch_solve('cholesky') + the update of
+ * _step (gpmp2.py:333-368,451-452) and _get_costs (gpmp2.py:493-495).
+ *   inv_sigma2 [n_fields] HOST array of 1/sigma_coll^2
+ *   diag_mean  NULL -> J^T J = A^T K A + delta I;  else trust region: + delta * diag(mean_b diag(A^T K A))
+ *   workspace  mpb_gpmp2_workspace_bytes(B,H,D) bytes (fp64 factor blocks)
+ *   cost [B]|NULL  b^T K b at the linearisation point;  dtheta [B,H,D]|NULL the step before scaling */
+long long mpb_gpmp2_workspace_bytes(int B, int H, int D);
+int mpb_gpmp2_solve(float* x, int B, int H, int d, const mpb_gp_desc* gp,
+                    const float* err, const float* hobs, const float* inv_sigma2_host, int n_fields,
+                    const double* diag_mean, float delta, float step,
+                    double* workspace, float* cost, float* dtheta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

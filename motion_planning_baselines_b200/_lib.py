@@ -53,6 +53,11 @@ _SIGNATURES = {
     'mpb_stoch_gpmp_iter': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                       C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
                                       _f, _f, _vp]),
+    'mpb_chomp_run': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _f, _f, _f, _i, _vp]),
+    'mpb_gpmp2_linearize': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _vp, _vp, _vp]),
+    'mpb_gpmp2_workspace_bytes': (C.c_longlong, [_i, _i, _i]),
+    'mpb_gpmp2_solve': (C.c_int, [_vp, _i, _i, _i, C.POINTER(GPDesc), _vp, _vp, C.POINTER(C.c_float), _i, _vp, _f, _f,
+                                  _vp, _vp, _vp, _vp]),
 }
 
 

@@ -165,6 +165,73 @@ class CostComposite(Cost):
             return [terms[i] if i >= 0 else zero for i in term_index], self.weight_cost_l
         return cost
 
+    def linearize_collision(self, trajs):
+        """-> err [n_fields,B,H], hobs [n_fields,B,H,d]: collision errors and H_obst = -d err/d q of every
+        waypoint (mpb_gpmp2_linearize; field_factor.py:41-57 without autograd)."""
+        x = self._flatten(trajs)
+        B, H, d = x.shape[0], self.n_support_points, self.n_dof
+        gp, fields, nf, _ = self._build()
+        err = torch.zeros(max(nf, 1), B, H, device=x.device, dtype=torch.float32)
+        hobs = torch.zeros(max(nf, 1), B, H, d, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().mpb_gpmp2_linearize(_lib.ptr(x), B, H, C.byref(self.robot.desc), fields, nf,
+                                                  _lib.ptr(err), _lib.ptr(hobs), None, _lib.stream_ptr()))
+        return err[:nf], hobs[:nf]
+
+    def get_linear_system(self, trajs, n_interpolated_points=None, **kwargs):
+        """Dense (A [B,rows,N], b [B,rows,1], K [B,rows,rows]) with the reference's row order
+        (cost_functions.py:107-144,191-231,291-314,538-554).  Kept for API parity and diagnostics: the collision
+        rows come from the analytic-Jacobian kernel, the (constant) GP rows are laid out with device tensor ops.
+        GPMP2._step never calls this -- it solves the block-tridiagonal system without materialising A or K."""
+        if n_interpolated_points is not None:
+            raise NotImplementedError('interpolated collision checking is a "next" row (SURVEY.md 8f)')
+        x = self._flatten(trajs)
+        B, H, D, d = x.shape[0], self.n_support_points, self.dim, self.n_dof
+        N, ta = H * D, dict(device=x.device, dtype=torch.float32)
+        err, hobs = self.linearize_collision(x)
+        eye = torch.eye(D, **ta)
+        As, bs, Ks = [], [], []
+        fi = 0
+        for cost in self.cost_l:
+            if isinstance(cost, CostGP):
+                Phi = torch.eye(D, **ta)
+                Phi[:d, d:] = torch.eye(d, **ta) * cost.dt
+                Q = torch.zeros(D, D, **ta)
+                Q[:d, :d], Q[:d, d:], Q[d:, :d], Q[d:, d:] = (torch.eye(d, **ta) * v for v in (cost.q11, cost.q12, cost.q12, cost.q22))
+                A = torch.zeros(B, N, N, **ta)
+                A[:, :D, :D] = eye
+                r = torch.arange(D, N, device=x.device)
+                A[:, r, r] = -1.0
+                A[:, D:, :-D] += torch.kron(torch.eye(H - 1, **ta), Phi)
+                b = torch.cat((cost.start_state - x[:, 0], (x[:, 1:] - x[:, :-1] @ Phi.t()).reshape(B, -1)), dim=1).unsqueeze(-1)
+                K = torch.block_diag(eye * cost.k_start, *([Q] * (H - 1))).expand(B, N, N)
+            elif isinstance(cost, CostGoalPrior):
+                A = torch.zeros(B, D, N, **ta)
+                A[:, :, -D:] = eye
+                b = (cost.goal_state - x[:, -1]).unsqueeze(-1)
+                K = (eye * cost.k_goal).expand(B, D, D)
+            elif isinstance(cost, CostCollision):
+                if cost.field is None:
+                    continue
+                A = torch.zeros(B, H - 1, H, D, **ta)
+                t = torch.arange(H - 1, device=x.device)
+                A[:, t, t + 1, :d] = hobs[fi][:, 1:]
+                A = A.reshape(B, H - 1, N)
+                b = err[fi][:, 1:].unsqueeze(-1)
+                K = (torch.eye(H - 1, **ta) * cost.inv_sigma2).expand(B, H - 1, H - 1)
+                fi += 1
+            else:
+                raise NotImplementedError(type(cost).__name__)
+            As.append(A), bs.append(b), Ks.append(K)
+        A, b = torch.cat(As, dim=1), torch.cat(bs, dim=1)
+        rows = A.shape[1]
+        K = torch.zeros(B, rows, rows, **ta)
+        o = 0
+        for k in Ks:
+            n = k.shape[1]
+            K[:, o:o + n, o:o + n] = k
+            o += n
+        return A, b, K
+
     def collision_free(self, trajs):
         """bool [B]: every collision hinge term of the trajectory (waypoints 1..H-1) is exactly 0."""
         x = self._flatten(trajs)

@@ -60,7 +60,11 @@ class PrimitiveField:
             out = s.min(dim=-1).values
         if self.box_centers.shape[0]:
             q = (x.unsqueeze(-2) - self.box_centers).abs() - self.box_half
-            outside = torch.sqrt(_sum_sq(torch.clamp(q, min=0.0)))
+            s2 = _sum_sq(torch.clamp(q, min=0.0))
+            # same forward values as sqrt(s2); where s2 == 0 (point inside the box) no gradient flows through the
+            # square root (plain sqrt would produce 0 * inf = NaN under autograd), leaving d/dx max_k q_k
+            pos = s2 > 0
+            outside = torch.sqrt(torch.where(pos, s2, torch.ones_like(s2))) * pos
             inside = torch.clamp(q.max(dim=-1).values, max=0.0)
             b = (outside + inside).min(dim=-1).values
             out = b if out is None else torch.minimum(out, b)
