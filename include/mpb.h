@@ -186,6 +186,42 @@ int mpb_gpmp2_solve(float* x, int B, int H, int d, const mpb_gp_desc* gp,
                     const double* diag_mean, float delta, float step,
                     double* workspace, float* cost, float* dtheta, void* stream);
 
+/* ---- importance-weight update split over CTAs / GPUs through packed partial records (csrc/softmax_split.cu) ----
+ * Same maths as mpb_softmax_update for one problem with 10^3..10^6 samples (BASELINE.json configs[4]) or one problem
+ * whose samples are sharded over GPUs; also MPPI.update_controller + _save_best (mppi.py:72-86,164-169).
+ * Record = [m, Z, cmin, argmin (int32 bits), v[H*Dw]] with m = max(-cost/temp), Z = sum exp(-cost/temp - m),
+ * v = sum exp(-cost/temp - m) (x - mu); mpb_softmax_record_len(H,Dw) floats.
+ *   partial: cost [P,S], x [P,S,H,Dfull] of which columns [c0,c0+Dw) of every waypoint are the updated variables,
+ *            mu [P,H,Dw] -> rec [n_chunks,P,REC]; sample_offset = global index of local sample 0 (argmin bookkeeping).
+ *   combine: rec [R,P,REC] (R = n_chunks x number of ranks after an all-gather along the first axis), merged in
+ *            fixed order r = 0..R-1 -> mu updated in place (mu += step * (SigmaR @ g | g)), grad [P,H,Dw]|NULL,
+ *            lse [P,2] = (m*, Z*)|NULL, best_cost [P]|NULL, best_idx [P]|NULL (first occurrence of the minimum).
+ *   weights: w[p,s] = exp(-cost/temp - m*) / Z*. */
+int mpb_softmax_record_len(int H, int Dw);
+int mpb_softmax_partial(const float* cost, const float* x, const float* mu, float* rec, float temp,
+                        int P, int S, int H, int Dfull, int c0, int Dw, int n_chunks, long long sample_offset, void* stream);
+int mpb_softmax_combine(const float* rec, int R, float* mu, float* grad, float* lse, float* best_cost, int32_t* best_idx,
+                        float step, const float* SigmaR, int P, int H, int Dw, void* stream);
+int mpb_softmax_weights(const float* cost, const float* lse, float* weights, float temp, int P, int S, void* stream);
+/* out[0] = sum of v[0..n) accumulated in fp64 in a fixed order (scratch: 1024 doubles). */
+int mpb_sum_f64(const float* v, long long n, double* out, double* scratch, void* stream);
+
+/* MPPI control sampling + rollout + quadratic cost + importance-sampling dot (csrc/mppi.cu).
+ * Replaces ControlTrajectoryGaussian.sample (priors/gaussian.py:276-298), MPPI.get_state_trajectories_rollout
+ * (mppi.py:190-210) with PointParticleDynamics.dynamics (dynamics/point.py:102-140; velocity control, deterministic),
+ * the quadratic part of traj_cost (point.py:198-225) and the V @ Cov_i^-1 @ mean_i dots of mppi.py:125-128.
+ *   L_ctrl, Cov_inv [C,T,T]; mean [T,C]; eps [C,N,T] (one block per control dimension, as torch draws them)
+ *   xu   [N,T,sd+C]  (state | control) rows = the `full_traj` the reference hands to the obstacle cost
+ *   quad [N]         pos + ctrl + terminal cost;  isv [N,C] the per-dimension IS dots */
+int mpb_mppi_rollout(const float* L_ctrl, const float* Cov_inv, const float* mean, const float* eps,
+                     const float* state0, const float* goal, const float* ctrl_min, const float* ctrl_max,
+                     float* xu, float* quad, float* isv, int N, int T, int C, int sd,
+                     float dt, float discount, float w_pos, float w_ctrl, float w_posT, void* stream);
+/* cost[n] = (quad[n] + energy[0]) + temp*isv[n,0] + temp*isv[n,1] + ...; energy (device fp64 scalar | NULL) is the
+ * obstacle cost SUMMED OVER THE BATCH, which the reference adds to every sample (point.py:196, quirk B2). */
+int mpb_mppi_finalize(const float* quad, const float* isv, const double* energy, float temp, float* cost,
+                      int N, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

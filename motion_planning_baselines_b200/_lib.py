@@ -58,6 +58,13 @@ _SIGNATURES = {
     'mpb_gpmp2_workspace_bytes': (C.c_longlong, [_i, _i, _i]),
     'mpb_gpmp2_solve': (C.c_int, [_vp, _i, _i, _i, C.POINTER(GPDesc), _vp, _vp, C.POINTER(C.c_float), _i, _vp, _f, _f,
                                   _vp, _vp, _vp, _vp]),
+    'mpb_softmax_record_len': (C.c_int, [_i, _i]),
+    'mpb_softmax_partial': (C.c_int, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, C.c_longlong, _vp]),
+    'mpb_softmax_combine': (C.c_int, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp]),
+    'mpb_softmax_weights': (C.c_int, [_vp, _vp, _vp, _f, _i, _i, _vp]),
+    'mpb_sum_f64': (C.c_int, [_vp, C.c_longlong, _vp, _vp, _vp]),
+    'mpb_mppi_rollout': (C.c_int, [_vp] * 11 + [_i, _i, _i, _i, _f, _f, _f, _f, _f, _vp]),
+    'mpb_mppi_finalize': (C.c_int, [_vp, _vp, _vp, _f, _vp, _i, _i, _vp]),
 }
 
 

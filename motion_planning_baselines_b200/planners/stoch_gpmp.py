@@ -127,7 +127,8 @@ class StochGPMP(OptimizationPlanner):
     def _update_distribution(self, costs, traj_samples):
         P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
         grad = torch.empty(P, H, D, **self.tensor_args)
-        _lib.check(_lib.lib().mpb_softmax_update(_lib.ptr(costs.contiguous()), _lib.ptr(traj_samples.contiguous()),
+        costs, traj_samples = costs.contiguous(), traj_samples.contiguous()         # named: temporaries must outlive the launch
+        _lib.check(_lib.lib().mpb_softmax_update(_lib.ptr(costs), _lib.ptr(traj_samples),
                                                  _lib.ptr(self._particle_means), _lib.ptr(self._w_buf), _lib.ptr(grad),
                                                  self.temperature, self.step_size, None, P, S, H, D, _lib.stream_ptr()))
         self._weights = self._w_buf.view(P, S, 1, 1)

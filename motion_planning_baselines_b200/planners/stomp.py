@@ -9,16 +9,18 @@ import torch
 import torch.distributions as dist
 
 from .. import _lib
+from ..update import SampleSplit, split_softmax_update
 from .base import OptimizationPlanner
 
 
 class STOMP(OptimizationPlanner):
+    SPLIT_THRESHOLD = 4096      # samples per particle above which the update is split over several CTAs
 
     def __init__(self, n_dof=None, n_support_points=None, num_particles_per_goal=None, num_samples=None,
                  opt_iters=None, dt=None, start_state=None, cost=None, initial_particle_means=None,
                  multi_goal_states=None, sigma_start_init=0.001, sigma_goal_init=0.001, sigma_gp_init=10.,
                  temperature=1., step_size=1., sigma_spectral=0.1, goal_state=None, pos_only=False,
-                 tensor_args=None, **kwargs):
+                 tensor_args=None, sample_split=None, **kwargs):
         super().__init__(name='STOMP', n_dof=n_dof, n_support_points=n_support_points,
                          num_particles_per_goal=num_particles_per_goal, opt_iters=opt_iters, dt=dt,
                          start_state=start_state, cost=cost, initial_particle_means=initial_particle_means,
@@ -42,7 +44,10 @@ class STOMP(OptimizationPlanner):
         # factor of the noise distribution from the reference's own routine (stomp.py:88-95), once, on the CPU
         self._L_R = dist.MultivariateNormal(torch.zeros(n_support_points), precision_matrix=R_cpu).scale_tril \
             .to(**self.tensor_args).contiguous()
-        P, S, H, D = self.num_particles, num_samples, n_support_points, self.d_state_opt
+        # sample-split mode: the S samples of every particle are sharded over the ranks of a process group
+        self.split = sample_split or SampleSplit(world=1, rank=0)
+        self._offset, self._s_local = self.split.local_slice(num_samples)
+        P, S, H, D = self.num_particles, self._s_local, n_support_points, self.d_state_opt
         self.state_particles = torch.empty(P, S, H, D, **self.tensor_args)
         self._w_buf = torch.empty(P, S, **self.tensor_args)
         self._cost_buf = torch.empty(P * S, **self.tensor_args)
@@ -66,13 +71,17 @@ class STOMP(OptimizationPlanner):
         pass            # the factor L_R is fixed at construction; nothing to rebuild
 
     def sample(self, eps=None):
-        """-> [P,S,H,D]; ``eps`` [S,D,P,H] is the block torch would draw (stomp.py:102)."""
-        P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
+        """-> [P,S_local,H,D]; ``eps`` [S,D,P,H] is the block torch would draw (stomp.py:102); with a sample split
+        every rank consumes its own slice of the sample axis."""
+        P, S, H, D = self.num_particles, self._s_local, self.n_support_points, self.d_state_opt
         if eps is None:
             eps = torch.randn(S, D, P, H, **self.tensor_args)
-        _lib.require_f32(eps)
-        assert eps.shape == (S, D, P, H)
-        _lib.check(_lib.lib().mpb_sample_stomp(_lib.ptr(self._L_R), _lib.ptr(self._particle_means), _lib.ptr(eps.contiguous()),
+        else:
+            _lib.require_f32(eps)
+            assert eps.shape == (self.num_samples, D, P, H)
+            eps = eps[self._offset:self._offset + S]
+        eps = eps.contiguous()
+        _lib.check(_lib.lib().mpb_sample_stomp(_lib.ptr(self._L_R), _lib.ptr(self._particle_means), _lib.ptr(eps),
                                                _lib.ptr(self.state_particles), P, S, H, D, _lib.stream_ptr()))
         return self.state_particles
 
@@ -95,7 +104,7 @@ class STOMP(OptimizationPlanner):
             self._update_distribution(self.costs, self.state_particles)
 
     def _sample_and_eval(self, eps=None, **observation):
-        P, S = self.num_particles, self.num_samples
+        P, S = self.num_particles, self._s_local
         self.state_particles = self.sample(eps=eps)
         flat = self.state_particles.flatten(0, 1)
         if hasattr(self.cost, 'eval') and hasattr(self.cost, '_build'):
@@ -105,9 +114,17 @@ class STOMP(OptimizationPlanner):
         return costs.view(P, S)
 
     def _update_distribution(self, costs, traj_particles):
-        P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
+        P, S, H, D = self.num_particles, self._s_local, self.n_support_points, self.d_state_opt
         _lib.require_f32(costs, traj_particles)
-        _lib.check(_lib.lib().mpb_softmax_update(_lib.ptr(costs.contiguous()), _lib.ptr(traj_particles.contiguous()),
+        if self.split.world > 1 or S > self.SPLIT_THRESHOLD:
+            # one problem with very many samples, or samples sharded over GPUs: partial records + fixed-order combine
+            traj_particles = traj_particles.contiguous()
+            r = split_softmax_update(costs, traj_particles, self._particle_means, self.temperature, self.lr, H, D,
+                                     SigmaR=self.Sigma, split=self.split, S_global=self.num_samples, weights_out=self._w_buf)
+            self._weights = r['weights'].view(P, S, 1, 1)
+            return
+        costs, traj_particles = costs.contiguous(), traj_particles.contiguous()     # named: temporaries must outlive the launch
+        _lib.check(_lib.lib().mpb_softmax_update(_lib.ptr(costs), _lib.ptr(traj_particles),
                                                  _lib.ptr(self._particle_means), _lib.ptr(self._w_buf), None,
                                                  self.temperature, self.lr, _lib.ptr(self.Sigma), P, S, H, D,
                                                  _lib.stream_ptr()))

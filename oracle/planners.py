@@ -179,3 +179,45 @@ def gpmp2_step(cost, means, delta, trust_region, step_size):
     costs = (b.transpose(1, 2) @ K @ b).reshape(B)
     return dict(A=A, b=b, K=K, JtJ=JtJ, g=g, d_theta=d_theta, costs=costs,
                 means=means + step_size * d_theta)
+
+
+# ------------------------------------------------------------------ sample-split update (multi-CTA / multi-GPU)
+def partial_record(costs, x, mu, temperature, sample_offset=0):
+    """Packed partial record of one block of samples:
+    [m, Z, cmin, argmin, v...] with m = max_s(-c_s/T), Z = sum_s exp(-c_s/T - m), v = sum_s exp(-c_s/T - m)(x_s - mu).
+    costs [P,S], x [P,S,M], mu [P,M] -> [P, 4+M] (float64; argmin stored as a number)."""
+    P, S = costs.shape
+    M = mu.shape[-1]
+    rec = torch.zeros(P, 4 + M, dtype=torch.float64)
+    if S == 0:
+        rec[:, 0] = -float('inf')
+        rec[:, 2] = float('inf')
+        rec[:, 3] = 2 ** 31 - 1
+        return rec
+    a = -costs.double() / temperature
+    m = a.max(dim=1).values
+    e = torch.exp(a - m.unsqueeze(1))
+    rec[:, 0] = m
+    rec[:, 1] = e.sum(1)
+    rec[:, 2] = costs.double().min(dim=1).values
+    rec[:, 3] = costs.argmin(dim=1).double() + sample_offset
+    rec[:, 4:] = (e.unsqueeze(-1) * (x.double() - mu.double().unsqueeze(1))).sum(1)
+    return rec
+
+
+def combine_records(recs, mu, step_size, Sigma_R=None, H=None):
+    """Fixed-order log-sum-exp merge of records [R,P,4+M] -> dict(means, grad, lse [P,2], best_cost, best_idx).
+    Ties of the minimum resolve to the lowest global sample index (torch.argmin semantics, mppi.py:166)."""
+    R, P, W = recs.shape
+    m = recs[:, :, 0].max(dim=0).values
+    scale = torch.exp(recs[:, :, 0] - m.unsqueeze(0))
+    scale[recs[:, :, 0] == -float('inf')] = 0
+    Z = (scale * recs[:, :, 1]).sum(0)
+    g = (scale.unsqueeze(-1) * recs[:, :, 4:]).sum(0) / Z.unsqueeze(-1)
+    cmin = recs[:, :, 2].min(dim=0).values
+    cand = torch.where(recs[:, :, 2] == cmin.unsqueeze(0), recs[:, :, 3], torch.full_like(recs[:, :, 3], float('inf')))
+    best_idx = cand.min(dim=0).values.long()
+    upd = g
+    if Sigma_R is not None:
+        upd = (Sigma_R.double() @ g.reshape(P, H, -1)).reshape(P, -1)
+    return dict(means=mu.double() + step_size * upd, grad=g, lse=torch.stack((m, Z), dim=1), best_cost=cmin, best_idx=best_idx)
