@@ -48,13 +48,19 @@ def main():
         U, X, c = p_split.optimize(opt_iters=1, eps=[eps], cost=cost, **obs)
         Uf, Xf, cf = p_full.optimize(opt_iters=1, eps=[eps], cost=cost_f, **obs)
         off, cnt = split.local_slice(N)
-        ok &= torch.equal(X, Xf[off:off + cnt]) and torch.equal(U, Uf[off:off + cnt])
-        ok &= close(c, cf[off:off + cnt], rtol=1e-6, atol=0)          # the batch-sum is reduced in a different order
-        ok &= int(p_split._best[1][0]) == int(p_full._best[1][0])
-        ok &= close(p_split._mean, p_full._mean)
-        ok &= close(p_split.best_traj, p_full.best_traj, rtol=0, atol=0) and float(p_split.best_cost) == float(p_split._best[0][0])
         gathered = split.all_gather_cat(p_split._mean.unsqueeze(0).contiguous())
-        ok &= all(torch.equal(gathered[0], gathered[r]) for r in range(world))
+        checks = dict(
+            rollouts=torch.equal(X, Xf[off:off + cnt]) and torch.equal(U, Uf[off:off + cnt]),
+            costs=close(c, cf[off:off + cnt], rtol=1e-6, atol=0),          # the batch sum is reduced in a different order
+            argmin=int(p_split._best[1][0]) == int(p_full._best[1][0]),
+            mean=close(p_split._mean, p_full._mean),
+            best_traj=torch.equal(p_split.best_traj, p_full.best_traj),
+            best_cost=close(p_split.best_cost, p_full.best_cost, rtol=1e-6, atol=0),
+            identical_across_ranks=all(torch.equal(gathered[0], gathered[r]) for r in range(world)))
+        if not all(checks.values()):
+            print(f'[rank {rank}] MPPI iter {it}: {checks} energy split {float(p_split._energy):.9g} full {float(p_full._energy):.9g} '
+                  f'max|dmean| {float((p_split._mean - p_full._mean).abs().max()):.3e}', flush=True)
+        ok &= all(checks.values())
         p_full._mean.copy_(p_split._mean)
     print(f'[rank {rank}] MPPI sample-split x{world}: {"ok" if ok else "MISMATCH"}', flush=True)
 
