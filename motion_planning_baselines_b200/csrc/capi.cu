@@ -1,6 +1,8 @@
 // C-ABI glue of libmpb_b200.so: error reporting, device queries and the fused iteration drivers.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 
 #include "mpb_common.cuh"
 
@@ -35,6 +37,25 @@ int sm_count() {
         cached_dev = dev;
     }
     return cached;
+}
+
+unsigned* sched_slot() {
+    constexpr int kMaxDev = 64, kSlots = 64;
+    static std::mutex mtx;
+    static unsigned* pool[kMaxDev] = {};
+    static std::atomic<unsigned> seq{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        if (!pool[dev]) {
+            unsigned* p = nullptr;
+            if (cudaMalloc(&p, kSlots * 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
+            if (cudaMemset(p, 0, kSlots * 2 * sizeof(unsigned)) != cudaSuccess) { cudaFree(p); return nullptr; }
+            pool[dev] = p;
+        }
+    }
+    return pool[dev] + 2 * (seq.fetch_add(1u) % kSlots);
 }
 
 }  // namespace mpb

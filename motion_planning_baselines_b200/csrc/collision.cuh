@@ -329,27 +329,34 @@ __device__ __forceinline__ void stage_robot(const mpb_robot_desc& r, const Robot
         lk[s] = r.sphere_link[s];
     }
     for (int i = threadIdx.x; i < r.q_dim * 12; i += blockDim.x) tf[i] = r.fixed_tf[i];
-    // per-link bounding spheres straight from global memory (tiny; one thread per link)
-    if ((int)threadIdx.x < r.q_dim) {
-        const int j = threadIdx.x;
+    // per-link bounding spheres: warp w handles links w, w+nwarps, ... with lanes over the sphere table, so the
+    // global-memory round trips overlap instead of forming one long dependent chain per link
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    for (int j = wid; j < r.q_dim; j += nwarp) {
         float mx = 0.f, my = 0.f, mz = 0.f;
         int n = 0, end = 0;
-        for (int s = 0; s < r.n_spheres; ++s) {
+        for (int s = lane; s < r.n_spheres; s += 32) {
             const int ls = r.sphere_link[s];
             if (ls == j) { mx += r.sphere_off[3 * s]; my += r.sphere_off[3 * s + 1]; mz += r.sphere_off[3 * s + 2]; ++n; }
-            if (ls <= j) end = s + 1;
+            if (ls <= j) end = max(end, s + 1);
         }
+        mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
+        n = __reduce_add_sync(MPB_FULL_MASK, n);
+        end = __reduce_max_sync(MPB_FULL_MASK, end);
         float R = 0.f;
         if (n > 0) {
             mx /= n; my /= n; mz /= n;
-            for (int s = 0; s < r.n_spheres; ++s) {
+            for (int s = lane; s < r.n_spheres; s += 32) {
                 if (r.sphere_link[s] != j) continue;
                 const float dx = r.sphere_off[3 * s] - mx, dy = r.sphere_off[3 * s + 1] - my, dz = r.sphere_off[3 * s + 2] - mz;
                 R = fmaxf(R, sqrtf(dx * dx + dy * dy + dz * dz) + r.sphere_r[s]);
             }
+            R = warp_max(R);
         }
-        reinterpret_cast<float4*>(smem + l.bound)[j] = make_float4(mx, my, mz, fmaf(R, 1.0001f, 1e-6f));
-        reinterpret_cast<int*>(smem + l.link_end)[j] = end;
+        if (lane == 0) {
+            reinterpret_cast<float4*>(smem + l.bound)[j] = make_float4(mx, my, mz, fmaf(R, 1.0001f, 1e-6f));
+            reinterpret_cast<int*>(smem + l.link_end)[j] = end;
+        }
     }
 }
 

@@ -35,6 +35,7 @@ struct CostArgs {
     unsigned char* free_flag;
     unsigned rows_off, queue_off, list_off;   // byte offsets into dynamic shared memory
     int row_stride;                    // floats
+    unsigned* sched;                   // [2] dynamic scheduler: next trajectory index, finished CTAs (self-resetting)
     int list_cap;                      // broad-phase list entries per warp (max primitives of one field)
 };
 
@@ -104,6 +105,31 @@ __device__ __forceinline__ void collide_block(unsigned char* smem, const FieldAr
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Next trajectory for this warp from the grid-wide counter (one atomic per warp and trajectory).
+__device__ __forceinline__ int next_traj(unsigned* ctr, int lane) {
+    unsigned v = 0;
+    if (lane == 0) v = atomicAdd(ctr, 1u);
+    return (int)__shfl_sync(MPB_FULL_MASK, v, 0);
+}
+
+// Asynchronous copy of one trajectory row into a warp's staging buffer (16-byte cp.async when aligned).
+__device__ __forceinline__ void issue_row(const float* xb, float* dst, int M, bool vec_ok, int lane) {
+    if (vec_ok) {
+        for (int i = lane; i < (M >> 2); i += 32) cp_async16(dst + 4 * i, xb + 4 * i);
+    } else {
+#pragma unroll 1
+        for (int i = lane; i < M; i += 32) dst[i] = __ldg(xb + i);
+    }
+    cp_async_commit();
+}
+
 template <int KIND, int G>
 __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_constant__ CostArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -113,7 +139,8 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* xs = reinterpret_cast<float*>(smem + a.rows_off) + (size_t)warp * a.row_stride;
+    float* xs = reinterpret_cast<float*>(smem + a.rows_off) + (size_t)warp * 2 * a.row_stride;   // current row
+    float* xnext = xs + a.row_stride;                                                             // row being prefetched
     WarpQueue q;
     q.base = a.queue_off + (unsigned)(warp * kQCap * 5 * sizeof(float));
     q.n = 0;
@@ -126,19 +153,15 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
     unsigned short* lbox = lsph + a.list_cap;
     const float point_r = (KIND == MPB_ROBOT_POINT) ? __ldg(a.robot.sphere_r) : 0.f;
 
-    for (int b = blockIdx.x * kWarps + warp; b < a.B; b += gridDim.x * kWarps) {
-        // ---- stage the trajectory row ------------------------------------------------------
-        const float* xb = a.x + (size_t)b * M;
-        if (vec_ok) {
-            const float4* src = reinterpret_cast<const float4*>(xb);
-            float4* dst = reinterpret_cast<float4*>(xs);
-#pragma unroll 2
-            for (int i = lane; i < (M >> 2); i += 32) dst[i] = __ldg(src + i);
-        } else {
-#pragma unroll 1
-            for (int i = lane; i < M; i += 32) xs[i] = __ldg(xb + i);
-        }
+    // Persistent warps pull trajectories from a grid-wide counter; the row of the NEXT trajectory streams into the
+    // second staging buffer (cp.async) while the current one is evaluated.
+    int b = next_traj(a.sched, lane);
+    if (b < a.B) issue_row(a.x + (size_t)b * M, xs, M, vec_ok, lane);
+    while (b < a.B) {
+        const int b_next = next_traj(a.sched, lane);
+        cp_async_wait_all();
         __syncwarp();
+        if (b_next < a.B) issue_row(a.x + (size_t)b_next * M, xnext, M, vec_ok, lane);
 
         double acc_gp = 0.0, acc_goal = 0.0, acc_is = 0.0;
         HingeAcc hacc;
@@ -309,16 +332,36 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
             if (a.free_flag) a.free_flag[b] = (unsigned char)(all_free ? 1 : 0);
         }
         __syncwarp();
+        float* t_ = xs; xs = xnext; xnext = t_;
+        b = b_next;
+    }
+    // the last CTA to finish re-arms the scheduler for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(a.sched + 1, 1u);
+        if (done == gridDim.x - 1) {
+            a.sched[0] = 0u;
+            a.sched[1] = 0u;
+            __threadfence();
+        }
     }
 }
 
 template <int KIND, int G>
-static cudaError_t launch(const CostArgs& a, int grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch(const CostArgs& a, int blocks_needed, size_t smem, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(cost_eval_kernel<KIND, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(cost_eval_kernel<KIND, G>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
+    // persistent grid: exactly one wave of resident CTAs; trajectories are handed out dynamically
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cost_eval_kernel<KIND, G>, kWarps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int resident = sm_count() * per_sm;
+    const int grid = blocks_needed < resident ? blocks_needed : resident;
     cost_eval_kernel<KIND, G><<<grid, kWarps * 32, smem, st>>>(a);
     return cudaSuccess;
 }
@@ -369,7 +412,7 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
     off = layout_robot(*robot, a.rl, off);
     a.row_stride = (a.M + 3) & ~3;
     a.rows_off = off;
-    off += (unsigned)(kWarps * a.row_stride * sizeof(float));
+    off += (unsigned)(kWarps * 2 * a.row_stride * sizeof(float));       // current + prefetched row per warp
     a.queue_off = off;
     off += (unsigned)(kWarps * kQCap * 5 * sizeof(float));
     a.list_cap = 8;
@@ -383,13 +426,15 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
     const size_t smem = off;
     MPB_REQUIRE(smem <= 227 * 1024, "mpb_cost_eval: %zu bytes of shared memory needed (H*D too large or too many primitives)", smem);
 
+    MPB_REQUIRE(B <= (1 << 30), "mpb_cost_eval: batch too large (%d)", B);
+    a.sched = sched_slot();
+    if (!a.sched) { set_error("mpb_cost_eval: could not allocate the scheduler counters"); return MPB_ECUDA; }
     const int blocks_needed = (B + kWarps - 1) / kWarps;
-    const int grid = blocks_needed < sm_count() * 8 ? blocks_needed : sm_count() * 8;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = (robot->kind == MPB_ROBOT_POINT) ? launch<MPB_ROBOT_POINT, 1>(a, grid, smem, st)
-                                                     : launch<MPB_ROBOT_CHAIN, 4>(a, grid, smem, st);
+    cudaError_t e = (robot->kind == MPB_ROBOT_POINT) ? launch<MPB_ROBOT_POINT, 1>(a, blocks_needed, smem, st)
+                                                     : launch<MPB_ROBOT_CHAIN, 4>(a, blocks_needed, smem, st);
     if (e != cudaSuccess) {
-        set_error("mpb_cost_eval: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        set_error("mpb_cost_eval: launch configuration failed: %s", cudaGetErrorString(e));
         return MPB_ECUDA;
     }
     return check_launch("mpb_cost_eval");

@@ -167,18 +167,37 @@ __global__ void __launch_bounds__(256) sample_stomp_kernel(const float* __restri
     }
 }
 
-// y[p,:] = Sigma_inv @ mu[p,:] for banded Sigma_inv, fp64 accumulation.
-__global__ void prior_matvec_kernel(const float* __restrict__ Sinv, const float* __restrict__ mu, float* __restrict__ y,
-                                    int P, int M, int hbw) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P * M) return;
-    const int p = idx / M, i = idx - p * M;
+// y[p,:] = Sigma_inv @ mu[p,:] for banded Sigma_inv, fp64 accumulation.  Sigma_inv = A^T Q^-1 A is symmetric, so
+// thread i walks COLUMN i of the band (Sigma_inv[j][i], j = i-hbw..i+hbw): consecutive threads read consecutive
+// addresses (coalesced) where walking row i would stride by M.  A CTA serves kMvP particles at once (their mu rows
+// staged in shared memory) so that every band entry is fetched once per kMvP particles.
+constexpr int kMvP = 8;
+__global__ void __launch_bounds__(256) prior_matvec_kernel(const float* __restrict__ Sinv, const float* __restrict__ mu,
+                                                           float* __restrict__ y, int P, int M, int hbw) {
+    extern __shared__ __align__(16) float ms[];
+    const int p0 = blockIdx.y * kMvP;
+    const int i0 = blockIdx.x * blockDim.x;
+    const int lo = max(0, i0 - hbw), hi = min(M - 1, i0 + (int)blockDim.x - 1 + hbw);
+    const int span = blockDim.x + 2 * hbw;
+    for (int q = 0; q < kMvP; ++q) {
+        const int p = min(p0 + q, P - 1);
+        for (int j = lo + threadIdx.x; j <= hi; j += blockDim.x) ms[q * span + j - lo] = __ldg(mu + (size_t)p * M + j);
+    }
+    __syncthreads();
+    const int i = i0 + threadIdx.x;
+    if (i >= M) return;
     const int j0 = max(0, i - hbw), j1 = min(M - 1, i + hbw);
-    const float* row = Sinv + (size_t)i * M;
-    const float* m = mu + (size_t)p * M;
-    double acc = 0.0;
-    for (int j = j0; j <= j1; ++j) acc = fma((double)__ldg(row + j), (double)__ldg(m + j), acc);
-    y[idx] = (float)acc;
+    double acc[kMvP];
+#pragma unroll
+    for (int q = 0; q < kMvP; ++q) acc[q] = 0.0;
+    for (int j = j0; j <= j1; ++j) {
+        const double sv = (double)__ldg(Sinv + (size_t)j * M + i);
+#pragma unroll
+        for (int q = 0; q < kMvP; ++q) acc[q] = fma(sv, (double)ms[q * span + j - lo], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < kMvP; ++q)
+        if (p0 + q < P) y[(size_t)(p0 + q) * M + i] = (float)acc[q];
 }
 
 }  // namespace mpb
@@ -217,7 +236,10 @@ extern "C" int mpb_prior_matvec(const float* Sigma_inv, const float* mu, float* 
     MPB_REQUIRE(Sigma_inv && mu && y, "mpb_prior_matvec: null pointer");
     MPB_REQUIRE(P >= 0 && M >= 1 && half_bw >= 0, "mpb_prior_matvec: bad sizes");
     if (P == 0) return MPB_OK;
-    const int n = P * M;
-    prior_matvec_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(Sigma_inv, mu, y, P, M, half_bw);
+    MPB_REQUIRE(P <= 65535 * kMvP, "mpb_prior_matvec: too many particles per call");
+    dim3 grid((M + 255) / 256, (P + kMvP - 1) / kMvP);
+    const size_t smem = (size_t)kMvP * (256 + 2 * half_bw) * sizeof(float);
+    MPB_REQUIRE(smem <= 48 * 1024, "mpb_prior_matvec: half bandwidth %d too large", half_bw);
+    prior_matvec_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(Sigma_inv, mu, y, P, M, half_bw);
     return check_launch("mpb_prior_matvec");
 }

@@ -24,13 +24,19 @@ namespace mpb {
 
 constexpr int TC_BM = 128;          // rows of eps per tile  (UMMA M)
 constexpr int TC_BN = 256;          // columns of x per tile (UMMA N, rows of L)
-constexpr int TC_BK = 32;           // k per stage: 32 fp32 = one 128-byte swizzle row
-constexpr int TC_STAGES = 2;
+#ifndef MPB_TC_BK
+#define MPB_TC_BK 16
+#endif
+constexpr int TC_BK = MPB_TC_BK;    // k per stage: 32 fp32 = one 128-byte swizzle row, 16 fp32 = one 64-byte swizzle row
+constexpr int TC_STAGES = (TC_BK == 32) ? 2 : 4;      // 96 KiB / 48 KiB per stage -> 192 KiB of operand ring either way
+constexpr int TC_SWIZZLE_BYTES = TC_BK * 4;           // 128 | 64
 constexpr int TC_THREADS = 384;
 constexpr uint32_t A_TILE_BYTES = TC_BM * TC_BK * 4;      // 16 KiB
 constexpr uint32_t B_TILE_BYTES = TC_BN * TC_BK * 4;      // 32 KiB
 constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;     // A_hi | A_lo | B_hi | B_lo
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert((3 * TC_STAGES + 4) * 8 + 4 <= 256, "barrier block too small");
+static_assert((A_TILE_BYTES / 16) % 128 == 0, "transform loop assumes a multiple of 128 float4 per tile");
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,14 +109,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major operand tile with 128-byte swizzle: rows of 128 B, 8-row (1024 B) swizzle atoms stacked along M/N.
+// K-major operand tile with 128-byte (64-byte) swizzle: rows of 128 B (64 B), 8-row swizzle atoms of 1024 B (512 B)
+// stacked along M/N.
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address
     d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)((8 * TC_SWIZZLE_BYTES) >> 4) << 32;   // stride byte offset: 8 rows x swizzle row
     d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+    d |= (uint64_t)(TC_SWIZZLE_BYTES == 128 ? 2 : 4) << 61;   // SWIZZLE_128B | SWIZZLE_64B
     return d;
 }
 // kind::tf32, fp32 accumulate, both operands K-major, M x N.
@@ -131,12 +138,12 @@ sample_gp_tc_kernel(const __grid_constant__ CUtensorMap map_eps, const __grid_co
     extern __shared__ unsigned char smem_raw[];
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * STAGE_BYTES);
-    uint64_t* full_raw = bars;                      // [2] TMA landed
-    uint64_t* full_xf = bars + 2;                   // [2] eps split done
-    uint64_t* empty = bars + 4;                     // [2] MMAs that read the stage completed
-    uint64_t* tmem_full = bars + 6;                 // [2] accumulator ready
-    uint64_t* tmem_empty = bars + 8;                // [2] accumulator drained
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* full_raw = bars;                      // [STAGES] TMA landed
+    uint64_t* full_xf = bars + TC_STAGES;           // [STAGES] eps split done
+    uint64_t* empty = bars + 2 * TC_STAGES;         // [STAGES] MMAs that read the stage completed
+    uint64_t* tmem_full = bars + 3 * TC_STAGES;     // [2] accumulator ready
+    uint64_t* tmem_empty = bars + 3 * TC_STAGES + 2;    // [2] accumulator drained
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -338,7 +345,8 @@ static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, in
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, TC_SWIZZLE_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
