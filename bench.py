@@ -47,6 +47,21 @@ def peaks():
                 source='fallback (B200_PROFILING.md)')
 
 
+def ncu_traffic(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json), or None."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    try:
+        table = json.load(open(path))
+    except Exception:
+        return None
+    for key, rec in table.items():
+        if key in kernel_name:
+            return dict(bytes=rec['dram_read_bytes'] + rec['dram_write_bytes'], unit='B', source=rec.get('source'),
+                        algorithmic_bytes=rec.get('algorithmic_bytes'))
+    return None
+
+
 class ClockSampler(threading.Thread):
     """Polls NVML for SM clock and throttle reasons while the timed region runs."""
 
@@ -184,6 +199,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-particles', type=int, default=32, help='particles per step of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-other-configs', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -339,7 +355,7 @@ def main():
         kernels.append(k)
     dom = max((k for k in kernels if 'achieved' in k), key=lambda k: k['ms'])
     roofline = dict(bound=dom['bound'], achieved=dom['achieved'], peak=dom['peak'], unit=dom['unit'], frac=dom['frac'],
-                    traffic=None, kernel=dom['kernel'], ms_per_launch=dom['ms'],
+                    traffic=ncu_traffic(dom['kernel']), kernel=dom['kernel'], ms_per_launch=dom['ms'],
                     peak_source=('nominal FP32 FMA rate 148 SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json holds only '
                                  'HBM and bf16 tensor peaks; this kernel is FP32-issue bound)') if dom['bound'] == 'fp32' else dom.get('note', pk['source']),
                     algorithmic_flop_per_sample=flops[2] if 'K2' in dom['kernel'] else flops[0], kernels=kernels)
@@ -353,6 +369,15 @@ def main():
                               "step's noise upload overlaps this step's kernels",
                          device_noise_ms_per_step=ms_e2e_dev / Ke),
                 roofline=roofline, collision_free_fraction_last_step=free_frac)
+    if world == 1 and not args.no_other_configs:
+        # the other BASELINE.json configs ("ms per planner iter"), informational: see bench_configs.py
+        del planner, eps_bufs, d_eps
+        torch.cuda.empty_cache()
+        try:
+            import bench_configs
+            line['other_configs'] = bench_configs.run_other_configs(dev, quick=True)
+        except Exception as exc:       # never lose the headline line to an informational extra
+            line['other_configs'] = dict(error=repr(exc))
     if not args.no_cpu_baseline:
         torch.cuda.empty_cache()
         r = cpu_reference_run(args.cpu_particles, steps=3, warmup=1, faithful=True)

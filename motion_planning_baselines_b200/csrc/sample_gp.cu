@@ -177,27 +177,37 @@ __global__ void __launch_bounds__(256) prior_matvec_kernel(const float* __restri
     extern __shared__ __align__(16) float ms[];
     const int p0 = blockIdx.y * kMvP;
     const int i0 = blockIdx.x * blockDim.x;
-    const int lo = max(0, i0 - hbw), hi = min(M - 1, i0 + (int)blockDim.x - 1 + hbw);
+    const int lo_j = max(0, i0 - hbw), hi_j = min(M - 1, i0 + (int)blockDim.x - 1 + hbw);
     const int span = blockDim.x + 2 * hbw;
     for (int q = 0; q < kMvP; ++q) {
         const int p = min(p0 + q, P - 1);
-        for (int j = lo + threadIdx.x; j <= hi; j += blockDim.x) ms[q * span + j - lo] = __ldg(mu + (size_t)p * M + j);
+        for (int j = lo_j + threadIdx.x; j <= hi_j; j += blockDim.x) ms[q * span + j - lo_j] = __ldg(mu + (size_t)p * M + j);
     }
     __syncthreads();
     const int i = i0 + threadIdx.x;
     if (i >= M) return;
     const int j0 = max(0, i - hbw), j1 = min(M - 1, i + hbw);
-    double acc[kMvP];
+    // Terms reach 1e7 and cancel to O(1): accumulate in double-float (hi + lo fp32 pairs, error-free TwoProd / TwoSum).
+    // Native FP64 issues at 1/32 of the FP32 rate on this part and made this kernel FP64-pipe bound.
+    float hi[kMvP], lo[kMvP];
 #pragma unroll
-    for (int q = 0; q < kMvP; ++q) acc[q] = 0.0;
+    for (int q = 0; q < kMvP; ++q) hi[q] = lo[q] = 0.f;
     for (int j = j0; j <= j1; ++j) {
-        const double sv = (double)__ldg(Sinv + (size_t)j * M + i);
+        const float sv = __ldg(Sinv + (size_t)j * M + i);
 #pragma unroll
-        for (int q = 0; q < kMvP; ++q) acc[q] = fma(sv, (double)ms[q * span + j - lo], acc[q]);
+        for (int q = 0; q < kMvP; ++q) {
+            const float m = ms[q * span + j - lo_j];
+            const float p = __fmul_rn(sv, m);
+            const float e = fmaf(sv, m, -p);                      // sv*m = p + e exactly
+            const float t = __fadd_rn(hi[q], p);
+            const float z = __fsub_rn(t, hi[q]);
+            lo[q] = __fadd_rn(lo[q], __fadd_rn(__fadd_rn(__fsub_rn(hi[q], __fsub_rn(t, z)), __fsub_rn(p, z)), e));
+            hi[q] = t;
+        }
     }
 #pragma unroll
     for (int q = 0; q < kMvP; ++q)
-        if (p0 + q < P) y[(size_t)(p0 + q) * M + i] = (float)acc[q];
+        if (p0 + q < P) y[(size_t)(p0 + q) * M + i] = __fadd_rn(hi[q], lo[q]);
 }
 
 }  // namespace mpb
