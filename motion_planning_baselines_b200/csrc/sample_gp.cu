@@ -192,8 +192,15 @@ __global__ void __launch_bounds__(256) prior_matvec_kernel(const float* __restri
     float hi[kMvP], lo[kMvP];
 #pragma unroll
     for (int q = 0; q < kMvP; ++q) hi[q] = lo[q] = 0.f;
-    for (int j = j0; j <= j1; ++j) {
-        const float sv = __ldg(Sinv + (size_t)j * M + i);
+    constexpr int kU = 6;                // band entries fetched together: the loads are independent, the sums are not
+    for (int jb = j0; jb <= j1; jb += kU) {
+        float svv[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) svv[u] = (jb + u <= j1) ? __ldg(Sinv + (size_t)(jb + u) * M + i) : 0.f;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+        const int j = min(jb + u, j1);
+        const float sv = svv[u];
 #pragma unroll
         for (int q = 0; q < kMvP; ++q) {
             const float m = ms[q * span + j - lo_j];
@@ -203,6 +210,7 @@ __global__ void __launch_bounds__(256) prior_matvec_kernel(const float* __restri
             const float z = __fsub_rn(t, hi[q]);
             lo[q] = __fadd_rn(lo[q], __fadd_rn(__fadd_rn(__fsub_rn(hi[q], __fsub_rn(t, z)), __fsub_rn(p, z)), e));
             hi[q] = t;
+        }
         }
     }
 #pragma unroll

@@ -8,14 +8,20 @@
 // whose dropped term E_lo*L_lo is O(2^-22) relative.
 //
 // Structure (one persistent CTA per SM, 384 threads, warp-specialised):
-//   warp 0      TMA producer: cp.async.bulk.tensor loads of the raw eps tile [128 x 32] and of the pre-split
-//               factor tiles L_hi / L_lo [256 x 32] (128-byte swizzle) into a 2-stage shared-memory ring
-//   warps 4-7   transform: split the eps tile in place into hi (low 13 mantissa bits cleared) and lo = e - hi
-//   warp 1      MMA issuer: one elected thread issues 12 tcgen05.mma.kind::tf32 per stage (4 k-steps x 3
-//               products), accumulators [128 x 256] fp32 in TMEM, double buffered (2 x 256 columns)
+//   warp 0      TMA producer: cp.async.bulk.tensor loads of the raw eps tile [128 x 16] and of the pre-split factor
+//               tiles L_hi / L_lo [224 x 16] (64-byte swizzle) into a 6-stage shared-memory ring (36 KiB per stage)
+//   warps 4-7   transform: each thread owns one eps row of the tile, splits it into hi (low 13 mantissa bits cleared)
+//               and lo = e - hi and writes both with tcgen05.st into a 2-slot A-operand ring in TENSOR MEMORY
+//   warp 1      MMA issuer: one elected thread issues 6 tcgen05.mma.kind::tf32 per stage (2 k-steps x 3 products) with
+//               the A operand read from TMEM and B from shared memory; accumulators [128 x 224] fp32 in TMEM, double
+//               buffered (columns 0-223 and 224-447; the A ring lives in columns 448-511)
 //   warps 8-11  epilogue: tcgen05.ld the accumulator, add mu_p, store the row of x (particle-major)
+// Why A sits in TMEM: with both operands in shared memory the kernel was bound by shared-memory bandwidth (every
+// M128 x N256 x K8 tf32 MMA re-reads 4 KiB of A and 8 KiB of B; three products per k-step), ncu: tensor pipe 47 % busy.
+// Keeping E_hi / E_lo in tensor memory removes the A reads and the transform's write-back from the shared-memory port.
 // L is lower triangular, so k-blocks right of the diagonal block are never loaded or multiplied.
-// Pipelines: smem full/empty mbarriers (TMA -> transform -> MMA -> TMA) and TMEM full/empty (MMA <-> epilogue).
+// Pipelines: smem full/empty mbarriers (TMA -> transform/MMA -> TMA), A-ring full/empty (transform <-> MMA) and TMEM
+// accumulator full/empty (MMA <-> epilogue).
 #include <cuda.h>
 
 #include "mpb_common.cuh"
@@ -23,20 +29,21 @@
 namespace mpb {
 
 constexpr int TC_BM = 128;          // rows of eps per tile  (UMMA M)
-constexpr int TC_BN = 256;          // columns of x per tile (UMMA N, rows of L)
-#ifndef MPB_TC_BK
-#define MPB_TC_BK 16
-#endif
-constexpr int TC_BK = MPB_TC_BK;    // k per stage: 32 fp32 = one 128-byte swizzle row, 16 fp32 = one 64-byte swizzle row
-constexpr int TC_STAGES = (TC_BK == 32) ? 2 : 4;      // 96 KiB / 48 KiB per stage -> 192 KiB of operand ring either way
-constexpr int TC_SWIZZLE_BYTES = TC_BK * 4;           // 128 | 64
+constexpr int TC_BN = 224;          // columns of x per tile (UMMA N, rows of L): 896 = 4 x 224, 2 x 224 + 64 = 512 TMEM columns
+constexpr int TC_BK = 16;           // k per stage: 16 fp32 = one 64-byte swizzle row
+constexpr int TC_STAGES = 6;
+constexpr int TC_ASLOTS = 2;        // A-operand slots in tensor memory (hi | lo, 2 x TC_BK columns each)
+constexpr int TC_SWIZZLE_BYTES = TC_BK * 4;
 constexpr int TC_THREADS = 384;
-constexpr uint32_t A_TILE_BYTES = TC_BM * TC_BK * 4;      // 16 KiB
-constexpr uint32_t B_TILE_BYTES = TC_BN * TC_BK * 4;      // 32 KiB
-constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;     // A_hi | A_lo | B_hi | B_lo
+constexpr uint32_t A_TILE_BYTES = TC_BM * TC_BK * 4;      // 8 KiB   raw eps
+constexpr uint32_t B_TILE_BYTES = TC_BN * TC_BK * 4;      // 14 KiB  per factor part
+constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;         // eps | L_hi | L_lo  = 36 KiB
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-static_assert((3 * TC_STAGES + 4) * 8 + 4 <= 256, "barrier block too small");
-static_assert((A_TILE_BYTES / 16) % 128 == 0, "transform loop assumes a multiple of 128 float4 per tile");
+constexpr uint32_t TC_ACC_COLS = 2 * TC_BN;               // 448: two accumulators
+constexpr uint32_t TC_A_COL0 = TC_ACC_COLS;               // A ring starts here (64 columns)
+static_assert(TC_ACC_COLS + TC_ASLOTS * 2 * TC_BK <= 512, "tensor memory budget");
+static_assert((2 * TC_STAGES + 2 * TC_ASLOTS + 4) * 8 + 4 <= 256, "barrier block too small");
+static_assert(STAGE_BYTES % 1024 == 0 && A_TILE_BYTES % 1024 == 0 && B_TILE_BYTES % 512 == 0, "swizzle atom alignment");
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,9 +94,31 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T : A operand read from tensor memory (128 lanes x 8 columns of 32-bit values per k-step)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -138,20 +167,24 @@ sample_gp_tc_kernel(const __grid_constant__ CUtensorMap map_eps, const __grid_co
     extern __shared__ unsigned char smem_raw[];
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * STAGE_BYTES);
-    uint64_t* full_raw = bars;                      // [STAGES] TMA landed
-    uint64_t* full_xf = bars + TC_STAGES;           // [STAGES] eps split done
-    uint64_t* empty = bars + 2 * TC_STAGES;         // [STAGES] MMAs that read the stage completed
-    uint64_t* tmem_full = bars + 3 * TC_STAGES;     // [2] accumulator ready
-    uint64_t* tmem_empty = bars + 3 * TC_STAGES + 2;    // [2] accumulator drained
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 4);
+    uint64_t* full = bars;                                   // [STAGES] TMA landed (eps + L_hi + L_lo)
+    uint64_t* empty = bars + TC_STAGES;                      // [STAGES] MMAs that read the stage completed
+    uint64_t* a_full = bars + 2 * TC_STAGES;                 // [ASLOTS] E_hi | E_lo written to tensor memory
+    uint64_t* a_empty = a_full + TC_ASLOTS;                  // [ASLOTS] MMAs that read the A slot completed
+    uint64_t* tmem_full = a_empty + TC_ASLOTS;               // [2] accumulator ready
+    uint64_t* tmem_empty = tmem_full + 2;                    // [2] accumulator drained
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(&full_raw[s], 1);
-            mbar_init(&full_xf[s], 4);
+            mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < TC_ASLOTS; ++s) {
+            mbar_init(&a_full[s], 4);
+            mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
@@ -188,10 +221,10 @@ sample_gp_tc_kernel(const __grid_constant__ CUtensorMap map_eps, const __grid_co
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* st = tiles + stage * STAGE_BYTES;
-                    mbar_expect_tx(&full_raw[stage], A_TILE_BYTES + 2 * B_TILE_BYTES);
-                    tma_load_2d(&map_eps, &full_raw[stage], st, kb * TC_BK, r * TC_BM);
-                    tma_load_2d(&map_lhi, &full_raw[stage], st + 2 * A_TILE_BYTES, kb * TC_BK, jc * TC_BN);
-                    tma_load_2d(&map_llo, &full_raw[stage], st + 2 * A_TILE_BYTES + B_TILE_BYTES, kb * TC_BK, jc * TC_BN);
+                    mbar_expect_tx(&full[stage], A_TILE_BYTES + 2 * B_TILE_BYTES);
+                    tma_load_2d(&map_eps, &full[stage], st, kb * TC_BK, r * TC_BM);
+                    tma_load_2d(&map_lhi, &full[stage], st + A_TILE_BYTES, kb * TC_BK, jc * TC_BN);
+                    tma_load_2d(&map_llo, &full[stage], st + A_TILE_BYTES + B_TILE_BYTES, kb * TC_BK, jc * TC_BN);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -199,10 +232,8 @@ sample_gp_tc_kernel(const __grid_constant__ CUtensorMap map_eps, const __grid_co
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
+            int stage = 0, slot = 0, acc = 0;
+            uint32_t phase = 0, slot_phase = 0, acc_phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 int r, jc, n_cols, n_kb;
                 tile_coords(t, r, jc, n_cols, n_kb);
@@ -211,54 +242,68 @@ sample_gp_tc_kernel(const __grid_constant__ CUtensorMap map_eps, const __grid_co
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
                 for (int kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait(&full_xf[stage], phase);
+                    mbar_wait(&full[stage], phase);                // L_hi / L_lo tiles landed
+                    mbar_wait(&a_full[slot], slot_phase);          // E_hi / E_lo in tensor memory
                     tc_fence_after();
                     const uint32_t st = smem_u32(tiles + stage * STAGE_BYTES);
-                    const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + A_TILE_BYTES);
-                    const uint64_t b_hi = make_sw128_desc(st + 2 * A_TILE_BYTES);
-                    const uint64_t b_lo = make_sw128_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                    const uint64_t b_hi = make_sw128_desc(st + A_TILE_BYTES);
+                    const uint64_t b_lo = make_sw128_desc(st + A_TILE_BYTES + B_TILE_BYTES);
+                    const uint32_t a_hi = tmem_base + TC_A_COL0 + (uint32_t)(slot * 2 * TC_BK);
+                    const uint32_t a_lo = a_hi + TC_BK;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);      // +32 B per k-step inside the swizzle row
-                        umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, (kb | k) ? 1u : 0u);   // small terms first
-                        umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
-                        umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+                        umma_tf32_ts(d_tmem, a_lo + 8 * k, b_hi + koff, idesc, (kb | k) ? 1u : 0u);   // small terms first
+                        umma_tf32_ts(d_tmem, a_hi + 8 * k, b_lo + koff, idesc, 1u);
+                        umma_tf32_ts(d_tmem, a_hi + 8 * k, b_hi + koff, idesc, 1u);
                     }
                     umma_commit(&empty[stage]);
+                    umma_commit(&a_empty[slot]);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    if (++slot == TC_ASLOTS) { slot = 0; slot_phase ^= 1; }
                 }
                 umma_commit(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 4 && warp < 8) {
-        // ================================ transform: eps -> hi | lo =====================
-        const int tid = threadIdx.x - 128;          // 0..127
-        int stage = 0;
-        uint32_t phase = 0;
+        // ================================ transform: eps row -> E_hi | E_lo in tensor memory =====================
+        const int m = threadIdx.x - 128;             // row of the tile = TMEM lane (warp q may access lanes 32q..32q+31)
+        const int q = warp & 3;
+        // 64-byte swizzle of the TMA tile: 16-byte chunk c of row m sits at physical chunk c ^ ((m >> 1) & 3)
+        const uint32_t row_off = (uint32_t)((m >> 3) * 512 + (m & 7) * 64);
+        const int sw = (m >> 1) & 3;
+        int stage = 0, slot = 0;
+        uint32_t phase = 0, slot_phase = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             int r, jc, n_cols, n_kb;
             tile_coords(t, r, jc, n_cols, n_kb);
             for (int kb = 0; kb < n_kb; ++kb) {
-                mbar_wait(&full_raw[stage], phase);
-                float4* hi = reinterpret_cast<float4*>(tiles + stage * STAGE_BYTES);
-                float4* lo = reinterpret_cast<float4*>(tiles + stage * STAGE_BYTES + A_TILE_BYTES);
+                mbar_wait(&full[stage], phase);
+                const unsigned char* rowp = tiles + stage * STAGE_BYTES + row_off;
+                float hi[16], lo[16];
 #pragma unroll
-                for (int i = 0; i < (int)(A_TILE_BYTES / 16 / 128); ++i) {       // 8 x float4 per thread
-                    const int idx = i * 128 + tid;
-                    const float4 v = hi[idx];
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-                    hi[idx] = h;
-                    lo[idx] = l;
+                for (int c = 0; c < 4; ++c) {
+                    const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ sw) << 4));
+                    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float h = __uint_as_float(__float_as_uint(e[i]) & 0xffffe000u);
+                        hi[4 * c + i] = h;
+                        lo[4 * c + i] = e[i] - h;
+                    }
                 }
-                fence_async_proxy();
+                mbar_wait(&a_empty[slot], slot_phase ^ 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + TC_A_COL0 + (uint32_t)(slot * 2 * TC_BK);
+                tmem_st16(taddr, hi);
+                tmem_st16(taddr + TC_BK, lo);
+                tmem_wait_st();
+                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full_xf[stage]);
+                if (lane == 0) mbar_arrive(&a_full[slot]);
                 if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                if (++slot == TC_ASLOTS) { slot = 0; slot_phase ^= 1; }
             }
         }
     } else if (warp >= 8) {
