@@ -23,7 +23,7 @@ class GPMP2(OptimizationPlanner):
                  num_particles_per_goal=None, opt_iters=None, dt=None, start_state=None, step_size=1.,
                  multi_goal_states=None, initial_particle_means=None, sigma_start_init=None, sigma_start_sample=None,
                  sigma_goal_init=None, sigma_goal_sample=None, sigma_gp_init=None, solver_params=None,
-                 stop_criteria=None, **kwargs):
+                 stop_criteria=None, batch_split=None, **kwargs):
         super().__init__(name='GPMP', n_dof=n_dof, n_support_points=n_support_points,
                          num_particles_per_goal=num_particles_per_goal, opt_iters=opt_iters, dt=dt,
                          start_state=start_state, initial_particle_means=initial_particle_means,
@@ -57,6 +57,10 @@ class GPMP2(OptimizationPlanner):
             multi_goal_states=None if multi_goal_states is None else multi_goal_states.to(**self.tensor_args),
             num_particles_per_goal=num_particles_per_goal, **kwargs)
         self._ws = None
+        # batch_split (update.SampleSplit): the particles of ONE batch are sharded over the ranks of a process group.
+        # Everything is independent per trajectory except the trust-region term, which uses the mean over the WHOLE
+        # batch of diag(A^T K A) (gpmp2.py:366, quirk B10): an [H*d] all-reduce per step keeps the result identical.
+        self.batch_split = batch_split
         self.reset(initial_particle_means=initial_particle_means)
 
     def set_prior_factors(self):
@@ -114,6 +118,14 @@ class GPMP2(OptimizationPlanner):
         trust = bool(self.solver_params.get('trust_region', False))
         _lib.check(lib.mpb_gpmp2_linearize(_lib.ptr(self._particle_means), B, H, C.byref(self.robot.desc), fields, nf,
                                            _lib.ptr(w['err']), _lib.ptr(w['hobs']), _lib.ptr(w['dm']) if trust else None, st))
+        if trust and self.batch_split is not None and self.batch_split.world > 1:
+            import torch.distributed as dist
+            # local mean -> global mean: sum of (local mean * local count) over ranks / global count
+            cnt = torch.tensor([float(B)], device=w['dm'].device, dtype=torch.float64)
+            w['dm'].mul_(float(B))
+            dist.all_reduce(w['dm'], group=self.batch_split.group)
+            dist.all_reduce(cnt, group=self.batch_split.group)
+            w['dm'].div_(cnt)
         inv_s2 = (C.c_float * max(1, nf))(*[fields[i].inv_sigma2 for i in range(nf)])
         _lib.check(lib.mpb_gpmp2_solve(_lib.ptr(self._particle_means), B, H, d, C.byref(gp), _lib.ptr(w['err']), _lib.ptr(w['hobs']),
                                        inv_s2, nf, _lib.ptr(w['dm']) if trust else None, float(self.solver_params['delta']),

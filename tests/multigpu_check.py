@@ -89,7 +89,34 @@ def main():
         ok2 &= all(torch.equal(gathered[0], gathered[r]) for r in range(world))
         s_full._particle_means.copy_(s_split._particle_means)
     print(f'[rank {rank}] STOMP sample-split x{world}: {"ok" if ok2 else "MISMATCH"}', flush=True)
-    flag = torch.tensor([int(ok and ok2)], device=dev['device'])
+    # ---- GPMP2 (trust region = batch mean, quirk B10) and CHOMP (global-P smoothness, quirk B1): particles sharded ------
+    from test_gpu_planners import _chomp, _gpmp2
+    from conftest import load_golden
+    import numpy as np
+    g = load_golden('gpmp2_pm2d')
+    Bg, H, dd = 64 * world, 32, 2
+    cfg = configs.config('C2')
+    gen_c = torch.Generator().manual_seed(5)
+    w = torch.linspace(0, 1, H).view(1, H, 1)
+    xg = torch.zeros(Bg, H, 2 * dd)
+    xg[..., :dd] = torch.tensor(cfg['start']) * (1 - w) + torch.tensor(cfg['goal']) * w + 0.25 * torch.randn(Bg, H, dd, generator=gen_c).cumsum(1) / np.sqrt(H)
+    off, cnt = split.local_slice(Bg)
+    full = _gpmp2(g, dev, means=xg, P=Bg, H=H)
+    part = _gpmp2(g, dev, means=xg[off:off + cnt], P=cnt, H=H)
+    part.batch_split = split
+    ok3 = True
+    for it in range(2):
+        tf = full.optimize(opt_iters=1)
+        tp = part.optimize(opt_iters=1)
+        ok3 &= close(tp, tf[off:off + cnt], rtol=1e-6, atol=1e-7)
+    gc = load_golden('chomp_pm2d')
+    gc2 = dict(gc, meta=dict(gc['meta'], H=H))
+    cf = _chomp(gc2, dev, P=Bg, x0=xg)
+    cp = _chomp(gc2, dev, P=cnt, x0=xg[off:off + cnt])
+    cp.num_particles_global = Bg
+    ok3 &= torch.equal(cp.optimize(opt_iters=5), cf.optimize(opt_iters=5)[off:off + cnt])
+    print(f'[rank {rank}] GPMP2 / CHOMP particle-split x{world}: {"ok" if ok3 else "MISMATCH"}', flush=True)
+    flag = torch.tensor([int(ok and ok2 and ok3)], device=dev['device'])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     if rank == 0:
