@@ -378,7 +378,7 @@ def main():
             line['other_configs'] = bench_configs.run_other_configs(dev, quick=True)
         except Exception as exc:       # never lose the headline line to an informational extra
             line['other_configs'] = dict(error=repr(exc))
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:     # the CPU baseline is reported at N=1 only (rank 0)
         torch.cuda.empty_cache()
         r = cpu_reference_run(args.cpu_particles, steps=3, warmup=1, faithful=True)
         line['cpu_baseline'] = dict(
