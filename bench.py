@@ -219,7 +219,19 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback for the product path)'
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # NCCL prints its version banner to STDOUT on the first collective; stdout must carry exactly one JSON line,
+        # so file descriptor 1 points at stderr until the communicator is up.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     dev = dict(device=torch.device('cuda', local_rank), dtype=torch.float32)
     K, W = args.steps, max(args.warmup, 3)
 
