@@ -144,7 +144,9 @@ def cpu_reference_setup(P_cpu):
 
 
 def cpu_reference_run(P_cpu, steps, warmup, faithful=True):
+    from oracle import fields as ofields
     from oracle import planners as oplanners
+    ofields.EXACT_SQRT = False          # time torch's own fp32 sqrt, as the reference's eager CPU path would run it
     torch.set_num_threads(os.cpu_count() or 1)
     spec, means, L, Sinv, sig = cpu_reference_setup(P_cpu)
     gen = torch.Generator().manual_seed(0)

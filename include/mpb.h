@@ -52,9 +52,18 @@ typedef struct mpb_robot_desc {
 } mpb_robot_desc;
 
 /* Replaces one entry of `collision_fields` (mp_baselines/planners/gpmp2.py:72-79), i.e. the
- * object whose compute_cost() FieldFactor calls (costs/factors/field_factor.py:39):
- * a union of sphere and axis-aligned box primitives, cost = sum over robot spheres of
- * relu(radius + cutoff_margin - sdf(centre)). */
+ * object whose compute_cost() FieldFactor calls (costs/factors/field_factor.py:39).  The reference's
+ * task.get_collision_fields() returns up to three kinds (examples/panda_spheres_GPMP.py:41-57):
+ *   MPB_FIELD_PRIMITIVES  objects: a union of sphere and axis-aligned box primitives,
+ *                         err = sum over robot spheres s of relu(r_s + cutoff_margin - sdf(c_s))
+ *   MPB_FIELD_SELF        self-collision (chain robots): a list of robot-sphere pairs (i,j) on different links,
+ *                         err = sum over pairs of relu(r_i + r_j + cutoff_margin - ||c_i - c_j||)
+ *   MPB_FIELD_WORKSPACE   workspace boundaries: sdf(c) = min over axes of min(c - ws_min, ws_max - c),
+ *                         err = sum over robot spheres of relu(r_s + cutoff_margin - sdf(c_s)) */
+#define MPB_FIELD_PRIMITIVES 0
+#define MPB_FIELD_SELF 1
+#define MPB_FIELD_WORKSPACE 2
+#define MPB_MAX_SELF_PAIRS 4096
 typedef struct mpb_field_desc {
     int32_t n_spheres;
     int32_t n_boxes;
@@ -64,6 +73,12 @@ typedef struct mpb_field_desc {
     float weight;               /* CostComposite weight * 1/sigma_coll^2 is applied as
                                    weight * (inv_sigma2 * sum_t err)  (cost_functions.py:85,185-186) */
     float inv_sigma2;
+    int32_t kind;               /* MPB_FIELD_* (0 = primitives, the layout of the first seven members) */
+    int32_t n_pairs;            /* SELF: number of sphere pairs, <= MPB_MAX_SELF_PAIRS */
+    const int32_t* pairs;       /* SELF: [n_pairs,2] robot-sphere indices with link(i) < link(j), sorted by
+                                   (link(i), link(j)) so that the pairs of one link pair are contiguous */
+    float ws_min[3];            /* WORKSPACE: lower / upper corner (the third entry is ignored in 2-D) */
+    float ws_max[3];
 } mpb_field_desc;
 
 /* Replaces CostGP + CostGoalPrior parameters (cost_functions.py:234-289,488-536;
@@ -83,6 +98,9 @@ typedef struct mpb_gp_desc {
 
 const char* mpb_last_error(void);
 int mpb_version(void);
+/* sizeof(mpb_robot_desc | mpb_field_desc | mpb_gp_desc) for which = 0 | 1 | 2: lets a foreign-language binding
+ * verify its struct layout before the first call. */
+int mpb_sizeof_desc(int which);
 
 /* x[p,s,:] = mu[p,:] + L @ eps[s,p,:]
  * Replaces MultiMPPrior.sample (costs/factors/mp_priors_multi.py:253-256) =

@@ -24,9 +24,15 @@ class RobotDesc(C.Structure):
                 ('sphere_r', C.c_void_p)]
 
 
+FIELD_PRIMITIVES, FIELD_SELF, FIELD_WORKSPACE = 0, 1, 2
+MPB_MAX_SELF_PAIRS = 4096
+
+
 class FieldDesc(C.Structure):
     _fields_ = [('n_spheres', C.c_int32), ('n_boxes', C.c_int32), ('spheres', C.c_void_p), ('boxes', C.c_void_p),
-                ('cutoff_margin', C.c_float), ('weight', C.c_float), ('inv_sigma2', C.c_float)]
+                ('cutoff_margin', C.c_float), ('weight', C.c_float), ('inv_sigma2', C.c_float),
+                ('kind', C.c_int32), ('n_pairs', C.c_int32), ('pairs', C.c_void_p),
+                ('ws_min', C.c_float * 3), ('ws_max', C.c_float * 3)]
 
 
 class GPDesc(C.Structure):
@@ -41,6 +47,7 @@ _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 _SIGNATURES = {
     'mpb_last_error': (C.c_char_p, []),
     'mpb_version': (C.c_int, []),
+    'mpb_sizeof_desc': (C.c_int, [_i]),
     'mpb_sample_gp': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'mpb_split_tf32': (C.c_int, [_vp, _vp, _vp, C.c_longlong, _vp]),
     'mpb_sample_gp_tc_supported': (C.c_int, [_i, _i, _i]),
@@ -83,6 +90,10 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
+        for which, struct in enumerate((RobotDesc, FieldDesc, GPDesc)):
+            if handle.mpb_sizeof_desc(which) != C.sizeof(struct):
+                raise MpbError(f'{struct.__name__}: ctypes layout ({C.sizeof(struct)} B) differs from the library '
+                               f'({handle.mpb_sizeof_desc(which)} B); rebuild with ./build.sh')
         _lib = handle
     return _lib
 

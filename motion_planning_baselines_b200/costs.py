@@ -16,7 +16,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .fields import CollisionField
+from .fields import Field
 
 
 class Cost:
@@ -43,8 +43,9 @@ class Cost:
 class CostCollision(Cost):
     def __init__(self, robot, n_support_points, field=None, sigma_coll=None, **kwargs):
         super().__init__(robot, n_support_points, **kwargs)
-        if field is not None and not isinstance(field, CollisionField):
-            raise _lib.MpbError('CostCollision needs a motion_planning_baselines_b200.CollisionField')
+        if field is not None and not isinstance(field, Field):
+            raise _lib.MpbError('CostCollision needs a motion_planning_baselines_b200.fields.Field '
+                                '(CollisionField, SelfCollisionField or WorkspaceBoundaryField)')
         self.field = field
         self.sigma_coll = sigma_coll
         self.inv_sigma2 = 1. / (sigma_coll ** 2)          # FieldFactor.K (field_factor.py:15)

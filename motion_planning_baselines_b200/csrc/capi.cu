@@ -61,7 +61,15 @@ unsigned* sched_slot() {
 }  // namespace mpb
 
 extern "C" const char* mpb_last_error(void) { return mpb::g_err; }
-extern "C" int mpb_version(void) { return 100; }
+extern "C" int mpb_version(void) { return 101; }
+extern "C" int mpb_sizeof_desc(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(mpb_robot_desc);
+        case 1: return (int)sizeof(mpb_field_desc);
+        case 2: return (int)sizeof(mpb_gp_desc);
+        default: return -1;
+    }
+}
 
 // One Stoch-GPMP iteration (mp_baselines/planners/stoch_gpmp.py:291-299): K1 -> matvec -> K2 -> K3,
 // all enqueued on `stream` with no host synchronisation.  The prior factor L never changes, so the

@@ -34,7 +34,7 @@ struct ChompArgs {
 template <int KIND>
 __global__ void __launch_bounds__(kChompWarps * 32) chomp_kernel(const __grid_constant__ ChompArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    stage_fields(a.fields, smem);
+    stage_fields(a.fields, a.robot, smem);
     if (KIND == MPB_ROBOT_CHAIN) stage_robot(a.robot, a.rl, smem);
     __syncthreads();
 
@@ -129,6 +129,10 @@ extern "C" int mpb_chomp_run(float* x, int P, int H, const mpb_robot_desc* robot
     a.x = x; a.P = P; a.H = H; a.d = robot->q_dim; a.D = 2 * a.d; a.M = H * a.D;
     a.robot = *robot;
     a.fields.n_fields = n_fields;
+    {
+        const char* why = validate_fields(fields, n_fields, *robot);
+        MPB_REQUIRE(!why, "mpb_chomp_run: %s", why);
+    }
     for (int i = 0; i < n_fields; ++i) a.fields.f[i] = fields[i];
     a.R = R; a.smooth2 = 2.f * smooth_scale; a.lr = lr; a.clip = grad_clip; a.n_iters = n_iters;
     unsigned off = layout_fields(a.fields, 0);

@@ -24,33 +24,76 @@ struct FieldLayout {
     unsigned sph, sphx, boxc, boxh;   // float4[n_sph], float2[n_sph], float4[n_box], float4[n_box]
     int n_sph, n_box;
     float margin, weight, inv_sigma2;
+    int kind;                         // MPB_FIELD_*
+    unsigned pairs, grp, lastb;       // SELF: ushort2[n_pairs]; ushort2[MAX_DOF*MAX_DOF] pair range of link pair (a,b);
+    int n_pairs;                      //       int[MAX_DOF] largest b with a non-empty range for first link a (0: none)
+    float lo[3], hi[3];               // WORKSPACE
 };
 
 struct FieldArgs {              // by-value kernel argument
     int n_fields;
+    int has_extra;              // any field that is not MPB_FIELD_PRIMITIVES
     mpb_field_desc f[MPB_MAX_FIELDS];
     FieldLayout l[MPB_MAX_FIELDS];
 };
 
+// Host-side validation shared by every entry point that takes fields.  Returns nullptr or a message.
+inline const char* validate_fields(const mpb_field_desc* fields, int n_fields, const mpb_robot_desc& robot) {
+    if (n_fields < 0 || n_fields > MPB_MAX_FIELDS) return "n_fields out of range";
+    if (n_fields > 0 && !fields) return "fields is null";
+    for (int i = 0; i < n_fields; ++i) {
+        const mpb_field_desc& d = fields[i];
+        if (d.kind == MPB_FIELD_PRIMITIVES) {
+            if (d.n_spheres < 0 || d.n_boxes < 0 || (d.n_spheres > 0 && !d.spheres) || (d.n_boxes > 0 && !d.boxes))
+                return "a primitive field has inconsistent sphere / box arrays";
+            if (d.n_spheres >= 65536 || d.n_boxes >= 65536) return "too many primitives in one field";
+        } else if (d.kind == MPB_FIELD_SELF) {
+            if (d.n_pairs < 0 || d.n_pairs > MPB_MAX_SELF_PAIRS || (d.n_pairs > 0 && !d.pairs))
+                return "a self-collision field needs 0..MPB_MAX_SELF_PAIRS sphere pairs";
+            if (d.n_pairs > 0 && robot.kind != MPB_ROBOT_CHAIN) return "self-collision fields need a chain robot";
+            if (robot.n_spheres >= 65536) return "too many robot spheres for a self-collision field";
+        } else if (d.kind == MPB_FIELD_WORKSPACE) {
+            for (int k = 0; k < robot.ws_dim; ++k)
+                if (!(d.ws_min[k] < d.ws_max[k])) return "workspace field needs ws_min < ws_max on every axis";
+        } else {
+            return "unknown field kind";
+        }
+    }
+    return nullptr;
+}
+
 // Fills fa.l[] starting at byte offset `base` (16-byte aligned); returns the end offset.
 inline unsigned layout_fields(FieldArgs& fa, unsigned base) {
     unsigned p = base;
+    fa.has_extra = 0;
     for (int i = 0; i < fa.n_fields; ++i) {
         const mpb_field_desc& d = fa.f[i];
         FieldLayout& l = fa.l[i];
-        l.sph = p;  p += (unsigned)d.n_spheres * 16;
-        l.boxc = p; p += (unsigned)d.n_boxes * 16;
-        l.boxh = p; p += (unsigned)d.n_boxes * 16;
-        l.sphx = p; p += (unsigned)d.n_spheres * 8;
+        l.kind = d.kind;
+        if (d.kind != MPB_FIELD_PRIMITIVES) fa.has_extra = 1;
+        const int ns = d.kind == MPB_FIELD_PRIMITIVES ? d.n_spheres : 0, nb = d.kind == MPB_FIELD_PRIMITIVES ? d.n_boxes : 0;
+        l.sph = p;  p += (unsigned)ns * 16;
+        l.boxc = p; p += (unsigned)nb * 16;
+        l.boxh = p; p += (unsigned)nb * 16;
+        l.sphx = p; p += (unsigned)ns * 8;
         p = (p + 15u) & ~15u;
-        l.n_sph = d.n_spheres; l.n_box = d.n_boxes;
+        l.n_sph = ns; l.n_box = nb;
         l.margin = d.cutoff_margin; l.weight = d.weight; l.inv_sigma2 = d.inv_sigma2;
+        l.n_pairs = d.kind == MPB_FIELD_SELF ? d.n_pairs : 0;
+        l.pairs = l.grp = l.lastb = p;
+        if (l.n_pairs > 0) {
+            l.pairs = p; p += (unsigned)l.n_pairs * 4;
+            l.grp = p;   p += MPB_MAX_DOF * MPB_MAX_DOF * 4;
+            l.lastb = p; p += MPB_MAX_DOF * 4;
+            p = (p + 15u) & ~15u;
+        }
+        for (int k = 0; k < 3; ++k) { l.lo[k] = d.ws_min[k]; l.hi[k] = d.ws_max[k]; }
     }
     return p;
 }
 
-// Cooperative staging by the whole CTA (caller syncs afterwards).
-__device__ __forceinline__ void stage_fields(const FieldArgs& fa, unsigned char* smem) {
+// Cooperative staging by the whole CTA (caller syncs afterwards).  Every thread of the CTA must call it.
+__device__ __forceinline__ void stage_fields(const FieldArgs& fa, const mpb_robot_desc& robot, unsigned char* smem) {
     for (int i = 0; i < fa.n_fields; ++i) {
         const mpb_field_desc& d = fa.f[i];
         const FieldLayout& l = fa.l[i];
@@ -58,16 +101,63 @@ __device__ __forceinline__ void stage_fields(const FieldArgs& fa, unsigned char*
         float2* sphx = reinterpret_cast<float2*>(smem + l.sphx);
         float4* boxc = reinterpret_cast<float4*>(smem + l.boxc);
         float4* boxh = reinterpret_cast<float4*>(smem + l.boxh);
-        for (int o = threadIdx.x; o < d.n_spheres; o += blockDim.x) {
+        for (int o = threadIdx.x; o < l.n_sph; o += blockDim.x) {
             const float4 s = reinterpret_cast<const float4*>(d.spheres)[o];
             sph[o] = s;
             sphx[o] = make_float2(-s.w * s.w, -2.f * s.w);
         }
-        for (int o = threadIdx.x; o < d.n_boxes; o += blockDim.x) {
+        for (int o = threadIdx.x; o < l.n_box; o += blockDim.x) {
             boxc[o] = reinterpret_cast<const float4*>(d.boxes)[2 * o];
             boxh[o] = reinterpret_cast<const float4*>(d.boxes)[2 * o + 1];
         }
+        if (l.n_pairs > 0) {
+            // pair list + the [first,last) range of every link pair (the list is sorted by link pair)
+            ushort2* pr = reinterpret_cast<ushort2*>(smem + l.pairs);
+            ushort2* grp = reinterpret_cast<ushort2*>(smem + l.grp);
+            int* lastb = reinterpret_cast<int*>(smem + l.lastb);
+            for (int k = threadIdx.x; k < MPB_MAX_DOF * MPB_MAX_DOF; k += blockDim.x) grp[k] = make_ushort2(0, 0);
+            for (int k = threadIdx.x; k < MPB_MAX_DOF; k += blockDim.x) lastb[k] = 0;
+            __syncthreads();
+            for (int p = threadIdx.x; p < l.n_pairs; p += blockDim.x) {
+                const int si = d.pairs[2 * p], sj = d.pairs[2 * p + 1];
+                pr[p] = make_ushort2((unsigned short)si, (unsigned short)sj);
+                const int key = robot.sphere_link[si] * MPB_MAX_DOF + robot.sphere_link[sj];
+                int prev = -1, next = -1;
+                if (p > 0) prev = robot.sphere_link[d.pairs[2 * p - 2]] * MPB_MAX_DOF + robot.sphere_link[d.pairs[2 * p - 1]];
+                if (p + 1 < l.n_pairs) next = robot.sphere_link[d.pairs[2 * p + 2]] * MPB_MAX_DOF + robot.sphere_link[d.pairs[2 * p + 3]];
+                if (key != prev) grp[key].x = (unsigned short)p;
+                if (key != next) {
+                    grp[key].y = (unsigned short)(p + 1);
+                    atomicMax(lastb + key / MPB_MAX_DOF, key % MPB_MAX_DOF);
+                }
+            }
+        }
     }
+}
+
+// WORKSPACE field: signed distance to the nearest wall, first minimal entry in the oracle's order
+// (x-lo_x, y-lo_y, [z-lo_z,] hi_x-x, hi_y-y [, hi_z-z]); every operation is a single rounded subtraction.
+template <bool GRAD>
+__device__ __forceinline__ float workspace_sdf(const FieldLayout& f, int ws_dim, float cx, float cy, float cz, float* gx,
+                                               float* gy, float* gz) {
+    float best = __fsub_rn(cx, f.lo[0]);
+    int arg = 0;
+    float v = __fsub_rn(cy, f.lo[1]);
+    if (v < best) { best = v; arg = 1; }
+    if (ws_dim == 3) { v = __fsub_rn(cz, f.lo[2]); if (v < best) { best = v; arg = 2; } }
+    v = __fsub_rn(f.hi[0], cx); if (v < best) { best = v; arg = 3; }
+    v = __fsub_rn(f.hi[1], cy); if (v < best) { best = v; arg = 4; }
+    if (ws_dim == 3) { v = __fsub_rn(f.hi[2], cz); if (v < best) { best = v; arg = 5; } }
+    if (GRAD) {
+        *gx = arg == 0 ? 1.f : (arg == 3 ? -1.f : 0.f);
+        *gy = arg == 1 ? 1.f : (arg == 4 ? -1.f : 0.f);
+        *gz = arg == 2 ? 1.f : (arg == 5 ? -1.f : 0.f);
+    }
+    return best;
+}
+
+__device__ __forceinline__ float workspace_hinge(const FieldLayout& f, int ws_dim, float cx, float cy, float cz, float b) {
+    return fmaxf(__fsub_rn(b, workspace_sdf<false>(f, ws_dim, cx, cy, cz, nullptr, nullptr, nullptr)), 0.f);
 }
 
 // ---- pass 1: conservative candidate test for a register block of G sphere centres -------------

@@ -85,15 +85,29 @@ __device__ __forceinline__ void enqueue(unsigned char* smem, const FieldArgs& fa
     }
 }
 
-template <int G>
+__device__ __forceinline__ void acc_add(HingeAcc& acc, int f, float h) {
+    acc.all_zero = acc.all_zero && (h == 0.f);
+#pragma unroll
+    for (int k = 0; k < MPB_MAX_FIELDS; ++k)
+        if (k == f) acc.h[k] += h;
+}
+
+template <int G, bool XF>
 __device__ __forceinline__ void collide_block(unsigned char* smem, const FieldArgs& fa, WarpQueue& q,
                                               const float (&cx)[G], const float (&cy)[G], const float (&cz)[G],
-                                              const float (&rad)[G], bool active, int lane, HingeAcc& acc) {
+                                              const float (&rad)[G], bool active, int lane, HingeAcc& acc, int ws_dim) {
     for (int f = 0; f < fa.n_fields; ++f) {
         const FieldLayout& fl = fa.l[f];
         float b[G];
 #pragma unroll
         for (int k = 0; k < G; ++k) b[k] = __fadd_rn(rad[k], fl.margin);
+        if (XF && fl.kind != MPB_FIELD_PRIMITIVES) {
+            if (fl.kind == MPB_FIELD_WORKSPACE && active) {
+#pragma unroll
+                for (int k = 0; k < G; ++k) acc_add(acc, f, workspace_hinge(fl, ws_dim, cx[k], cy[k], cz[k], b[k]));
+            }
+            continue;                      // a point robot has no self-collision pairs
+        }
         unsigned cand = cull_block<G>(smem, fl, cx, cy, cz, b);
         if (!active) cand = 0u;
         const unsigned any = __reduce_or_sync(MPB_FULL_MASK, cand);
@@ -101,6 +115,95 @@ __device__ __forceinline__ void collide_block(unsigned char* smem, const FieldAr
 #pragma unroll
             for (int k = 0; k < G; ++k)
                 if (any & (1u << k)) enqueue(smem, fa, q, (cand >> k) & 1u, cx[k], cy[k], cz[k], b[k], f, lane, acc);
+        }
+    }
+}
+
+// Self-collision pass of one waypoint per lane (chain robots; rare path, not inlined).  Link frames are rebuilt by a
+// nested chain walk -- Ta after joint a, T continued from Ta up to joint b -- with exactly the operation sequence of
+// the main loop, so sphere centres are bit-identical to the ones the other fields see.  A link pair is skipped for the
+// whole warp when no lane has the two links' bounding spheres within reach; surviving pairs are evaluated exactly
+// (single rounded operations in the oracle's order, oracle/fields.py SelfCollisionField).
+__device__ __noinline__ void self_collision_pass(const FieldLayout& fl, const RobotLayout& rl, const float* xt, int d,
+                                                 bool active, float& hsum, bool& all_zero) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const float4* rsphere = reinterpret_cast<const float4*>(smem + rl.sphere);
+    const float4* rbound = reinterpret_cast<const float4*>(smem + rl.bound);
+    const float* rtf = reinterpret_cast<const float*>(smem + rl.tf);
+    const ushort2* pr = reinterpret_cast<const ushort2*>(smem + fl.pairs);
+    const ushort2* grp = reinterpret_cast<const ushort2*>(smem + fl.grp);
+    const int* lastb = reinterpret_cast<const int*>(smem + fl.lastb);
+    Frame Ta;
+    frame_identity(Ta);
+#pragma unroll 1
+    for (int a = 0; a < d - 1; ++a) {
+        frame_advance(Ta, rtf + a * 12, xt[a], xt[d + a]);
+        const int b_last = lastb[a];
+        if (b_last <= a) continue;
+        const float4 ba = rbound[a];
+        const float ax = fmaf(Ta.r00, ba.x, fmaf(Ta.r01, ba.y, fmaf(Ta.r02, ba.z, Ta.tx)));
+        const float ay = fmaf(Ta.r10, ba.x, fmaf(Ta.r11, ba.y, fmaf(Ta.r12, ba.z, Ta.ty)));
+        const float az = fmaf(Ta.r20, ba.x, fmaf(Ta.r21, ba.y, fmaf(Ta.r22, ba.z, Ta.tz)));
+        Frame T = Ta;
+#pragma unroll 1
+        for (int b = a + 1; b <= b_last; ++b) {
+            frame_advance(T, rtf + b * 12, xt[b], xt[d + b]);
+            const ushort2 g = grp[a * MPB_MAX_DOF + b];
+            if (g.x == g.y) continue;
+            const float4 bb = rbound[b];
+            const float ex = fmaf(T.r00, bb.x, fmaf(T.r01, bb.y, fmaf(T.r02, bb.z, T.tx))) - ax;
+            const float ey = fmaf(T.r10, bb.x, fmaf(T.r11, bb.y, fmaf(T.r12, bb.z, T.ty))) - ay;
+            const float ez = fmaf(T.r20, bb.x, fmaf(T.r21, bb.y, fmaf(T.r22, bb.z, T.tz))) - az;
+            const float reach = ba.w + bb.w + fl.margin;
+            const bool near = active && fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < fmaf(reach * reach, 1.001f, 1e-6f);
+            if (!__any_sync(MPB_FULL_MASK, near)) continue;
+#pragma unroll 1
+            for (int p = g.x; p < g.y; ++p) {
+                const ushort2 ij = pr[p];
+                const float4 oi = rsphere[ij.x], oj = rsphere[ij.y];
+                const float cix = fmaf(Ta.r00, oi.x, fmaf(Ta.r01, oi.y, fmaf(Ta.r02, oi.z, Ta.tx)));
+                const float ciy = fmaf(Ta.r10, oi.x, fmaf(Ta.r11, oi.y, fmaf(Ta.r12, oi.z, Ta.ty)));
+                const float ciz = fmaf(Ta.r20, oi.x, fmaf(Ta.r21, oi.y, fmaf(Ta.r22, oi.z, Ta.tz)));
+                const float cjx = fmaf(T.r00, oj.x, fmaf(T.r01, oj.y, fmaf(T.r02, oj.z, T.tx)));
+                const float cjy = fmaf(T.r10, oj.x, fmaf(T.r11, oj.y, fmaf(T.r12, oj.z, T.ty)));
+                const float cjz = fmaf(T.r20, oj.x, fmaf(T.r21, oj.y, fmaf(T.r22, oj.z, T.tz)));
+                const float dx = __fsub_rn(cix, cjx), dy = __fsub_rn(ciy, cjy), dz = __fsub_rn(ciz, cjz);
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                const float thr = __fadd_rn(__fadd_rn(oi.w, oj.w), fl.margin);
+                if (near && d2 < fmaf(thr * thr, 1.0001f, 1e-6f)) {
+                    const float h = fmaxf(__fsub_rn(thr, __fsqrt_rn(d2)), 0.f);
+                    hsum += h;
+                    all_zero = all_zero && (h == 0.f);
+                }
+            }
+        }
+    }
+}
+
+// Workspace-boundary hinge of the spheres [s_begin, s_end) of one link (chain robots).  Skipped for the whole warp
+// when the lanes' bounding spheres all lie inside the workspace shrunk by their radius + margin.
+__device__ __noinline__ void workspace_link_pass(const FieldLayout& fl, const RobotLayout& rl, const Frame& T, float bx,
+                                                 float by, float bz, float Rm, int s_begin, int s_end, bool active,
+                                                 float& hsum, bool& all_zero) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const float slack = fmaf(fabsf(Rm), 1e-3f, 1e-5f) + Rm;
+    const float lox = warp_min_f(active ? bx : CUDART_INF_F), hix = warp_max_f(active ? bx : -CUDART_INF_F);
+    const float loy = warp_min_f(active ? by : CUDART_INF_F), hiy = warp_max_f(active ? by : -CUDART_INF_F);
+    const float loz = warp_min_f(active ? bz : CUDART_INF_F), hiz = warp_max_f(active ? bz : -CUDART_INF_F);
+    const bool inside = (lox - slack > fl.lo[0]) && (hix + slack < fl.hi[0]) && (loy - slack > fl.lo[1]) &&
+                        (hiy + slack < fl.hi[1]) && (loz - slack > fl.lo[2]) && (hiz + slack < fl.hi[2]);
+    if (inside) return;
+    const float4* rsphere = reinterpret_cast<const float4*>(smem + rl.sphere);
+#pragma unroll 1
+    for (int s = s_begin; s < s_end; ++s) {
+        const float4 o = rsphere[s];
+        const float cx = fmaf(T.r00, o.x, fmaf(T.r01, o.y, fmaf(T.r02, o.z, T.tx)));
+        const float cy = fmaf(T.r10, o.x, fmaf(T.r11, o.y, fmaf(T.r12, o.z, T.ty)));
+        const float cz = fmaf(T.r20, o.x, fmaf(T.r21, o.y, fmaf(T.r22, o.z, T.tz)));
+        const float h = workspace_hinge(fl, 3, cx, cy, cz, __fadd_rn(o.w, fl.margin));
+        if (active) {
+            hsum += h;
+            all_zero = all_zero && (h == 0.f);
         }
     }
 }
@@ -130,11 +233,11 @@ __device__ __forceinline__ void issue_row(const float* xb, float* dst, int M, bo
     cp_async_commit();
 }
 
-template <int KIND, int G>
+template <int KIND, int G, bool XF>
 __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_constant__ CostArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
 
-    stage_fields(a.fields, smem);
+    stage_fields(a.fields, a.robot, smem);
     if (KIND == MPB_ROBOT_CHAIN) stage_robot(a.robot, a.rl, smem);
     __syncthreads();
 
@@ -227,7 +330,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
                     cy[0] = xt[1];
                     cz[0] = (a.robot.ws_dim == 3) ? xt[2] : 0.f;
                     rad[0] = point_r;
-                    collide_block<1>(smem, a.fields, q, cx, cy, cz, rad, active, lane, hacc);
+                    collide_block<1, XF>(smem, a.fields, q, cx, cy, cz, rad, active, lane, hacc, a.robot.ws_dim);
                 } else {
                     // every neighbour has consumed this batch of rows: turn (q | qdot) into (cos q | sin q) in place
                     __syncwarp();
@@ -258,6 +361,18 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
 #pragma unroll 1
                         for (int f = 0; f < nf; ++f) {
                             const FieldLayout& fl = a.fields.l[f];
+                            if (XF && fl.kind != MPB_FIELD_PRIMITIVES) {
+                                if (fl.kind == MPB_FIELD_WORKSPACE) {
+                                    float hs = 0.f;
+                                    bool az = true;
+                                    workspace_link_pass(fl, a.rl, T, bx, by, bz, bs.w + fl.margin, s_begin, s_end, active, hs, az);
+                                    hacc.all_zero = hacc.all_zero && az;
+#pragma unroll
+                                    for (int k = 0; k < MPB_MAX_FIELDS; ++k)
+                                        if (k == f) hacc.h[k] += hs;
+                                }
+                                continue;
+                            }
                             int n_ls, n_lb;
                             __syncwarp();
                             broad_phase(smem, fl, bx, by, bz, bs.w + fl.margin, active, lane, lsph, n_ls, lbox, n_lb);
@@ -291,6 +406,20 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
                             }
                         }
                         s_begin = s_end;
+                    }
+                    if (XF) {
+#pragma unroll 1
+                        for (int f = 0; f < nf; ++f) {
+                            const FieldLayout& fl = a.fields.l[f];
+                            if (fl.kind != MPB_FIELD_SELF || fl.n_pairs == 0) continue;
+                            float hs = 0.f;
+                            bool az = true;
+                            self_collision_pass(fl, a.rl, xt, d, active, hs, az);
+                            hacc.all_zero = hacc.all_zero && az;
+#pragma unroll
+                            for (int k = 0; k < MPB_MAX_FIELDS; ++k)
+                                if (k == f) hacc.h[k] += hs;
+                        }
                     }
                 }
             }
@@ -348,21 +477,21 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
     }
 }
 
-template <int KIND, int G>
+template <int KIND, int G, bool XF>
 static cudaError_t launch(const CostArgs& a, int blocks_needed, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(cost_eval_kernel<KIND, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(cost_eval_kernel<KIND, G, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(cost_eval_kernel<KIND, G>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(cost_eval_kernel<KIND, G, XF>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     // persistent grid: exactly one wave of resident CTAs; trajectories are handed out dynamically
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cost_eval_kernel<KIND, G>, kWarps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cost_eval_kernel<KIND, G, XF>, kWarps * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const int resident = sm_count() * per_sm;
     const int grid = blocks_needed < resident ? blocks_needed : resident;
-    cost_eval_kernel<KIND, G><<<grid, kWarps * 32, smem, st>>>(a);
+    cost_eval_kernel<KIND, G, XF><<<grid, kWarps * 32, smem, st>>>(a);
     return cudaSuccess;
 }
 
@@ -378,7 +507,6 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
     MPB_REQUIRE(x && cost && robot, "mpb_cost_eval: null x/cost/robot");
     MPB_REQUIRE(H >= 2, "mpb_cost_eval: need B >= 0 and H >= 2 (got B=%d H=%d)", B, H);
     MPB_REQUIRE(n_fields >= 0 && n_fields <= MPB_MAX_FIELDS, "mpb_cost_eval: n_fields=%d not in [0,%d]", n_fields, MPB_MAX_FIELDS);
-    MPB_REQUIRE(n_fields == 0 || fields, "mpb_cost_eval: fields is null");
     MPB_REQUIRE(robot->kind == MPB_ROBOT_POINT || robot->kind == MPB_ROBOT_CHAIN, "mpb_cost_eval: unknown robot kind %d", robot->kind);
     MPB_REQUIRE(robot->ws_dim == 2 || robot->ws_dim == 3, "mpb_cost_eval: ws_dim must be 2 or 3");
     if (robot->kind == MPB_ROBOT_POINT)
@@ -393,12 +521,11 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
     a.x = x; a.B = B; a.H = H; a.d = robot->q_dim; a.D = 2 * robot->q_dim; a.M = H * a.D;
     a.robot = *robot;
     a.fields.n_fields = n_fields;
-    for (int i = 0; i < n_fields; ++i) {
-        MPB_REQUIRE(fields[i].n_spheres >= 0 && fields[i].n_boxes >= 0 &&
-                    (fields[i].n_spheres == 0 || fields[i].spheres) && (fields[i].n_boxes == 0 || fields[i].boxes),
-                    "mpb_cost_eval: field %d has inconsistent primitive arrays", i);
-        a.fields.f[i] = fields[i];
+    {
+        const char* why = validate_fields(fields, n_fields, *robot);
+        MPB_REQUIRE(!why, "mpb_cost_eval: %s", why);
     }
+    for (int i = 0; i < n_fields; ++i) a.fields.f[i] = fields[i];
     if (gp && gp->enabled) {
         MPB_REQUIRE(gp->start_state && (!gp->has_goal || gp->goal_state), "mpb_cost_eval: gp start/goal state is null");
         a.gp = *gp;
@@ -417,7 +544,7 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
     off += (unsigned)(kWarps * kQCap * 5 * sizeof(float));
     a.list_cap = 8;
     for (int i = 0; i < n_fields; ++i) {
-        MPB_REQUIRE(fields[i].n_spheres < 65536 && fields[i].n_boxes < 65536, "mpb_cost_eval: too many primitives in field %d", i);
+        if (fields[i].kind != MPB_FIELD_PRIMITIVES) continue;
         const int m = fields[i].n_spheres > fields[i].n_boxes ? fields[i].n_spheres : fields[i].n_boxes;
         if (m > a.list_cap) a.list_cap = (m + 7) & ~7;
     }
@@ -431,8 +558,13 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
     if (!a.sched) { set_error("mpb_cost_eval: could not allocate the scheduler counters"); return MPB_ECUDA; }
     const int blocks_needed = (B + kWarps - 1) / kWarps;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = (robot->kind == MPB_ROBOT_POINT) ? launch<MPB_ROBOT_POINT, 1>(a, blocks_needed, smem, st)
-                                                     : launch<MPB_ROBOT_CHAIN, 4>(a, blocks_needed, smem, st);
+    cudaError_t e;
+    if (a.fields.has_extra)       // self-collision / workspace fields present: the variant that carries those passes
+        e = (robot->kind == MPB_ROBOT_POINT) ? launch<MPB_ROBOT_POINT, 1, true>(a, blocks_needed, smem, st)
+                                             : launch<MPB_ROBOT_CHAIN, 4, true>(a, blocks_needed, smem, st);
+    else
+        e = (robot->kind == MPB_ROBOT_POINT) ? launch<MPB_ROBOT_POINT, 1, false>(a, blocks_needed, smem, st)
+                                             : launch<MPB_ROBOT_CHAIN, 4, false>(a, blocks_needed, smem, st);
     if (e != cudaSuccess) {
         set_error("mpb_cost_eval: launch configuration failed: %s", cudaGetErrorString(e));
         return MPB_ECUDA;

@@ -37,7 +37,7 @@ struct LinArgs {
 template <int KIND>
 __global__ void __launch_bounds__(128) gpmp2_linearize_kernel(const __grid_constant__ LinArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    stage_fields(a.fields, smem);
+    stage_fields(a.fields, a.robot, smem);
     if (KIND == MPB_ROBOT_CHAIN) stage_robot(a.robot, a.rl, smem);
     __syncthreads();
     const float point_r = (KIND == MPB_ROBOT_POINT) ? __ldg(a.robot.sphere_r) : 0.f;
@@ -363,6 +363,10 @@ extern "C" int mpb_gpmp2_linearize(const float* x, int B, int H, const mpb_robot
     a.x = x; a.B = B; a.H = H; a.d = robot->q_dim; a.D = 2 * a.d; a.M = H * a.D;
     a.robot = *robot;
     a.fields.n_fields = n_fields;
+    {
+        const char* why = validate_fields(fields, n_fields, *robot);
+        MPB_REQUIRE(!why, "mpb_gpmp2_linearize: %s", why);
+    }
     for (int i = 0; i < n_fields; ++i) a.fields.f[i] = fields[i];
     a.err = err; a.hobs = hobs;
     unsigned off = layout_fields(a.fields, 0);

@@ -106,6 +106,26 @@ def panda_model():
                       q_min=PANDA_Q_MIN, q_max=PANDA_Q_MAX, name='panda')
 
 
+# Link pairs checked for self-collision.  Like an SRDF's disabled pairs: adjacent links are skipped, and so are
+# (1,3), (4,6) (their sphere groups overlap in every configuration) and (2,4) (overlap in 79 % of uniformly drawn
+# configurations: the elbow) -- measured with this sphere table over 20 000 random joint vectors.
+PANDA_SELF_LINK_PAIRS = [(0, 2), (0, 3), (0, 4), (0, 5), (0, 6), (1, 4), (1, 5), (1, 6), (2, 5), (2, 6), (3, 5), (3, 6)]
+
+
+def self_collision_pairs(model, link_pairs=None):
+    """[Np,2] sphere-index pairs (i on link a, j on link b) for every allowed link pair (a,b), sorted by link pair."""
+    if link_pairs is None:
+        link_pairs = PANDA_SELF_LINK_PAIRS if model.name == 'panda' else \
+            [(a, b) for a in range(model.q_dim) for b in range(a + 2, model.q_dim)]
+    link = np.asarray(model.sphere_link)
+    out = []
+    for a, b in sorted(link_pairs):
+        for i in np.nonzero(link == a)[0]:
+            for j in np.nonzero(link == b)[0]:
+                out.append((int(i), int(j)))
+    return np.asarray(out, dtype=np.int32).reshape(-1, 2)
+
+
 class ObstacleSet:
     """Union of sphere and axis-aligned box primitives in a ws_dim workspace
     (the role of MultiSphereField / MultiBoxField behind CostCollision)."""

@@ -2,7 +2,7 @@
 (TEST INFRASTRUCTURE -- see oracle/__init__.py)."""
 import torch
 
-from .fields import PrimitiveField
+from .fields import PrimitiveField, SelfCollisionField, WorkspaceBoundaryField
 from .robots import PointMassRobot, SerialChainRobot
 
 TA = dict(device='cpu', dtype=torch.float32)
@@ -20,3 +20,12 @@ def oracle_field(obst, model, tensor_args=TA):
                           box_centers=obst.box_centers, box_half=obst.box_half,
                           link_radii=model.sphere_r, cutoff_margin=obst.cutoff_margin,
                           ws_dim=obst.ws_dim, tensor_args=tensor_args)
+
+
+def oracle_self_field(pairs, model, cutoff_margin, tensor_args=TA):
+    return SelfCollisionField(pairs, model.sphere_r, cutoff_margin=cutoff_margin, tensor_args=tensor_args)
+
+
+def oracle_workspace_field(ws_min, ws_max, model, cutoff_margin, tensor_args=TA):
+    return WorkspaceBoundaryField(ws_min, ws_max, link_radii=model.sphere_r, cutoff_margin=cutoff_margin,
+                                  tensor_args=tensor_args)
