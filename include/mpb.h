@@ -96,9 +96,22 @@ typedef struct mpb_gp_desc {
     const float* goal_state;    /* [D] goal with zero velocity  (gpmp2.py:60-61), or NULL */
 } mpb_gp_desc;
 
+/* Replaces the cost terms a caller may append through `extra_costs` (gpmp2.py:82-83) or put into its own
+ * CostComposite: CostGPTrajectory (cost_functions.py:317-357) and CostJointLimits (cost_functions.py:393-429). */
+typedef struct mpb_extra_cost_desc {
+    int32_t gp_traj_enabled;    /* adds w_gp_traj * sum_t e_t^T Q^-1 e_t, e_t = x_{t+1} - Phi x_t (no start term) */
+    float t11, t12, t22;        /* Q^-1 = [[t11 I, t12 I],[t12 I, t22 I]] for this term's own sigma_gp */
+    float w_gp_traj;
+    int32_t jl_enabled;         /* per trajectory: sum_{t,j} relu(q_min_j + eps - q)^2 + relu(q - (q_max_j - eps))^2 */
+    float jl_eps;
+    float w_jl;                 /* used by mpb_chomp_run only (gradient weight); mpb_cost_eval returns the raw term */
+    const float* q_min;         /* [d] */
+    const float* q_max;         /* [d] */
+} mpb_extra_cost_desc;
+
 const char* mpb_last_error(void);
 int mpb_version(void);
-/* sizeof(mpb_robot_desc | mpb_field_desc | mpb_gp_desc) for which = 0 | 1 | 2: lets a foreign-language binding
+/* sizeof(mpb_robot_desc | mpb_field_desc | mpb_gp_desc | mpb_extra_cost_desc) for which = 0 | 1 | 2 | 3: lets a foreign-language binding
  * verify its struct layout before the first call. */
 int mpb_sizeof_desc(int which);
 
@@ -145,6 +158,21 @@ int mpb_cost_eval(const float* x, int B, int H,
                   const mpb_gp_desc* gp,
                   const float* is_vec, int samples_per_particle, float is_scale,
                   float* cost, float* terms, uint8_t* free_flag, void* stream);
+/* Same with the optional extra terms: the CostGPTrajectory term is added to cost[] (and appended to `terms` after the
+ * field rows); the CostJointLimits term is written UNWEIGHTED per trajectory to jl_per_traj [B] and NOT added to
+ * cost[]: the reference sums it over the whole batch into one scalar (cost_functions.py:411-424, `.sum(-1)` of a flat
+ * list) which its composite then adds to every trajectory -- the caller reduces jl_per_traj with mpb_sum_f64. */
+int mpb_cost_eval_ex(const float* x, int B, int H,
+                     const mpb_robot_desc* robot,
+                     const mpb_field_desc* fields, int n_fields,
+                     const mpb_gp_desc* gp,
+                     const float* is_vec, int samples_per_particle, float is_scale,
+                     float* cost, float* terms, uint8_t* free_flag,
+                     const mpb_extra_cost_desc* extra, float* jl_per_traj, void* stream);
+
+/* out[b,j] = x[b,:,j]^T R x[b,:,j] for a tridiagonal R [H,H] (only the three diagonals are read), accumulated in
+ * fp64.  Replaces CostSmoothnessCHOMP.eval (cost_functions.py:371-387) with R = CHOMP._get_R_mat (chomp.py:81-101). */
+int mpb_smoothness_cost(const float* x, const float* R, float* out, int B, int H, int D, void* stream);
 
 /* w = softmax(-cost/temp) over samples; g = sum_s w (x_s - mu); mu += step * (SigmaR @ g if
  * SigmaR else g).  Replaces StochGPMP._update_distribution (stoch_gpmp.py:267-279) and
@@ -178,6 +206,11 @@ int mpb_stoch_gpmp_iter(const float* L, const float* L_split, const float* Sigma
 int mpb_chomp_run(float* x, int P, int H,
                   const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
                   const float* R, float smooth_scale, float lr, float grad_clip, int n_iters, void* stream);
+/* Same with a CostJointLimits term in the cost (extra->jl_enabled; gradient w_jl * d/dq of the term above). */
+int mpb_chomp_run_ex(float* x, int P, int H,
+                     const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
+                     const float* R, float smooth_scale, float lr, float grad_clip, int n_iters,
+                     const mpb_extra_cost_desc* extra, void* stream);
 
 /* GPMP2 step, part 1: collision errors and Jacobians of every waypoint.
  * Replaces FieldFactor.get_error(calc_jacobian=True) (costs/factors/field_factor.py:41-57) as used by
@@ -189,6 +222,16 @@ int mpb_chomp_run(float* x, int P, int H,
 int mpb_gpmp2_linearize(const float* x, int B, int H,
                         const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
                         float* err, float* hobs, double* diag_mean, void* stream);
+/* Same with interpolated collision checking (CostComposite.get_linear_system(n_interpolated_points=n),
+ * cost_functions.py:115-119; field_factor.py:44-57): err stays the error AT the support points, while
+ *   hobs[f,b,t,:] = - d/dq_t  sum_i err_f(p_i),   p = the trajectory linearly up-sampled in joint space with n extra
+ * points per segment, first point dropped.  interp_w_host [n+1] (HOST array) holds the interpolation weights
+ * w_0 = 0 < w_1 < ... < w_n < 1 of the points inside a segment: p = q_t (1 - w_k) + q_{t+1} w_k. */
+#define MPB_MAX_INTERP 32
+int mpb_gpmp2_linearize_ex(const float* x, int B, int H,
+                           const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
+                           float* err, float* hobs, double* diag_mean,
+                           int n_interp, const float* interp_w_host, void* stream);
 
 /* GPMP2 step, part 2: assemble the block-tridiagonal normal equations (never materialising A, K, J^T J),
  * block-Cholesky solve, update x += step * dtheta.  Replaces CostGP/CostGoalPrior.get_linear_system

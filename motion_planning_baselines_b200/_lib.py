@@ -41,6 +41,13 @@ class GPDesc(C.Structure):
                 ('w_gp', C.c_float), ('w_goal', C.c_float), ('start_state', C.c_void_p), ('goal_state', C.c_void_p)]
 
 
+class ExtraCostDesc(C.Structure):
+    _fields_ = [('gp_traj_enabled', C.c_int32), ('t11', C.c_float), ('t12', C.c_float), ('t22', C.c_float),
+                ('w_gp_traj', C.c_float), ('jl_enabled', C.c_int32), ('jl_eps', C.c_float), ('w_jl', C.c_float),
+                ('q_min', C.c_void_p), ('q_max', C.c_void_p)]
+
+
+MPB_MAX_INTERP = 32
 _lib = None
 
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
@@ -56,11 +63,18 @@ _SIGNATURES = {
     'mpb_prior_matvec': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'mpb_cost_eval': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
                                 _vp, _i, _f, _vp, _vp, _vp, _vp]),
+    'mpb_cost_eval_ex': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
+                                   _vp, _i, _f, _vp, _vp, _vp, C.POINTER(ExtraCostDesc), _vp, _vp]),
+    'mpb_smoothness_cost': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'mpb_softmax_update': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _vp]),
     'mpb_stoch_gpmp_iter': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                       C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
                                       _f, _f, _vp]),
     'mpb_chomp_run': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _f, _f, _f, _i, _vp]),
+    'mpb_chomp_run_ex': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _f, _f, _f, _i,
+                                   C.POINTER(ExtraCostDesc), _vp]),
+    'mpb_gpmp2_linearize_ex': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _vp, _vp,
+                                         _i, C.POINTER(C.c_float), _vp]),
     'mpb_gpmp2_linearize': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _vp, _vp, _vp]),
     'mpb_gpmp2_workspace_bytes': (C.c_longlong, [_i, _i, _i]),
     'mpb_gpmp2_solve': (C.c_int, [_vp, _i, _i, _i, C.POINTER(GPDesc), _vp, _vp, C.POINTER(C.c_float), _i, _vp, _f, _f,
@@ -90,7 +104,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        for which, struct in enumerate((RobotDesc, FieldDesc, GPDesc)):
+        for which, struct in enumerate((RobotDesc, FieldDesc, GPDesc, ExtraCostDesc)):
             if handle.mpb_sizeof_desc(which) != C.sizeof(struct):
                 raise MpbError(f'{struct.__name__}: ctypes layout ({C.sizeof(struct)} B) differs from the library '
                                f'({handle.mpb_sizeof_desc(which)} B); rebuild with ./build.sh')

@@ -7,12 +7,17 @@
     CostCollision(robot, n_support_points, field=, sigma_coll=)         cost_functions.py:147-189
     CostGP(robot, n_support_points, start_state, dt, sigma_params)      cost_functions.py:234-289
     CostGoalPrior(robot, n_support_points, multi_goal_states=, ...)     cost_functions.py:488-536
+    CostGPTrajectory(robot, n_support_points, dt, sigma_gp=)            cost_functions.py:317-357
+    CostGPTrajectoryPositionOnlyWrapper(...)                            cost_functions.py:360-368
+    CostSmoothnessCHOMP(robot, n_support_points)                        cost_functions.py:371-390
+    CostJointLimits(robot, n_support_points, eps=)                      cost_functions.py:393-429
     build_gpmp2_cost_composite(...)                                      gpmp2.py:23-89
 
 There is no CPU implementation behind these classes: tensors must live on the CUDA device.
 """
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -84,6 +89,66 @@ class CostGoalPrior(Cost):
         self.k_goal = float(torch.ones((), dtype=torch.float32) / sigma_goal_prior ** 2)
 
 
+class CostGPTrajectory(Cost):
+    """GP-prior smoothness of a whole trajectory without the start term (cost_functions.py:317-357)."""
+
+    def __init__(self, robot, n_support_points, dt, sigma_gp=None, **kwargs):
+        super().__init__(robot, n_support_points, **kwargs)
+        self.dt = dt
+        self.sigma_gp = sigma_gp
+        qc = torch.ones((), dtype=torch.float32) / sigma_gp ** 2
+        self.q11 = float(12. * (dt ** -3.) * qc)
+        self.q12 = float(-6. * (dt ** -2.) * qc)
+        self.q22 = float(4. * (dt ** -1.) * qc)
+
+
+class CostGPTrajectoryPositionOnlyWrapper(CostGPTrajectory):
+    """Position-only trajectories [B,H,d]: velocities by central differences (zero at both ends), then the
+    GP-trajectory cost (cost_functions.py:360-368; ``finite_difference_vector`` is external -- semantics as in
+    oracle/ref_shim)."""
+
+    def eval(self, trajs, **observation):
+        vel = torch.zeros_like(trajs)
+        vel[..., 1:-1, :] = (trajs[..., 2:, :] - trajs[..., :-2, :]) / (2 * self.dt)
+        full = torch.cat((trajs, vel), dim=-1)
+        inner = CostGPTrajectory(self.robot, self.n_support_points, self.dt, sigma_gp=self.sigma_gp, tensor_args=self.tensor_args)
+        return inner.eval(full, **observation)
+
+
+class CostSmoothnessCHOMP(Cost):
+    """x[:, :, j]^T R x[:, :, j] with CHOMP's finite-difference precision R -> [B, D] (cost_functions.py:371-390).
+    Like the reference's it returns one value per state column, so it cannot be a member of a composite."""
+
+    def __init__(self, robot, n_support_points, **kwargs):
+        super().__init__(robot, n_support_points, **kwargs)
+        self.dt = robot.dt
+        from .planners.chomp import CHOMP
+        self.Sigma_inv = CHOMP._get_R_mat(dt=self.dt, n_support_points=n_support_points, tensor_args=self.tensor_args)
+
+    def eval(self, trajs, **observation):
+        _lib.require_f32(trajs)
+        x = trajs.contiguous()
+        B, H, D = x.shape
+        out = torch.empty(B, D, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().mpb_smoothness_cost(_lib.ptr(x), _lib.ptr(self.Sigma_inv), _lib.ptr(out), B, H, D, _lib.stream_ptr()))
+        return out
+
+
+class CostJointLimits(Cost):
+    """Squared violation of the joint limits shrunk by eps (cost_functions.py:393-429).  As in the reference the
+    value is SUMMED OVER THE WHOLE BATCH into one 0-dim tensor (its ``.sum(-1)`` runs over the flat list of violating
+    entries), which a composite then adds to every trajectory."""
+
+    def __init__(self, robot, n_support_points, eps=np.deg2rad(3), **kwargs):
+        super().__init__(robot, n_support_points, **kwargs)
+        self.eps = float(eps)
+
+    def eval(self, trajs, **observation):
+        assert trajs.ndim == 3
+        comp = CostComposite(self.robot, self.n_support_points, [self], tensor_args=self.tensor_args)
+        return comp._eval_full(trajs)[1]
+
+
 class CostComposite(Cost):
     def __init__(self, robot, n_support_points, cost_list, weights_cost_l=None, **kwargs):
         super().__init__(robot, n_support_points, **kwargs)
@@ -94,6 +159,8 @@ class CostComposite(Cost):
     def _build(self, unit_weights=False):
         gp = _lib.GPDesc(enabled=0, has_goal=0, w_gp=1.0, w_goal=1.0)
         fields = []
+        self._extra = None
+        self._w_jl = 0.0
         self._keepalive = []
         order = []                                          # kernel term index of every cost_l entry
         n_gp = n_goal = 0
@@ -120,8 +187,26 @@ class CostComposite(Cost):
                     continue
                 order.append(('field', len(fields)))
                 fields.append(cost.field.desc(weight=w, inv_sigma2=cost.inv_sigma2))
+            elif isinstance(cost, CostGPTrajectory):
+                ex = self._extra or _lib.ExtraCostDesc()
+                assert not ex.gp_traj_enabled, 'one CostGPTrajectory per composite'
+                if gp.enabled and abs(gp.dt - cost.dt) > 1e-6 * abs(cost.dt):
+                    raise NotImplementedError('CostGP and CostGPTrajectory must share dt')
+                gp.dt = cost.dt
+                ex.gp_traj_enabled, ex.t11, ex.t12, ex.t22, ex.w_gp_traj = 1, cost.q11, cost.q12, cost.q22, w
+                self._extra = ex
+                order.append(('gp_traj', 0))
+            elif isinstance(cost, CostJointLimits):
+                ex = self._extra or _lib.ExtraCostDesc()
+                assert not ex.jl_enabled, 'one CostJointLimits per composite'
+                ex.jl_enabled, ex.jl_eps, ex.w_jl = 1, cost.eps, w
+                ex.q_min, ex.q_max = self.robot.q_min.data_ptr(), self.robot.q_max.data_ptr()
+                self._extra = ex
+                self._w_jl = w
+                order.append(('jl', 0))
             else:
-                raise NotImplementedError(f'{type(cost).__name__} has no fused implementation yet')
+                raise NotImplementedError(f'{type(cost).__name__} has no fused implementation (CostSmoothnessCHOMP returns '
+                                          f'[B,D] and cannot be summed into a composite in the reference either)')
         if gp.has_goal and not gp.enabled:
             raise NotImplementedError('CostGoalPrior without CostGP is not supported by the fused kernel')
         if len(fields) > _lib.MPB_MAX_FIELDS:
@@ -130,8 +215,14 @@ class CostComposite(Cost):
         n_head = int(gp.enabled) + int(gp.has_goal)
         term_index = []
         for kind, i in order:
-            term_index.append({'gp': 0, 'goal': 1, 'field': n_head + i, 'none': -1}[kind])
+            term_index.append({'gp': 0, 'goal': 1, 'field': n_head + i, 'none': -1, 'gp_traj': n_head + len(fields),
+                               'jl': -2}[kind])
         return gp, arr, len(fields), term_index
+
+    @property
+    def has_extra_terms(self):
+        self._build()
+        return self._extra is not None
 
     def _flatten(self, trajs):
         assert trajs.ndim in (3, 4)
@@ -144,38 +235,80 @@ class CostComposite(Cost):
 
     def eval(self, trajs, trajs_interpolated=None, return_invidual_costs_and_weights=False,
              is_vec=None, samples_per_particle=1, is_scale=0.0, out=None, free_flag=None, **kwargs):
-        """Reference signature plus optional fused extras (IS term, collision-free flags)."""
-        if trajs_interpolated is not None:
-            raise NotImplementedError('interpolated collision checking is a "next" row (SURVEY.md 8f)')
+        """Reference signature plus optional fused extras (IS term, collision-free flags).
+
+        ``trajs_interpolated`` is accepted and has NO effect, exactly as in the reference: its composite forwards the
+        q_pos / H_positions of ``trajs`` to every term (cost_functions.py:71,85), FieldFactor.get_error uses those
+        (field_factor.py:31-39), so the collision term is evaluated on the support points either way (verified by
+        running the reference: oracle/make_golden_next.py, tests/golden/extra_costs_*.npz)."""
+        if trajs_interpolated is not None and trajs_interpolated.shape[0] != trajs.reshape(-1, *trajs.shape[-2:]).shape[0]:
+            raise _lib.MpbError('trajs_interpolated must have the batch size of trajs')
         if kwargs.get('obstacle_spheres') is not None:
             raise NotImplementedError('per-call obstacle_spheres are not supported')
+        res = self._eval_full(trajs, return_terms=return_invidual_costs_and_weights, is_vec=is_vec,
+                              samples_per_particle=samples_per_particle, is_scale=is_scale, out=out, free_flag=free_flag)
+        if return_invidual_costs_and_weights:
+            return res[2], self.weight_cost_l
+        return res[0]
+
+    def _eval_full(self, trajs, return_terms=False, is_vec=None, samples_per_particle=1, is_scale=0.0, out=None,
+                   free_flag=None):
+        """-> (total [B], joint-limit batch sum (0-dim) | None, per-cost list | None)."""
         x = self._flatten(trajs)
         B = x.shape[0]
-        if B == 0 and not return_invidual_costs_and_weights:
-            return out if out is not None else torch.empty(0, device=x.device, dtype=torch.float32)
-        gp, fields, nf, term_index = self._build(unit_weights=return_invidual_costs_and_weights)
-        cost = out if out is not None else torch.empty(B, device=x.device, dtype=torch.float32)
-        n_terms = int(gp.enabled) + int(gp.has_goal) + nf
-        terms = torch.empty(n_terms, B, device=x.device, dtype=torch.float32) if return_invidual_costs_and_weights else None
-        _lib.check(_lib.lib().mpb_cost_eval(
+        ta = dict(device=x.device, dtype=torch.float32)
+        if B == 0 and not return_terms:
+            return (out if out is not None else torch.empty(0, **ta)), torch.zeros((), **ta), None
+        gp, fields, nf, term_index = self._build(unit_weights=return_terms)
+        extra = self._extra
+        cost = out if out is not None else torch.empty(B, **ta)
+        n_terms = int(gp.enabled) + int(gp.has_goal) + nf + int(bool(extra is not None and extra.gp_traj_enabled))
+        terms = torch.empty(max(n_terms, 1), B, **ta) if return_terms else None
+        jl = torch.empty(B, **ta) if extra is not None and extra.jl_enabled else None
+        _lib.check(_lib.lib().mpb_cost_eval_ex(
             _lib.ptr(x), B, self.n_support_points, C.byref(self.robot.desc), fields, nf, C.byref(gp),
             _lib.ptr(is_vec), samples_per_particle, is_scale,
-            _lib.ptr(cost), _lib.ptr(terms), _lib.ptr(free_flag), _lib.stream_ptr()))
-        if return_invidual_costs_and_weights:
-            zero = torch.zeros(B, device=x.device, dtype=torch.float32)
-            return [terms[i] if i >= 0 else zero for i in term_index], self.weight_cost_l
-        return cost
+            _lib.ptr(cost), _lib.ptr(terms), _lib.ptr(free_flag),
+            C.byref(extra) if extra is not None else None, _lib.ptr(jl), _lib.stream_ptr()))
+        jl_sum = None
+        if jl is not None:
+            # the reference's joint-limit term is one scalar for the whole batch, added to every trajectory
+            acc = torch.empty(1, device=x.device, dtype=torch.float64)
+            scratch = torch.empty(1024, device=x.device, dtype=torch.float64)
+            _lib.check(_lib.lib().mpb_sum_f64(_lib.ptr(jl), B, _lib.ptr(acc), _lib.ptr(scratch), _lib.stream_ptr()))
+            jl_sum = acc[0].to(torch.float32)
+            if not return_terms:
+                cost.add_(jl_sum * self._w_jl)
+        per_cost = None
+        if return_terms:
+            zero = torch.zeros(B, **ta)
+            per_cost = [jl_sum if i == -2 else (terms[i] if i >= 0 else zero) for i in term_index]
+        return cost, jl_sum, per_cost
 
-    def linearize_collision(self, trajs):
+    @staticmethod
+    def interpolation_weights(n_interpolated_points):
+        """(n, host float array [n+1]) for mpb_gpmp2_linearize_ex: the weights of ``interpolate_points_v1`` (external;
+        linear up-sampling with n extra points per segment, see oracle/costs.py)."""
+        n = int(n_interpolated_points or 0)
+        if n <= 0:
+            return 0, None
+        if n > _lib.MPB_MAX_INTERP:
+            raise _lib.MpbError(f'at most {_lib.MPB_MAX_INTERP} interpolated points per segment')
+        w = torch.linspace(0, 1, n + 2, dtype=torch.float32)[:-1]
+        return n, (C.c_float * (n + 1))(*[float(v) for v in w])
+
+    def linearize_collision(self, trajs, n_interpolated_points=None):
         """-> err [n_fields,B,H], hobs [n_fields,B,H,d]: collision errors and H_obst = -d err/d q of every
-        waypoint (mpb_gpmp2_linearize; field_factor.py:41-57 without autograd)."""
+        waypoint (mpb_gpmp2_linearize; field_factor.py:41-57 without autograd).  With ``n_interpolated_points`` the
+        Jacobian is that of the up-sampled trajectory's summed error (cost_functions.py:115-119)."""
         x = self._flatten(trajs)
         B, H, d = x.shape[0], self.n_support_points, self.n_dof
         gp, fields, nf, _ = self._build()
         err = torch.zeros(max(nf, 1), B, H, device=x.device, dtype=torch.float32)
         hobs = torch.zeros(max(nf, 1), B, H, d, device=x.device, dtype=torch.float32)
-        _lib.check(_lib.lib().mpb_gpmp2_linearize(_lib.ptr(x), B, H, C.byref(self.robot.desc), fields, nf,
-                                                  _lib.ptr(err), _lib.ptr(hobs), None, _lib.stream_ptr()))
+        n, w = self.interpolation_weights(n_interpolated_points)
+        _lib.check(_lib.lib().mpb_gpmp2_linearize_ex(_lib.ptr(x), B, H, C.byref(self.robot.desc), fields, nf,
+                                                     _lib.ptr(err), _lib.ptr(hobs), None, n, w, _lib.stream_ptr()))
         return err[:nf], hobs[:nf]
 
     def get_linear_system(self, trajs, n_interpolated_points=None, **kwargs):
@@ -183,12 +316,10 @@ class CostComposite(Cost):
         (cost_functions.py:107-144,191-231,291-314,538-554).  Kept for API parity and diagnostics: the collision
         rows come from the analytic-Jacobian kernel, the (constant) GP rows are laid out with device tensor ops.
         GPMP2._step never calls this -- it solves the block-tridiagonal system without materialising A or K."""
-        if n_interpolated_points is not None:
-            raise NotImplementedError('interpolated collision checking is a "next" row (SURVEY.md 8f)')
         x = self._flatten(trajs)
         B, H, D, d = x.shape[0], self.n_support_points, self.dim, self.n_dof
         N, ta = H * D, dict(device=x.device, dtype=torch.float32)
-        err, hobs = self.linearize_collision(x)
+        err, hobs = self.linearize_collision(x, n_interpolated_points=n_interpolated_points)
         eye = torch.eye(D, **ta)
         As, bs, Ks = [], [], []
         fi = 0
@@ -220,6 +351,8 @@ class CostComposite(Cost):
                 b = err[fi][:, 1:].unsqueeze(-1)
                 K = (torch.eye(H - 1, **ta) * cost.inv_sigma2).expand(B, H - 1, H - 1)
                 fi += 1
+            elif isinstance(cost, (CostGPTrajectory, CostJointLimits)):
+                continue            # their get_linear_system returns nothing in the reference (cost_functions.py:356,428)
             else:
                 raise NotImplementedError(type(cost).__name__)
             As.append(A), bs.append(b), Ks.append(K)
@@ -237,7 +370,7 @@ class CostComposite(Cost):
         """bool [B]: every collision hinge term of the trajectory (waypoints 1..H-1) is exactly 0."""
         x = self._flatten(trajs)
         flags = torch.empty(x.shape[0], device=x.device, dtype=torch.uint8)
-        self.eval(x, free_flag=flags)
+        self._eval_full(x, free_flag=flags)
         return flags.bool()
 
 

@@ -67,6 +67,7 @@ extern "C" int mpb_sizeof_desc(int which) {
         case 0: return (int)sizeof(mpb_robot_desc);
         case 1: return (int)sizeof(mpb_field_desc);
         case 2: return (int)sizeof(mpb_gp_desc);
+        case 3: return (int)sizeof(mpb_extra_cost_desc);
         default: return -1;
     }
 }

@@ -29,6 +29,7 @@ struct ChompArgs {
     int n_iters;
     unsigned rows_off;
     int row_stride;
+    mpb_extra_cost_desc ex;   // jl_enabled: CostJointLimits term in the cost
 };
 
 template <int KIND>
@@ -69,6 +70,16 @@ __global__ void __launch_bounds__(kChompWarps * 32) chomp_kernel(const __grid_co
                         const float wf = a.fields.l[f].weight * a.fields.l[f].inv_sigma2;
 #pragma unroll
                         for (int k = 0; k < MPB_MAX_DOF; ++k) gc[k] = fmaf(wf, g1[k], gc[k]);
+                    }
+                }
+                if (a.ex.jl_enabled) {      // d/dq of w_jl * sum relu(q_min+eps-q)^2 + relu(q-(q_max-eps))^2
+#pragma unroll
+                    for (int k = 0; k < MPB_MAX_DOF; ++k) {
+                        if (k < d) {
+                            const float lo = fmaxf(__fsub_rn(__fadd_rn(__ldg(a.ex.q_min + k), a.ex.jl_eps), xt[k]), 0.f);
+                            const float hi = fmaxf(__fsub_rn(xt[k], __fsub_rn(__ldg(a.ex.q_max + k), a.ex.jl_eps)), 0.f);
+                            gc[k] = fmaf(a.ex.w_jl, 2.f * (hi - lo), gc[k]);
+                        }
                     }
                 }
                 const double r0 = (double)__ldg(a.R + (size_t)t * H + t - 1), r1 = (double)__ldg(a.R + (size_t)t * H + t),
@@ -112,7 +123,15 @@ static cudaError_t launch_chomp(const ChompArgs& a, int grid, size_t smem, cudaS
 extern "C" int mpb_chomp_run(float* x, int P, int H, const mpb_robot_desc* robot, const mpb_field_desc* fields,
                              int n_fields, const float* R, float smooth_scale, float lr, float grad_clip, int n_iters,
                              void* stream) {
+    return mpb_chomp_run_ex(x, P, H, robot, fields, n_fields, R, smooth_scale, lr, grad_clip, n_iters, nullptr, stream);
+}
+
+extern "C" int mpb_chomp_run_ex(float* x, int P, int H, const mpb_robot_desc* robot, const mpb_field_desc* fields,
+                                int n_fields, const float* R, float smooth_scale, float lr, float grad_clip, int n_iters,
+                                const mpb_extra_cost_desc* extra, void* stream) {
     using namespace mpb;
+    MPB_REQUIRE(!extra || !extra->gp_traj_enabled, "mpb_chomp_run: the GP-trajectory term has no fused CHOMP gradient");
+    MPB_REQUIRE(!extra || !extra->jl_enabled || (extra->q_min && extra->q_max), "mpb_chomp_run: joint-limit term needs q_min / q_max");
     MPB_REQUIRE(P >= 0 && n_iters >= 0, "mpb_chomp_run: negative P or n_iters");
     if (P == 0 || n_iters == 0) return MPB_OK;
     MPB_REQUIRE(x && robot && R, "mpb_chomp_run: null x/robot/R");
@@ -134,6 +153,7 @@ extern "C" int mpb_chomp_run(float* x, int P, int H, const mpb_robot_desc* robot
         MPB_REQUIRE(!why, "mpb_chomp_run: %s", why);
     }
     for (int i = 0; i < n_fields; ++i) a.fields.f[i] = fields[i];
+    if (extra && extra->jl_enabled) a.ex = *extra;
     a.R = R; a.smooth2 = 2.f * smooth_scale; a.lr = lr; a.clip = grad_clip; a.n_iters = n_iters;
     unsigned off = layout_fields(a.fields, 0);
     off = layout_robot(*robot, a.rl, off);

@@ -37,6 +37,8 @@ struct CostArgs {
     int row_stride;                    // floats
     unsigned* sched;                   // [2] dynamic scheduler: next trajectory index, finished CTAs (self-resetting)
     int list_cap;                      // broad-phase list entries per warp (max primitives of one field)
+    mpb_extra_cost_desc ex;            // CostGPTrajectory / CostJointLimits (only read by the XF variant)
+    float* jl_out;                     // [B] raw joint-limit term per trajectory
 };
 
 // Per-warp queue of flagged spheres: structure of arrays in shared memory at byte offset `base`
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
         __syncwarp();
         if (b_next < a.B) issue_row(a.x + (size_t)b_next * M, xnext, M, vec_ok, lane);
 
-        double acc_gp = 0.0, acc_goal = 0.0, acc_is = 0.0;
+        double acc_gp = 0.0, acc_goal = 0.0, acc_is = 0.0, acc_gpt = 0.0, acc_jl = 0.0;
         HingeAcc hacc;
 #pragma unroll
         for (int f = 0; f < MPB_MAX_FIELDS; ++f) hacc.h[f] = 0.f;
@@ -311,6 +313,31 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
                         c = fmaf(e * a.gp.k_goal, e, c);
                     }
                     acc_goal += (double)c;
+                }
+            }
+            // ---- optional extra terms (before FK overwrites the joint angles) ------------
+            if (XF && valid) {
+                if (a.ex.gp_traj_enabled && t < H - 1) {          // CostGPTrajectory: GP factors with their own sigma
+                    const float* xn = xt + D;
+                    float c = 0.f;
+#pragma unroll 1
+                    for (int k = 0; k < d; ++k) {
+                        const float ep = xn[k] - fmaf(a.gp.dt, xt[d + k], xt[k]);
+                        const float ev = xn[d + k] - xt[d + k];
+                        c = fmaf(fmaf(a.ex.t11, ep, a.ex.t12 * ev), ep, c);
+                        c = fmaf(fmaf(a.ex.t12, ep, a.ex.t22 * ev), ev, c);
+                    }
+                    acc_gpt += (double)c;
+                }
+                if (a.ex.jl_enabled) {                            // CostJointLimits: squared violation, all waypoints
+                    float c = 0.f;
+#pragma unroll 1
+                    for (int k = 0; k < d; ++k) {
+                        const float lo = fmaxf(__fsub_rn(__fadd_rn(__ldg(a.ex.q_min + k), a.ex.jl_eps), xt[k]), 0.f);
+                        const float hi = fmaxf(__fsub_rn(xt[k], __fsub_rn(__ldg(a.ex.q_max + k), a.ex.jl_eps)), 0.f);
+                        c = fmaf(lo, lo, fmaf(hi, hi, c));
+                    }
+                    acc_jl += (double)c;
                 }
             }
             // ---- importance-sampling dot  x . (Sigma^-1 mu_p) ---------------------------
@@ -454,6 +481,16 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
                 ++term;
             }
         }
+        if (XF && a.ex.gp_traj_enabled) {
+            const float c = a.ex.w_gp_traj * (float)warp_sum(acc_gpt);
+            total += c;
+            if (a.terms && lane == 0) a.terms[(size_t)term * a.B + b] = c;
+            ++term;
+        }
+        if (XF && a.ex.jl_enabled) {
+            const float c = (float)warp_sum(acc_jl);
+            if (a.jl_out && lane == 0) a.jl_out[b] = c;
+        }
         if (isv) total += a.is_scale * (float)warp_sum(acc_is);
         const int all_free = __all_sync(MPB_FULL_MASK, hacc.all_zero);
         if (lane == 0) {
@@ -501,6 +538,15 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
                              const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp,
                              const float* is_vec, int samples_per_particle, float is_scale,
                              float* cost, float* terms, uint8_t* free_flag, void* stream) {
+    return mpb_cost_eval_ex(x, B, H, robot, fields, n_fields, gp, is_vec, samples_per_particle, is_scale, cost, terms,
+                            free_flag, nullptr, nullptr, stream);
+}
+
+extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_desc* robot,
+                                const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp,
+                                const float* is_vec, int samples_per_particle, float is_scale,
+                                float* cost, float* terms, uint8_t* free_flag,
+                                const mpb_extra_cost_desc* extra, float* jl_per_traj, void* stream) {
     using namespace mpb;
     MPB_REQUIRE(B >= 0, "mpb_cost_eval: negative batch size %d", B);
     if (B == 0) return MPB_OK;
@@ -532,6 +578,16 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
     } else {
         a.gp.enabled = 0;
     }
+    bool has_extra_terms = false;
+    if (extra && (extra->gp_traj_enabled || extra->jl_enabled)) {
+        MPB_REQUIRE(!extra->jl_enabled || (extra->q_min && extra->q_max && jl_per_traj),
+                    "mpb_cost_eval: joint-limit term needs q_min, q_max and jl_per_traj");
+        a.ex = *extra;
+        a.jl_out = jl_per_traj;
+        if (extra->gp_traj_enabled && !a.gp.enabled) a.gp.dt = gp ? gp->dt : 0.f;     // Phi needs dt
+        MPB_REQUIRE(!extra->gp_traj_enabled || gp, "mpb_cost_eval: the GP-trajectory term takes dt from the gp descriptor");
+        has_extra_terms = true;
+    }
     a.is_vec = is_vec; a.S = is_vec ? samples_per_particle : 1; a.is_scale = is_scale;
     a.cost = cost; a.terms = terms; a.free_flag = free_flag;
 
@@ -559,7 +615,7 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
     const int blocks_needed = (B + kWarps - 1) / kWarps;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    if (a.fields.has_extra)       // self-collision / workspace fields present: the variant that carries those passes
+    if (a.fields.has_extra || has_extra_terms)   // self-collision / workspace fields or extra terms: the variant that carries them
         e = (robot->kind == MPB_ROBOT_POINT) ? launch<MPB_ROBOT_POINT, 1, true>(a, blocks_needed, smem, st)
                                              : launch<MPB_ROBOT_CHAIN, 4, true>(a, blocks_needed, smem, st);
     else
@@ -570,4 +626,33 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
         return MPB_ECUDA;
     }
     return check_launch("mpb_cost_eval");
+}
+
+namespace mpb {
+// out[b,j] = sum_t x[b,t,j] * (R[t,t-1] x[b,t-1,j] + R[t,t] x[b,t,j] + R[t,t+1] x[b,t+1,j])
+__global__ void smoothness_cost_kernel(const float* __restrict__ x, const float* __restrict__ R, float* __restrict__ out,
+                                       int B, int H, int D) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * D) return;
+    const int b = (int)(i / D), j = (int)(i % D);
+    const float* xb = x + (size_t)b * H * D + j;
+    double acc = 0.0;
+    for (int t = 0; t < H; ++t) {
+        double r = (double)__ldg(R + (size_t)t * H + t) * (double)xb[(size_t)t * D];
+        if (t > 0) r += (double)__ldg(R + (size_t)t * H + t - 1) * (double)xb[(size_t)(t - 1) * D];
+        if (t < H - 1) r += (double)__ldg(R + (size_t)t * H + t + 1) * (double)xb[(size_t)(t + 1) * D];
+        acc += (double)xb[(size_t)t * D] * r;
+    }
+    out[i] = (float)acc;
+}
+}  // namespace mpb
+
+extern "C" int mpb_smoothness_cost(const float* x, const float* R, float* out, int B, int H, int D, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(B >= 0 && H >= 1 && D >= 1, "mpb_smoothness_cost: bad sizes");
+    if (B == 0) return MPB_OK;
+    MPB_REQUIRE(x && R && out, "mpb_smoothness_cost: null pointer");
+    const long long n = (long long)B * D;
+    smoothness_cost_kernel<<<(unsigned)((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(x, R, out, B, H, D);
+    return check_launch("mpb_smoothness_cost");
 }

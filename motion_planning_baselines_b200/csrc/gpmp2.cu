@@ -32,6 +32,8 @@ struct LinArgs {
     FieldArgs fields;
     float* err;        // [nf,B,H]
     float* hobs;       // [nf,B,H,d]
+    int n_interp;      // extra points per segment (0: none)
+    float w[MPB_MAX_INTERP + 1];
 };
 
 template <int KIND>
@@ -54,6 +56,28 @@ __global__ void __launch_bounds__(128) gpmp2_linearize_kernel(const __grid_const
             float e = 0.f;
             if (t >= 1) {                               // waypoint 0 carries no collision factor (cost_functions.py:165-169)
                 e = waypoint_err_grad<KIND>(smem, a.fields.l[f], a.rl, a.robot.ws_dim, point_r, q, d, g);
+                // interpolated collision checking: the Jacobian row of waypoint t collects the gradients of the
+                // up-sampled points of both adjacent segments, weighted by d p / d q_t (field_factor.py:44-57)
+#pragma unroll 1
+                for (int k = 1; k <= a.n_interp; ++k) {
+                    const float wk = a.w[k], uk = __fsub_rn(1.f, wk);
+                    float qi[MPB_MAX_DOF], gi[MPB_MAX_DOF];
+                    if (t < a.H - 1) {                  // segment t -> t+1: p = q_t (1-w) + q_{t+1} w
+#pragma unroll
+                        for (int j = 0; j < MPB_MAX_DOF; ++j)
+                            qi[j] = (j < d) ? __fadd_rn(__fmul_rn(q[j], uk), __fmul_rn(__ldg(xt + a.D + j), wk)) : 0.f;
+                        waypoint_err_grad<KIND>(smem, a.fields.l[f], a.rl, a.robot.ws_dim, point_r, qi, d, gi);
+#pragma unroll
+                        for (int j = 0; j < MPB_MAX_DOF; ++j) g[j] = fmaf(uk, gi[j], g[j]);
+                    }
+                    // segment t-1 -> t: p = q_{t-1} (1-w) + q_t w
+#pragma unroll
+                    for (int j = 0; j < MPB_MAX_DOF; ++j)
+                        qi[j] = (j < d) ? __fadd_rn(__fmul_rn(__ldg(xt - a.D + j), uk), __fmul_rn(q[j], wk)) : 0.f;
+                    waypoint_err_grad<KIND>(smem, a.fields.l[f], a.rl, a.robot.ws_dim, point_r, qi, d, gi);
+#pragma unroll
+                    for (int j = 0; j < MPB_MAX_DOF; ++j) g[j] = fmaf(wk, gi[j], g[j]);
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < MPB_MAX_DOF; ++k) g[k] = 0.f;
@@ -347,7 +371,15 @@ extern "C" long long mpb_gpmp2_workspace_bytes(int B, int H, int D) {
 extern "C" int mpb_gpmp2_linearize(const float* x, int B, int H, const mpb_robot_desc* robot,
                                    const mpb_field_desc* fields, int n_fields, float* err, float* hobs,
                                    double* diag_mean, void* stream) {
+    return mpb_gpmp2_linearize_ex(x, B, H, robot, fields, n_fields, err, hobs, diag_mean, 0, nullptr, stream);
+}
+
+extern "C" int mpb_gpmp2_linearize_ex(const float* x, int B, int H, const mpb_robot_desc* robot,
+                                      const mpb_field_desc* fields, int n_fields, float* err, float* hobs,
+                                      double* diag_mean, int n_interp, const float* interp_w_host, void* stream) {
     using namespace mpb;
+    MPB_REQUIRE(n_interp >= 0 && n_interp <= MPB_MAX_INTERP && (n_interp == 0 || interp_w_host),
+                "mpb_gpmp2_linearize: n_interp must be in [0,%d] with a weight array", MPB_MAX_INTERP);
     MPB_REQUIRE(B >= 0, "mpb_gpmp2_linearize: negative batch size");
     if (B == 0 || n_fields == 0) return MPB_OK;
     MPB_REQUIRE(x && robot && fields && err && hobs, "mpb_gpmp2_linearize: null pointer");
@@ -369,6 +401,11 @@ extern "C" int mpb_gpmp2_linearize(const float* x, int B, int H, const mpb_robot
     }
     for (int i = 0; i < n_fields; ++i) a.fields.f[i] = fields[i];
     a.err = err; a.hobs = hobs;
+    a.n_interp = n_interp;
+    for (int k = 0; k <= n_interp && n_interp > 0; ++k) {
+        MPB_REQUIRE(interp_w_host[k] >= 0.f && interp_w_host[k] < 1.f, "mpb_gpmp2_linearize: interpolation weights must lie in [0,1)");
+        a.w[k] = interp_w_host[k];
+    }
     unsigned off = layout_fields(a.fields, 0);
     off = layout_robot(*robot, a.rl, off);
     const size_t smem = off;

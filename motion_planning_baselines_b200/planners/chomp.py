@@ -67,9 +67,21 @@ class CHOMP(OptimizationPlanner):
         if gp.enabled:
             raise NotImplementedError('the fused CHOMP gradient covers CostCollision terms (GP terms: use GPMP2)')
         P_glob = self.num_particles_global if self.num_particles_global is not None else P
-        _lib.check(_lib.lib().mpb_chomp_run(_lib.ptr(self._particle_means), P, H, C.byref(self.cost.robot.desc), fields, nf,
-                                            _lib.ptr(self.Sigma_inv), float(P_glob) * float(self.weight_prior_cost),
-                                            float(self.lr), float(self.grad_clip), int(opt_iters), _lib.stream_ptr()))
+        extra = self.cost._extra
+        if extra is not None and extra.gp_traj_enabled:
+            raise NotImplementedError('the fused CHOMP gradient covers CostCollision and CostJointLimits terms')
+        if extra is not None:
+            # CostJointLimits is one scalar for the whole batch that the composite adds to EVERY particle's cost; the
+            # reference back-propagates costs.sum() (chomp.py:139), so its gradient carries a factor P -- the same
+            # mechanism as the P-scaled smoothness term (quirk B1)
+            scaled = _lib.ExtraCostDesc()
+            C.memmove(C.byref(scaled), C.byref(extra), C.sizeof(scaled))
+            scaled.w_jl = float(extra.w_jl) * float(P_glob)
+            extra = scaled
+        _lib.check(_lib.lib().mpb_chomp_run_ex(_lib.ptr(self._particle_means), P, H, C.byref(self.cost.robot.desc), fields, nf,
+                                               _lib.ptr(self.Sigma_inv), float(P_glob) * float(self.weight_prior_cost),
+                                               float(self.lr), float(self.grad_clip), int(opt_iters),
+                                               C.byref(extra) if extra is not None else None, _lib.stream_ptr()))
 
     def _eval(self, x, **observation):
         """costs [P] = cost(x) + weight_prior_cost * (smoothness summed over ALL particles)  (chomp.py:153-169).

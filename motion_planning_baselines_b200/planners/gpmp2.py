@@ -29,8 +29,7 @@ class GPMP2(OptimizationPlanner):
                          start_state=start_state, initial_particle_means=initial_particle_means,
                          multi_goal_states=multi_goal_states, sigma_start_init=sigma_start_init,
                          sigma_goal_init=sigma_goal_init, sigma_gp_init=sigma_gp_init, pos_only=False, **kwargs)
-        if n_interpolated_points is not None:
-            raise NotImplementedError('interpolated collision checking is a "next" row (SURVEY.md 8f)')
+        self.n_interpolated_points = n_interpolated_points
         self.robot = robot
         self.d_state_opt = 2 * self.n_dof
         self.goal_directed = multi_goal_states is not None
@@ -116,8 +115,10 @@ class GPMP2(OptimizationPlanner):
         gp, fields, nf, _ = self.cost._build()
         lib, st = _lib.lib(), _lib.stream_ptr()
         trust = bool(self.solver_params.get('trust_region', False))
-        _lib.check(lib.mpb_gpmp2_linearize(_lib.ptr(self._particle_means), B, H, C.byref(self.robot.desc), fields, nf,
-                                           _lib.ptr(w['err']), _lib.ptr(w['hobs']), _lib.ptr(w['dm']) if trust else None, st))
+        n_int, w_int = self.cost.interpolation_weights(self.n_interpolated_points)
+        _lib.check(lib.mpb_gpmp2_linearize_ex(_lib.ptr(self._particle_means), B, H, C.byref(self.robot.desc), fields, nf,
+                                              _lib.ptr(w['err']), _lib.ptr(w['hobs']), _lib.ptr(w['dm']) if trust else None,
+                                              n_int, w_int, st))
         if trust and self.batch_split is not None and self.batch_split.world > 1:
             import torch.distributed as dist
             # local mean -> global mean: sum of (local mean * local count) over ranks / global count

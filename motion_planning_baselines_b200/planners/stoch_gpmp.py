@@ -144,6 +144,8 @@ class StochGPMP(OptimizationPlanner):
         P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
         M = H * D
         gp, fields, nf, _ = self.cost._build()
+        if self.cost._extra is not None:      # extra_costs (joint limits, ...): the staged path carries them
+            return self._optimize_staged(opt_iters, eps, **observation)
         lib = _lib.lib()
         pos_mean = vel_mean = None
         for it in range(opt_iters):
@@ -165,6 +167,17 @@ class StochGPMP(OptimizationPlanner):
         self._recent_state_trajectories = self.state_samples[..., :self.n_dof]
         self._recent_control_particles = vel_mean
         self._recent_state_particles = pos_mean
+        self._recent_weights = self._weights
+        return self._get_traj()
+
+    def _optimize_staged(self, opt_iters, eps=None, **observation):
+        """optimize() through sample_and_eval + _update_distribution (composites with extra cost terms)."""
+        P, S, M = self.num_particles, self.num_samples, self.n_support_points * self.d_state_opt
+        for it in range(opt_iters):
+            e = eps[it] if eps is not None else torch.randn(S, P, M, **self.tensor_args)
+            (self._recent_control_samples, self._recent_state_trajectories, self._recent_control_particles,
+             self._recent_state_particles, costs) = self.sample_and_eval(eps=e, **observation)
+            self._update_distribution(costs, self.state_samples)
         self._recent_weights = self._weights
         return self._get_traj()
 

@@ -6,11 +6,46 @@ Functional restatement of
   * CostCollision.eval / get_linear_system   cost_functions.py:171-231 (+ field_factor.py:17-57)
   * CostComposite.eval / get_linear_system   cost_functions.py:70-144
   * build_gpmp2_cost_composite defaults      mp_baselines/planners/gpmp2.py:23-89
+  * CostGPTrajectory / CostSmoothnessCHOMP / CostJointLimits .eval   cost_functions.py:317-429
 Pinned by tests/golden/*.npz (generated from the unmodified reference).
 """
 import torch
 
 from .gp_prior import gp_Q_inv, phi_matrix, unary_K
+
+
+def interpolate_points(trajs, n_interpolated_points):
+    """Linear joint-space up-sampling with n extra points between consecutive waypoints: [B,H,D] ->
+    [B,(H-1)(n+1)+1,D].  The reference imports ``interpolate_points_v1`` from the absent torch_robotics
+    (cost_functions.py:13,118): PARITY UNPINNED, this is the spec (same as oracle/ref_shim)."""
+    B, H, D = trajs.shape
+    w = torch.linspace(0, 1, n_interpolated_points + 2, dtype=trajs.dtype, device=trajs.device)[:-1]
+    seg = trajs[:, :-1].unsqueeze(2) * (1 - w).view(1, 1, -1, 1) + trajs[:, 1:].unsqueeze(2) * w.view(1, 1, -1, 1)
+    return torch.cat((seg.reshape(B, -1, D), trajs[:, -1:]), dim=1)
+
+
+def joint_limits_cost(x, q_min, q_max, eps):
+    """CostJointLimits.eval (cost_functions.py:393-426): squared violation of the limits shrunk by eps, SUMMED OVER
+    THE WHOLE BATCH -- the reference's ``.sum(-1)`` runs over the flat list of violating entries, so the result
+    is a 0-dim tensor that a composite adds to every trajectory (quirk B14)."""
+    d = q_min.shape[0]
+    q = x[..., :d]
+    lower = torch.relu((q_min + eps) - q)
+    upper = torch.relu(q - (q_max - eps))
+    return (lower ** 2).sum() + (upper ** 2).sum()
+
+
+def smoothness_chomp_cost(x, R):
+    """CostSmoothnessCHOMP.eval (cost_functions.py:371-387): x[:, :, j]^T R x[:, :, j] per trajectory and state
+    column -> [B, D] (``batched_weighted_dot_prod`` is external; semantics as in oracle/ref_shim)."""
+    return (x.transpose(-1, -2) @ R.unsqueeze(0) @ x).diagonal(dim1=-2, dim2=-1)
+
+
+def gp_trajectory_cost(x, Phi, Q_inv):
+    """CostGPTrajectory.eval (cost_functions.py:343-354): the GP-prior part of CostGP without the start term."""
+    D = x.shape[-1]
+    e = (x[:, 1:].unsqueeze(-1) - Phi @ x[:, :-1].unsqueeze(-1))
+    return (e.transpose(2, 3) @ Q_inv.reshape(1, 1, D, D) @ e).sum(1).squeeze()
 
 
 class CostSpec:
@@ -83,9 +118,11 @@ class CostSpec:
         return free
 
     # ------------------------------------------------- linear system (GPMP2)
-    def linear_system(self, x):
+    def linear_system(self, x, n_interpolated_points=None):
         """Dense (A, b, K) with rows [start D | GP (H-1)D | goal D | (H-1) per field]
-        (cost_functions.py:107-144, 291-314, 538-554, 191-231)."""
+        (cost_functions.py:107-144, 291-314, 538-554, 191-231).  With n_interpolated_points the collision
+        Jacobian is that of the summed error over the linearly up-sampled trajectory (first point dropped) w.r.t.
+        the support points, while b stays the error AT the support points (field_factor.py:41-57)."""
         ta, D, H, d = self.tensor_args, self.D, self.H, self.d
         B, N = x.shape[0], self.D * self.H
         x = x.detach().clone().requires_grad_(True)
@@ -114,9 +151,16 @@ class CostSpec:
             K = self.K_goal.expand(B, D, D)
             As.append(A), bs.append(b), Ks.append(K)
 
+        x_interp = None if n_interpolated_points is None else interpolate_points(x, n_interpolated_points)
         for f in self.fields:
             err = self.collision_errors(x, f)                                 # [B,H-1]
-            grad = torch.autograd.grad(err.sum(), x, retain_graph=True)[0]
+            if x_interp is None:
+                err_j = err
+            else:
+                qi = self.robot.get_position(x_interp)
+                li = self.robot.fk_map_collision(qi)
+                err_j = f.compute_cost(qi[:, 1:], li[:, 1:], trajs_interp=x_interp).reshape(B, -1)   # quirk B6: the kwarg leaks
+            grad = torch.autograd.grad(err_j.sum(), x, retain_graph=True)[0]
             Hobs = -grad[:, 1:, :d]                                           # [B,H-1,d]
             A = torch.zeros(B, H - 1, N, **ta)
             for t in range(H - 1):

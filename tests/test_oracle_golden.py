@@ -166,3 +166,57 @@ def test_gpmp2_steps(name):
         step = (T(g[f'means{it + 1}']) - means).abs().max()
         assert_close(out['means'], g[f'means{it + 1}'], rtol=1e-3, atol=float(2e-3 * step), what='means')
         means = T(g[f'means{it + 1}'])
+
+
+# ---------------------------------------------------------------- SURVEY 8(f) "next" rows (oracle/make_golden_next.py)
+@pytest.mark.parametrize('name', ['gpmp2_interp_pm2d', 'gpmp2_interp_panda'])
+def test_gpmp2_interpolated_linear_system(name):
+    from motion_planning_baselines_b200 import configs
+    from oracle import planners as op
+    from oracle.build import TA, oracle_field, oracle_robot
+    from oracle.costs import CostSpec
+    g = load_golden(name)
+    m = g['meta']
+    cfg = configs.config(m['cfg'])
+    spec = CostSpec(oracle_robot(cfg['robot'], m['dt']), m['H'], m['dt'], T(g['start']), T(g['goal']),
+                    [oracle_field(cfg['obstacles'], cfg['robot'])], sigma_start=m['sigma_start'], sigma_gp=m['sigma_gp'],
+                    sigma_coll=m['sigma_coll'], sigma_goal_prior=m['sigma_goal_prior'], tensor_args=TA)
+    x = T(g['means0'])
+    A, b, K = spec.linear_system(x, n_interpolated_points=m['n_interp'])
+    scale = float(np.abs(g['A0']).max())
+    assert np.abs(A.numpy() - g['A0']).max() <= 1e-5 * scale
+    assert np.abs(g['A0'] - g['A0_plain']).max() > 1e-3 * scale, 'fixture must exercise the interpolation'
+    np.testing.assert_allclose(b.numpy(), g['b0'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(torch.diagonal(K, dim1=-2, dim2=-1).numpy(), g['Kdiag0'], rtol=1e-6)
+    A0, _, _ = spec.linear_system(x, n_interpolated_points=None)
+    assert np.abs(A0.numpy() - g['A0_plain']).max() <= 1e-5 * scale
+
+
+@pytest.mark.parametrize('name', ['extra_costs_pm2d', 'extra_costs_panda'])
+def test_extra_cost_terms(name):
+    from motion_planning_baselines_b200 import configs
+    from oracle import costs as oc
+    from oracle import gp_prior
+    from oracle import planners as op
+    from oracle.build import TA, oracle_field, oracle_robot
+    g = load_golden(name)
+    m = g['meta']
+    cfg = configs.config(m['cfg'])
+    robot = oracle_robot(cfg['robot'], m['dt'])
+    x = T(g['x'])
+    d, H = m['d'], m['H']
+    jl = oc.joint_limits_cost(x, robot.q_min, robot.q_max, m['eps'])
+    assert jl.ndim == 0
+    np.testing.assert_allclose(jl.numpy(), g['joint_limits'], rtol=1e-5)
+    sm = oc.smoothness_chomp_cost(x, op.chomp_R(H, m['dt'], TA))
+    np.testing.assert_allclose(sm.numpy(), g['smoothness'], rtol=1e-5, atol=1e-5 * float(np.abs(g['smoothness']).max()))
+    gpt = oc.gp_trajectory_cost(x, gp_prior.phi_matrix(d, m['dt'], TA), gp_prior.gp_Q_inv(d, m['dt'], m['sigma_gp'], TA))
+    np.testing.assert_allclose(gpt.numpy(), g['gp_traj'], rtol=1e-5)
+    spec = oc.CostSpec(robot, H, m['dt'], x[0, 0, :d], None, [oracle_field(cfg['obstacles'], cfg['robot'])],
+                       sigma_start=m['sigma_start'], sigma_gp=m['sigma_gp'], sigma_coll=m['sigma_coll'], tensor_args=TA)
+    w = m['weights']
+    total = w[0] * spec.gp_cost(x) + w[1] * spec.collision_cost(x, spec.fields[0]) + w[2] * jl + w[3] * gpt
+    np.testing.assert_allclose(spec.gp_cost(x).numpy(), g['term_gp'], rtol=1e-5)
+    np.testing.assert_allclose(spec.collision_cost(x, spec.fields[0]).numpy(), g['term_coll'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(total.numpy(), g['composite'], rtol=1e-5)
+    assert np.array_equal(g['composite_interp'], g['composite']), 'trajs_interpolated is ineffective in the reference'
