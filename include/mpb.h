@@ -283,6 +283,38 @@ int mpb_mppi_rollout(const float* L_ctrl, const float* Cov_inv, const float* mea
 int mpb_mppi_finalize(const float* quad, const float* isv, const double* energy, float temp, float* cost,
                       int N, int C, void* stream);
 
+/* ---- plug points of the UNMODIFIED reference planners (csrc/interop.cu) ----------------------------------------
+ * A reference planner that keeps its own Python loop calls its duck-typed robot / field / cost objects one at a
+ * time; these entry points back those methods, so the objects of this library drop into it as they are.
+ *
+ * robot.fk_map_collision(q_pos) (cost_functions.py:50-52): link_pos[n,s,:] = centre of collision sphere s at q[n,:].
+ * Chain robots only (a point robot's single sphere centre is q itself).  q [N,d] -> link_pos [N,Ns,3]. */
+int mpb_fk_spheres(const float* q, long long N, const mpb_robot_desc* robot, float* link_pos, void* stream);
+/* Its backward for torch.autograd (the reference differentiates through FK, field_factor.py:52-57, chomp.py:139):
+ * grad_q[n,k] = sum_s grad_link[n,s,:] . d link_pos[n,s,:] / d q[n,k]. */
+int mpb_fk_spheres_vjp(const float* q, const float* grad_link, long long N, const mpb_robot_desc* robot, float* grad_q,
+                       void* stream);
+/* field.compute_cost(q_pos, link_pos) (costs/factors/field_factor.py:39): err[n] = the field's hinge sum at the sphere
+ * centres link_pos[n] ([N,Ns,ws_dim]; radii and self-collision pair indices refer to robot's sphere table);
+ * grad_link [N,Ns,ws_dim]|NULL = d err[n] / d link_pos[n] (relu'(0) = 0 as in torch). */
+int mpb_field_cost(const float* link_pos, long long N, const mpb_robot_desc* robot, const mpb_field_desc* field,
+                   float* err, float* grad_link, void* stream);
+/* grad[b,t,:] = gout[b] * d cost[b] / d x[b,t,:] for the cost mpb_cost_eval_ex computes (fields, start/GP/goal terms,
+ * the CostGPTrajectory term) + w_jl * jl_gsum[0] * d jl[b] / d x[b,t,:] for the batch-summed joint-limit term.
+ * Backs `cost(x).sum().backward()` of the reference CHOMP loop (chomp.py:134-139) on the fused cost object; the
+ * collision part is analytic.  gout [B]|NULL (ones); jl_gsum device scalar|NULL (1); gp->dt is read even when
+ * gp->enabled == 0 and the GP-trajectory term is on. */
+int mpb_cost_grad(const float* x, int B, int H, const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
+                  const mpb_gp_desc* gp, const mpb_extra_cost_desc* extra, const float* gout, const float* jl_gsum,
+                  float* grad, void* stream);
+/* task.compute_collision(q) of the sample-based planners (rrt_base.py:100-101), batched over N configurations, and
+ * the per-waypoint flags behind the examples' trajectory statistics (examples/pointmass_dense_2d_CHOMP.py:130-133):
+ * row n of q starts at q + n*row_stride (row_stride = d for a list of configurations, D for a [B,H,D] trajectory
+ * tensor viewed as B*H states).  in_collision [N]|NULL: 1 iff any hinge of any field is > 0;
+ * err [N]|NULL: sum over fields of the unweighted hinge sums. */
+int mpb_collision_query(const float* q, long long N, int row_stride, const mpb_robot_desc* robot,
+                        const mpb_field_desc* fields, int n_fields, uint8_t* in_collision, float* err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,12 @@ _SIGNATURES = {
     'mpb_sum_f64': (C.c_int, [_vp, C.c_longlong, _vp, _vp, _vp]),
     'mpb_mppi_rollout': (C.c_int, [_vp] * 11 + [_i, _i, _i, _i, _f, _f, _f, _f, _f, _vp]),
     'mpb_mppi_finalize': (C.c_int, [_vp, _vp, _vp, _f, _vp, _i, _i, _vp]),
+    'mpb_fk_spheres': (C.c_int, [_vp, C.c_longlong, C.POINTER(RobotDesc), _vp, _vp]),
+    'mpb_fk_spheres_vjp': (C.c_int, [_vp, _vp, C.c_longlong, C.POINTER(RobotDesc), _vp, _vp]),
+    'mpb_field_cost': (C.c_int, [_vp, C.c_longlong, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _vp, _vp, _vp]),
+    'mpb_cost_grad': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
+                                C.POINTER(ExtraCostDesc), _vp, _vp, _vp, _vp]),
+    'mpb_collision_query': (C.c_int, [_vp, C.c_longlong, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _vp, _vp]),
 }
 
 

@@ -52,6 +52,8 @@ class CostCollision(Cost):
             raise _lib.MpbError('CostCollision needs a motion_planning_baselines_b200.fields.Field '
                                 '(CollisionField, SelfCollisionField or WorkspaceBoundaryField)')
         self.field = field
+        if field is not None and field.robot is None:
+            field.bind_robot(robot)                         # compute_cost() needs the sphere table (plug point 2)
         self.sigma_coll = sigma_coll
         self.inv_sigma2 = 1. / (sigma_coll ** 2)          # FieldFactor.K (field_factor.py:15)
 
@@ -245,6 +247,11 @@ class CostComposite(Cost):
             raise _lib.MpbError('trajs_interpolated must have the batch size of trajs')
         if kwargs.get('obstacle_spheres') is not None:
             raise NotImplementedError('per-call obstacle_spheres are not supported')
+        if trajs.requires_grad and torch.is_grad_enabled() and not return_invidual_costs_and_weights:
+            # the reference CHOMP loop differentiates the cost object: costs.sum().backward() (chomp.py:134-139)
+            if is_vec is not None:
+                raise NotImplementedError('the importance-sampling term has no fused gradient')
+            return _CostEvalGrad.apply(trajs, self)
         res = self._eval_full(trajs, return_terms=return_invidual_costs_and_weights, is_vec=is_vec,
                               samples_per_particle=samples_per_particle, is_scale=is_scale, out=out, free_flag=free_flag)
         if return_invidual_costs_and_weights:
@@ -284,6 +291,25 @@ class CostComposite(Cost):
             zero = torch.zeros(B, **ta)
             per_cost = [jl_sum if i == -2 else (terms[i] if i >= 0 else zero) for i in term_index]
         return cost, jl_sum, per_cost
+
+    def grad(self, trajs, grad_out=None):
+        """d (sum_b grad_out[b] * cost[b]) / d trajs, analytic (``mpb_cost_grad``): what autograd through FK + SDF
+        gives the reference (chomp.py:139).  trajs [B,H,D] (or [N,B,H,D]); grad_out [B] | None (ones)."""
+        x = self._flatten(trajs.detach())
+        B = x.shape[0]
+        gp, fields, nf, _ = self._build()
+        extra = self._extra
+        if extra is not None and extra.gp_traj_enabled and not gp.enabled:
+            gp.dt = [c for c in self.cost_l if isinstance(c, CostGPTrajectory)][0].dt
+        g = torch.empty_like(x)
+        go = None if grad_out is None else grad_out.reshape(-1).contiguous().float()
+        gsum = None
+        if extra is not None and extra.jl_enabled:     # the joint-limit scalar is added to EVERY trajectory of the batch
+            gsum = go.sum().reshape(1) if go is not None else torch.full((1,), float(B), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().mpb_cost_grad(
+            _lib.ptr(x), B, self.n_support_points, C.byref(self.robot.desc), fields, nf, C.byref(gp),
+            C.byref(extra) if extra is not None else None, _lib.ptr(go), _lib.ptr(gsum), _lib.ptr(g), _lib.stream_ptr()))
+        return g.view(trajs.shape)
 
     @staticmethod
     def interpolation_weights(n_interpolated_points):
@@ -372,6 +398,22 @@ class CostComposite(Cost):
         flags = torch.empty(x.shape[0], device=x.device, dtype=torch.uint8)
         self._eval_full(x, free_flag=flags)
         return flags.bool()
+
+
+class _CostEvalGrad(torch.autograd.Function):
+    """CostComposite.eval with an analytic backward (plug point 1 of SURVEY 8b: a cost object handed to the reference
+    CHOMP must survive ``costs.sum().backward()``)."""
+
+    @staticmethod
+    def forward(ctx, trajs, composite):
+        ctx.composite = composite
+        ctx.save_for_backward(trajs)
+        return composite._eval_full(trajs.detach())[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (trajs,) = ctx.saved_tensors
+        return ctx.composite.grad(trajs, grad_out), None
 
 
 def build_gpmp2_cost_composite(robot=None, n_support_points=None, dt=None, start_state=None, multi_goal_states=None,

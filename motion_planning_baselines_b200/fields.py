@@ -13,11 +13,54 @@ from .models import ObstacleSet
 class Field:
     """Anything a CostCollision can hold: produces a ``mpb_field_desc`` for the fused kernels."""
 
+    robot = None
+
     def desc(self, weight=1.0, inv_sigma2=1.0):
         raise NotImplementedError
 
     def zero_grad(self):
         pass
+
+    def bind_robot(self, robot):
+        """The robot whose sphere table (radii, link indices) ``compute_cost`` refers to.  Set by the ``robot=``
+        constructor argument or by the first CostCollision built around this field."""
+        self.robot = robot
+        return self
+
+    def compute_cost(self, q_pos, link_pos, **kwargs):
+        """The method ``FieldFactor.get_error`` calls (costs/factors/field_factor.py:39): hinge sum of every
+        configuration, link_pos [..., Ns, ws_dim] -> [...].  Unknown keyword arguments are ignored (the reference
+        forwards ``obstacle_spheres`` and, by accident, ``trajs_interp``: SURVEY quirk B6).  Differentiable w.r.t.
+        ``link_pos`` (the reference takes the Jacobian by autograd, field_factor.py:52-57); the fused planners of this
+        package never call it."""
+        if self.robot is None:
+            raise _lib.MpbError('compute_cost needs the robot sphere table: construct the field with robot=... '
+                                '(or call field.bind_robot(robot))')
+        return _FieldCost.apply(link_pos, self)
+
+
+class _FieldCost(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, link_pos, field):
+        robot = field.robot
+        _lib.require_f32(link_pos)
+        ns, ws = robot.model.n_spheres, robot.ws_dim
+        if tuple(link_pos.shape[-2:]) != (ns, ws):
+            raise _lib.MpbError(f'link_pos must end in [{ns}, {ws}] for robot {robot.name}, got {tuple(link_pos.shape)}')
+        lp = link_pos.detach().reshape(-1, ns, ws).contiguous()
+        err = torch.empty(lp.shape[0], device=lp.device, dtype=torch.float32)
+        need = link_pos.requires_grad
+        grad = torch.empty_like(lp) if need else None
+        fdesc = field.desc()
+        _lib.check(_lib.lib().mpb_field_cost(_lib.ptr(lp), lp.shape[0], robot.desc, fdesc, _lib.ptr(err), _lib.ptr(grad),
+                                             _lib.stream_ptr()))
+        ctx.grad_link = grad
+        return err.view(link_pos.shape[:-2])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g = ctx.grad_link
+        return (g * grad_out.reshape(-1, 1, 1)).view(*grad_out.shape, g.shape[-2], g.shape[-1]), None
 
 
 def _cuda_args(tensor_args):
@@ -30,8 +73,9 @@ def _cuda_args(tensor_args):
 
 
 class CollisionField(Field):
-    def __init__(self, obstacles: ObstacleSet, tensor_args=None):
+    def __init__(self, obstacles: ObstacleSet, tensor_args=None, robot=None):
         self.tensor_args = _cuda_args(tensor_args)
+        self.robot = robot
         self.obstacles = obstacles
         self.cutoff_margin = obstacles.cutoff_margin
         ws = obstacles.ws_dim
@@ -60,8 +104,9 @@ class SelfCollisionField(Field):
     examples/panda_spheres_GPMP.py:41-45; MPB_FIELD_SELF).  ``pairs`` [Np,2] index the robot's sphere table;
     they are re-ordered here as the C ABI wants them: link(i) < link(j), sorted by (link(i), link(j))."""
 
-    def __init__(self, robot_model, pairs=None, cutoff_margin=0.0, tensor_args=None):
+    def __init__(self, robot_model, pairs=None, cutoff_margin=0.0, tensor_args=None, robot=None):
         self.tensor_args = _cuda_args(tensor_args)
+        self.robot = robot
         if robot_model.kind != 'chain':
             raise _lib.MpbError('self-collision fields need a chain robot')
         if pairs is None:
@@ -93,8 +138,9 @@ class WorkspaceBoundaryField(Field):
     relu(r_s + cutoff_margin - sdf) summed over the robot's spheres (the role of the external task's
     workspace-boundary field; MPB_FIELD_WORKSPACE)."""
 
-    def __init__(self, ws_min, ws_max, cutoff_margin=0.0, tensor_args=None):
+    def __init__(self, ws_min, ws_max, cutoff_margin=0.0, tensor_args=None, robot=None):
         self.tensor_args = _cuda_args(tensor_args)
+        self.robot = robot
         self.ws_min = [float(v) for v in np.asarray(ws_min).reshape(-1)]
         self.ws_max = [float(v) for v in np.asarray(ws_max).reshape(-1)]
         assert len(self.ws_min) == len(self.ws_max) and len(self.ws_min) in (2, 3)

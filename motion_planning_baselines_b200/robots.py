@@ -48,6 +48,34 @@ class Robot:
     def get_velocity(self, x):
         return x[..., self.q_dim:2 * self.q_dim]
 
+    def fk_map_collision(self, q_pos, **kwargs):
+        """Centres of the collision spheres, [..., d] -> [..., Ns, ws_dim]: the method the reference's
+        ``Cost.get_q_pos_vel_and_fk_map`` calls (cost_functions.py:50-52).  The fused kernels never call it (they keep
+        the link frames in registers); it exists so that an unmodified reference planner can use this robot.
+        Differentiable: the backward is ``mpb_fk_spheres_vjp``."""
+        if self.model.kind != 'chain':
+            return q_pos[..., :self.ws_dim].unsqueeze(-2)
+        return _FkSpheres.apply(q_pos, self)
+
+
+class _FkSpheres(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_pos, robot):
+        _lib.require_f32(q_pos)
+        q = q_pos.detach().reshape(-1, robot.q_dim).contiguous()
+        out = torch.empty(q.shape[0], robot.model.n_spheres, 3, device=q.device, dtype=torch.float32)
+        _lib.check(_lib.lib().mpb_fk_spheres(_lib.ptr(q), q.shape[0], robot.desc, _lib.ptr(out), _lib.stream_ptr()))
+        ctx.robot, ctx.q = robot, q
+        return out.view(*q_pos.shape[:-1], robot.model.n_spheres, 3)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        robot, q = ctx.robot, ctx.q
+        g = grad_out.reshape(-1, robot.model.n_spheres, 3).contiguous().float()
+        gq = torch.empty_like(q)
+        _lib.check(_lib.lib().mpb_fk_spheres_vjp(_lib.ptr(q), _lib.ptr(g), q.shape[0], robot.desc, _lib.ptr(gq), _lib.stream_ptr()))
+        return gq.view(*grad_out.shape[:-2], robot.q_dim), None
+
 
 def RobotPointMass(q_dim=2, radius=0.0, dt=1.0, tensor_args=None):
     return Robot(point_mass_model(q_dim, radius), dt=dt, tensor_args=tensor_args)

@@ -1,5 +1,6 @@
 """Aggregate ncu per-instruction 'Instructions Executed' by CUDA source line (needs -lineinfo build).
-usage: ncu_lines.py <report.ncu-rep> <object.o> <kernel-mangled-substring>"""
+usage: ncu_lines.py <report.ncu-rep> <object.o> <kernel-mangled-substring> [top-N] [ncu -k regex, needed when the report holds
+several kernels]"""
 import csv, sys, subprocess, collections, re, os, tempfile
 rep, obj, ksub = sys.argv[1], sys.argv[2], sys.argv[3]
 tmp = tempfile.mkdtemp()
@@ -17,7 +18,8 @@ for l in dis:
     if m: cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
     m = re.match(r'\s*/\*([0-9a-f]{4,})\*/', l)
     if m: line_of[int(m.group(1), 16)] = cur
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+kflt = ['-k', 'regex:' + sys.argv[5]] if len(sys.argv) > 5 else []
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + kflt, capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hi = [i for i, r in enumerate(rows) if 'Source' in r and 'Address' in r][0]
 hdr = rows[hi]
