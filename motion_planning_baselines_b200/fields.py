@@ -49,7 +49,7 @@ class _FieldCost(torch.autograd.Function):
             raise _lib.MpbError(f'link_pos must end in [{ns}, {ws}] for robot {robot.name}, got {tuple(link_pos.shape)}')
         lp = link_pos.detach().reshape(-1, ns, ws).contiguous()
         err = torch.empty(lp.shape[0], device=lp.device, dtype=torch.float32)
-        need = link_pos.requires_grad
+        need = ctx.needs_input_grad[0]
         grad = torch.empty_like(lp) if need else None
         fdesc = field.desc()
         _lib.check(_lib.lib().mpb_field_cost(_lib.ptr(lp), lp.shape[0], robot.desc, fdesc, _lib.ptr(err), _lib.ptr(grad),
