@@ -131,6 +131,25 @@ int mpb_sample_gp_tc_supported(int P, int S, int M);
 int mpb_sample_gp_tc(const float* L_hi, const float* L_lo, const float* mu, const float* eps, float* x,
                      int P, int S, int M, void* stream);
 
+/* Structured FP32 variant of mpb_sample_gp for a factor that decouples over the degrees of freedom
+ * (csrc/sample_gp_kron.cu).  The reference's prior precision (mp_priors_multi.py:213-251 with the identity-scaled
+ * K_s, K_g, Q_c of unary_factor.py:19 / gp_factor.py:23-26) couples only entries of the same dof, and
+ * torch's factorisation keeps exact zeros exact, so L @ eps is `dof` independent [2H,2H] triangular mat-vecs.
+ *   mpb_sample_gp_kron_pack : checks bit-exactly that every dropped entry of L [M,M] (M = 2*H*dof, state order
+ *                             (t,[pos|vel],j)) is 0.0f (*structured = 1, host int) and writes the per-dof blocks
+ *                             k-major: LkT [dof][2H][2H], LkT[j][2t'+b][2t+a] = L[(t,a,j),(t',b,j)].  Synchronises
+ *                             `stream` (one-off setup).
+ *   mpb_sample_gp_kron      : same contract and layouts as mpb_sample_gp; identical to the dense FP32 sum in
+ *                             ascending k.  Shapes: mpb_sample_gp_kron_supported(H, dof) != 0; 16-byte aligned pointers. */
+int mpb_sample_gp_kron_supported(int H, int dof);
+int mpb_sample_gp_kron_pack(const float* L, float* LkT, int H, int dof, int* structured, void* stream);
+int mpb_sample_gp_kron(const float* LkT, const float* mu, const float* eps, float* x,
+                       int P, int S, int H, int dof, void* stream);
+/* Tensor-core variant (warp-level m16n8k8 TF32 MMA, 3xTF32 split of both operands, fp32 accumulation): same
+ * contract; agrees with mpb_sample_gp_kron to ~1e-6 of the noise amplitude. */
+int mpb_sample_gp_kron_tc(const float* LkT, const float* mu, const float* eps, float* x,
+                          int P, int S, int H, int dof, void* stream);
+
 /* STOMP noise: x[p,s,h,j] = mu[p,h,j] + (h==0||h==H-1 ? 0 : sum_k L_R[h,k] eps[s,j,p,k])
  * Replaces STOMP.sample (mp_baselines/planners/stomp.py:97-108); eps is [S,D,P,H]. */
 int mpb_sample_stomp(const float* L_R, const float* mu, const float* eps, float* x,
@@ -185,7 +204,16 @@ int mpb_softmax_update(const float* cost, const float* x, float* mu, float* weig
 /* One fused Stoch-GPMP iteration = sample_gp -> prior_matvec -> cost_eval(+IS) -> softmax_update.
  * Replaces the body of StochGPMP.optimize (stoch_gpmp.py:291-299).
  * L_split: NULL (FP32 SIMT sampler) or the [2,M,M] output of mpb_split_tf32 (tensor-core sampler).
- * workspace: x [P,S,H,D], cost [P,S], weights [P,S], is_vec [P,M]; free_flag [P*S] may be NULL. */
+ * workspace: x [P,S,H,D], cost [P,S], weights [P,S], is_vec [P,M]; free_flag [P*S] may be NULL.
+ * mpb_stoch_gpmp_iter_kron: same, sampling through mpb_sample_gp_kron with the packed factor L_kron. */
+int mpb_stoch_gpmp_iter_kron(const float* L_kron, const float* Sigma_inv, const float* eps,
+                             float* mu, float* x, float* cost, float* weights, float* is_vec,
+                             uint8_t* free_flag,
+                             int P, int S, int H,
+                             const mpb_robot_desc* robot,
+                             const mpb_field_desc* fields, int n_fields,
+                             const mpb_gp_desc* gp,
+                             float temp, float step, void* stream);
 int mpb_stoch_gpmp_iter(const float* L, const float* L_split, const float* Sigma_inv, const float* eps,
                         float* mu, float* x, float* cost, float* weights, float* is_vec,
                         uint8_t* free_flag,

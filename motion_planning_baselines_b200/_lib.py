@@ -59,6 +59,10 @@ _SIGNATURES = {
     'mpb_split_tf32': (C.c_int, [_vp, _vp, _vp, C.c_longlong, _vp]),
     'mpb_sample_gp_tc_supported': (C.c_int, [_i, _i, _i]),
     'mpb_sample_gp_tc': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'mpb_sample_gp_kron_supported': (C.c_int, [_i, _i]),
+    'mpb_sample_gp_kron_pack': (C.c_int, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _vp]),
+    'mpb_sample_gp_kron': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'mpb_sample_gp_kron_tc': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'mpb_sample_stomp': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'mpb_prior_matvec': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'mpb_cost_eval': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
@@ -70,6 +74,9 @@ _SIGNATURES = {
     'mpb_stoch_gpmp_iter': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                       C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
                                       _f, _f, _vp]),
+    'mpb_stoch_gpmp_iter_kron': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                           C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
+                                           _f, _f, _vp]),
     'mpb_chomp_run': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _f, _f, _f, _i, _vp]),
     'mpb_chomp_run_ex': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _f, _f, _f, _i,
                                    C.POINTER(ExtraCostDesc), _vp]),

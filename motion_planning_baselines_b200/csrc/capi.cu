@@ -90,3 +90,18 @@ extern "C" int mpb_stoch_gpmp_iter(const float* L, const float* L_split, const f
     if (rc) return rc;
     return mpb_softmax_update(cost, x, mu, weights, nullptr, temp, step, nullptr, P, S, H, D, stream);
 }
+
+extern "C" int mpb_stoch_gpmp_iter_kron(const float* L_kron, const float* Sigma_inv, const float* eps, float* mu, float* x,
+                                        float* cost, float* weights, float* is_vec, uint8_t* free_flag, int P, int S,
+                                        int H, const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
+                                        const mpb_gp_desc* gp, float temp, float step, void* stream) {
+    MPB_REQUIRE(robot, "mpb_stoch_gpmp_iter_kron: robot is null");
+    const int D = 2 * robot->q_dim, M = H * D;
+    int rc = mpb_sample_gp_kron(L_kron, mu, eps, x, P, S, H, robot->q_dim, stream);
+    if (rc) return rc;
+    rc = mpb_prior_matvec(Sigma_inv, mu, is_vec, P, M, 2 * D - 1, stream);
+    if (rc) return rc;
+    rc = mpb_cost_eval(x, P * S, H, robot, fields, n_fields, gp, is_vec, S, temp, cost, nullptr, free_flag, stream);
+    if (rc) return rc;
+    return mpb_softmax_update(cost, x, mu, weights, nullptr, temp, step, nullptr, P, S, H, D, stream);
+}

@@ -1,0 +1,497 @@
+// K1s (structured FP32 variant): GP-prior sampling  x[p,s,:] = mu[p,:] + L @ eps[s,p,:]  for a factor that
+// decouples over the degrees of freedom.
+//
+// Replaces MultiMPPrior.sample (mp_baselines/planners/costs/factors/mp_priors_multi.py:253-256).  The reference's
+// prior precision is A^T Q^-1 A with K_s, K_g and Q_c proportional to the identity (unary_factor.py:19,
+// gp_factor.py:23-26,42-50), so in the state ordering (t, [pos|vel], j) it only couples entries of the SAME dof j.
+// Cholesky and the triangular solve (torch _precision_to_scale_tril) keep exact zeros exact, hence scale_tril has
+// L[(t,a,j),(t',b,j')] == 0.0f whenever j != j': the [M,M] mat-vec is really `dof` independent [2H,2H] lower-triangular
+// mat-vecs (7x fewer flops for the Panda; 2H = 128).  The per-dof blocks are NOT bit-identical to each other (fp32
+// round-off of an ill-conditioned factorisation), so all `dof` blocks are kept.  mpb_sample_gp_kron_pack verifies the
+// zero pattern bit-exactly and extracts the blocks; dropping exact zeros from an fp32 sum changes nothing, so the
+// result equals the dense FP32 sum over the same ascending k order.
+//
+// Mapping: persistent CTAs, one tile = 32 sample rows x M columns staged in shared memory TRANSPOSED ([column][row],
+// XOR-swizzled so that both the transposing stores and the 128-bit row reads are bank-conflict free).  One warp group
+// per dof; warp a of a group owns the 16-row output blocks a and NB-1-a (the triangular work of the pair is the same
+// for every a); lanes = 4 row quads x 8 sample quads, 4x4 register tile.  The factor block streams through a per-warp
+// double-buffered cp.async ring (16 k x 16 rows per chunk), no CTA barrier inside the contraction.  Results go back
+// into the tile in place; the store phase adds mu_p and writes full 32-byte sectors; the next tile's rows are already
+// in flight in registers while the current tile is stored.  Bound: FP32 FMA issue (16 FFMA per 2 LDS.128).
+#include "mpb_common.cuh"
+
+namespace mpb {
+
+constexpr int kTileRows = 32;
+
+template <int DOF, int H>
+struct KronCfg {
+    static constexpr int D = 2 * DOF, M = H * D, N = 2 * H;       // N = rows/cols of one per-dof block
+    static constexpr int NB = N / 16;                              // 16-row output blocks per dof
+    static constexpr int WPD = NB / 2;                             // warps per dof
+    static constexpr int WARPS = DOF * WPD, THREADS = WARPS * 32;
+    static constexpr int TILE_FLOATS = kTileRows * M;
+    static constexpr int LBUF_FLOATS = 2 * 16 * 16;                // per warp: two chunks of 16 k x 16 rows
+    static constexpr int ITEMS = M / 4;                            // (half tile of 16 rows) x (8-column group)
+    static constexpr int IPW = ITEMS / WARPS;                      // = 8 for every (DOF, H)
+    static constexpr size_t SMEM = (size_t)(TILE_FLOATS + WARPS * LBUF_FLOATS) * sizeof(float);
+    static_assert(H % 16 == 0, "H must be a multiple of 16");
+    static_assert(ITEMS % WARPS == 0 && IPW == 8, "tile load mapping");
+    static_assert(THREADS <= 1024, "too many warps");
+};
+
+__device__ __forceinline__ int tile_off(int c, int r) { return c * kTileRows + (r ^ ((c & 7) << 2)); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int DOF, int H>
+__global__ void __launch_bounds__(KronCfg<DOF, H>::THREADS, 1)
+sample_gp_kron_kernel(const float* __restrict__ LkT, const float* __restrict__ mu, const float* __restrict__ eps,
+                      float* __restrict__ x, int P, int S) {
+    using Cfg = KronCfg<DOF, H>;
+    constexpr int D = Cfg::D, M = Cfg::M, N = Cfg::N, NB = Cfg::NB, WPD = Cfg::WPD, WARPS = Cfg::WARPS;
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* lbuf = smem + Cfg::TILE_FLOATS + warp * Cfg::LBUF_FLOATS;
+
+    const long long Ntot = (long long)P * S;
+    const int ntiles = (int)((Ntot + kTileRows - 1) / kTileRows);
+
+    // contraction role
+    const int j = warp / WPD, a = warp - j * WPD;
+    const int ig = lane >> 3, sg = lane & 7;
+    const float* Lj = LkT + (size_t)j * N * N;
+    int xo[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) xo[m] = (4 * sg) ^ (((m + j) & 7) << 2);
+
+    // tile load / store role: lane -> (row within a 16-row half, 4-column quad of an 8-column group)
+    const int rl = lane >> 1, cl = lane & 1;
+
+    float4 pre[Cfg::IPW];
+    auto gload = [&](int t) {
+        const long long n0 = (long long)t * kTileRows;
+        const float* src[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const long long n = n0 + hf * 16 + rl;
+            if (n < Ntot) {
+                const int p = (int)(n / S), s = (int)(n - (long long)p * S);
+                src[hf] = eps + ((size_t)s * P + p) * M;
+            } else {
+                src[hf] = nullptr;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < Cfg::IPW; ++it) {
+            const int item = warp + it * WARPS;
+            const int hf = item & 1, c0 = (item >> 1) * 8 + cl * 4;
+            const float* sp = hf ? src[1] : src[0];
+            pre[it] = sp ? __ldg(reinterpret_cast<const float4*>(sp + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int it = 0; it < Cfg::IPW; ++it) {
+            const int item = warp + it * WARPS;
+            const int hf = item & 1, c0 = (item >> 1) * 8 + cl * 4, r = hf * 16 + rl;
+            tile[(c0 + 0) * kTileRows + (r ^ ((cl * 4 + 0) << 2))] = pre[it].x;
+            tile[(c0 + 1) * kTileRows + (r ^ ((cl * 4 + 1) << 2))] = pre[it].y;
+            tile[(c0 + 2) * kTileRows + (r ^ ((cl * 4 + 2) << 2))] = pre[it].z;
+            tile[(c0 + 3) * kTileRows + (r ^ ((cl * 4 + 3) << 2))] = pre[it].w;
+        }
+    };
+
+    // out[16*blk + 4*ig + ii][4*sg + ss] = sum_{k < 16*(blk+1)} LkT[k][16*blk + 4*ig + ii] * e[k][4*sg + ss]
+    auto contract = [&](int blk, float (&acc)[4][4]) {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss) acc[ii][ss] = 0.f;
+        const int nchunks = blk + 1;
+        const float* lsrc = Lj + (size_t)(lane >> 2) * N + 16 * blk + 4 * (lane & 3);     // row kk = lane>>2 (+8)
+        float* ldst = lbuf + (lane >> 2) * 16 + 4 * (lane & 3);
+        auto issue = [&](int q) {
+            float* dst = ldst + (q & 1) * 256;
+            const float* s0 = lsrc + (size_t)q * 16 * N;
+            cp_async16(dst, s0);
+            cp_async16(dst + 8 * 16, s0 + (size_t)8 * N);
+            cp_async_commit();
+        };
+        issue(0);
+        for (int q = 0; q < nchunks; ++q) {
+            cp_async_wait_all();
+            __syncwarp();
+            if (q + 1 < nchunks) issue(q + 1);
+            const float* lb = lbuf + (q & 1) * 256 + 4 * ig;
+            const float* eb = tile + (size_t)(q * 8 * D + j) * kTileRows;
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+                const int cK = (kk >> 1) * D + (kk & 1) * DOF;          // column of k within the chunk, minus j
+                const float4 e = *reinterpret_cast<const float4*>(eb + cK * kTileRows + xo[cK & 7]);
+                const float4 l = *reinterpret_cast<const float4*>(lb + kk * 16);
+                const float lv[4] = {l.x, l.y, l.z, l.w}, ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int ss = 0; ss < 4; ++ss) acc[ii][ss] = fmaf(lv[ii], ev[ss], acc[ii][ss]);
+            }
+        }
+        __syncwarp();
+    };
+    auto put = [&](int blk, const float (&acc)[4][4]) {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const int i = 16 * blk + 4 * ig + ii;
+            const int c = (i >> 1) * D + (i & 1) * DOF + j;
+            *reinterpret_cast<float4*>(tile + c * kTileRows + ((4 * sg) ^ ((c & 7) << 2))) =
+                make_float4(acc[ii][0], acc[ii][1], acc[ii][2], acc[ii][3]);
+        }
+    };
+
+    int t = blockIdx.x;
+    if (t < ntiles) gload(t);
+    for (; t < ntiles; t += gridDim.x) {
+        sstore();
+        __syncthreads();
+        float acc0[4][4], acc1[4][4];
+        contract(a, acc0);
+        contract(NB - 1 - a, acc1);
+        __syncthreads();                       // every read of the noise tile is done: overwrite it in place
+        put(a, acc0);
+        put(NB - 1 - a, acc1);
+        __syncthreads();
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) gload(tn);            // next tile's rows fly while this one is stored
+        const long long n0 = (long long)t * kTileRows;
+        const float* mrow[2];
+        float* xrow[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const long long n = n0 + hf * 16 + rl;
+            if (n < Ntot) {
+                mrow[hf] = mu + (size_t)(n / S) * M;
+                xrow[hf] = x + (size_t)n * M;
+            } else {
+                mrow[hf] = nullptr;
+                xrow[hf] = nullptr;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < Cfg::IPW; ++it) {
+            const int item = warp + it * WARPS;
+            const int hf = item & 1, c0 = (item >> 1) * 8 + cl * 4, r = hf * 16 + rl;
+            float* xr = hf ? xrow[1] : xrow[0];
+            const float* mr = hf ? mrow[1] : mrow[0];
+            if (xr) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mr + c0));
+                float4 o;
+                o.x = m4.x + tile[(c0 + 0) * kTileRows + (r ^ ((cl * 4 + 0) << 2))];
+                o.y = m4.y + tile[(c0 + 1) * kTileRows + (r ^ ((cl * 4 + 1) << 2))];
+                o.z = m4.z + tile[(c0 + 2) * kTileRows + (r ^ ((cl * 4 + 2) << 2))];
+                o.w = m4.w + tile[(c0 + 3) * kTileRows + (r ^ ((cl * 4 + 3) << 2))];
+                *reinterpret_cast<float4*>(xr + c0) = o;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- tensor-core variant (legacy warp-level MMA, 3xTF32) -------------------------------------------------------------
+// Same work split (one warp group per dof, warp a owns the 16-row blocks a and NB-1-a, per-warp cp.async ring for the
+// factor block); the 16-row x 32-sample output block of a warp is four m16n8k8 TF32 MMAs per 8 k.  Both operands are
+// split into a TF32-representable high part (mantissa truncated to 10 bits) and the exact fp32 remainder;
+// lo*hi + hi*lo + hi*hi accumulate in fp32 (the dropped lo*lo term is 2^-20 relative).  Fragments are gathered by the
+// threads themselves, so the per-dof column stride of the noise rows costs nothing -- which is why this kernel uses
+// mma.sync and not tcgen05: a tcgen05 formulation needs the factor block resident next to a >= 128-sample tile in
+// canonical core-matrix layout, and a 32-row tile of all dofs already fills shared memory.
+// The tile keeps the rows in their NATURAL layout [32 rows][M + 4]: rows are copied global->shared with coalesced
+// 16-byte cp.async (no registers), the padded stride (= 4 mod 32) makes the B-fragment gathers and the accumulator
+// scatter bank-conflict free, and the store phase is a coalesced row copy that adds mu_p and immediately refills the
+// slot it has just read with the next tile's noise, so the next tile streams in while this one is written out.
+template <int DOF, int H>
+struct KronMmaCfg : KronCfg<DOF, H> {
+    using Base = KronCfg<DOF, H>;
+    static constexpr int RS = Base::M + 4;                         // padded row stride in floats
+    static constexpr int TILE_FLOATS = kTileRows * RS;
+    static constexpr int V4_PER_ROW = Base::M / 4;
+    static constexpr int IPT = kTileRows * V4_PER_ROW / Base::THREADS;   // float4 slots per thread = 8
+    static constexpr size_t SMEM = (size_t)(TILE_FLOATS + Base::WARPS * Base::LBUF_FLOATS) * sizeof(float) + 2 * kTileRows * 16;
+    static_assert(RS % 32 == 4, "row stride must be 4 mod 32");
+    static_assert(kTileRows * V4_PER_ROW % Base::THREADS == 0, "tile copy mapping");
+};
+
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(__fsub_rn(v, __uint_as_float(hi)));
+}
+
+struct KronRow {            // per tile row: where its noise comes from and which particle it belongs to
+    long long src;          // float offset of the eps row, or -1 past the end
+    int p, pad;
+};
+
+template <int DOF, int H>
+__global__ void __launch_bounds__(KronCfg<DOF, H>::THREADS, 1)
+sample_gp_kron_mma_kernel(const float* __restrict__ LkT, const float* __restrict__ mu, const float* __restrict__ eps,
+                          float* __restrict__ x, int P, int S) {
+    using Cfg = KronMmaCfg<DOF, H>;
+    constexpr int M = Cfg::M, N = Cfg::N, NB = Cfg::NB, WPD = Cfg::WPD, RS = Cfg::RS, THREADS = Cfg::THREADS;
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* lbuf = smem + Cfg::TILE_FLOATS + warp * Cfg::LBUF_FLOATS;
+    KronRow* rows = reinterpret_cast<KronRow*>(smem + Cfg::TILE_FLOATS + Cfg::WARPS * Cfg::LBUF_FLOATS);   // [2][32]
+
+    const long long Ntot = (long long)P * S;
+    const int ntiles = (int)((Ntot + kTileRows - 1) / kTileRows);
+
+    const int j = warp / WPD, a = warp - j * WPD;
+    const int g = lane >> 2, t4 = lane & 3;
+    const float* Lj = LkT + (size_t)j * N * N;
+
+    auto row_table = [&](int t, int buf) {          // threads 0..31
+        const long long n = (long long)t * kTileRows + threadIdx.x;
+        KronRow r;
+        r.src = -1; r.p = 0; r.pad = 0;
+        if (n < Ntot) {
+            const int p = (int)(n / S), s = (int)(n - (long long)p * S);
+            r.src = ((long long)s * P + p) * M;
+            r.p = p;
+        }
+        rows[buf * kTileRows + threadIdx.x] = r;
+    };
+    auto fill_slot = [&](int buf, int r, int v) {   // float4 slot (row r, 4-column group v) <- next tile's noise
+        const long long src = rows[buf * kTileRows + r].src;
+        float* dst = tile + r * RS + 4 * v;
+        if (src >= 0) cp_async16_cg(dst, eps + src + 4 * v);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+
+    // acc[n][.] : m16n8 accumulator of n-tile n (samples 8n..8n+7) for rows 16*blk .. 16*blk+15
+    auto contract = [&](int blk, float (&acc)[4][4]) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+        const int nchunks = blk + 1;
+        // staging: lane -> (k row kk = lane>>2 (+8), 4-row part = lane&3); 16-byte chunks XOR-swizzled by bit 1 of kk
+        const int skk = lane >> 2, spart = lane & 3;
+        const float* lsrc = Lj + (size_t)skk * N + 16 * blk + 4 * spart;
+        float* ldst = lbuf + skk * 16 + ((4 * spart) ^ (((skk >> 1) & 1) << 3));
+        auto issue = [&](int q) {
+            float* dst = ldst + (q & 1) * 256;
+            const float* s0 = lsrc + (size_t)q * 16 * N;
+            cp_async16(dst, s0);
+            cp_async16(dst + 8 * 16, s0 + (size_t)8 * N);     // kk + 8 has the same swizzle bit
+            cp_async_commit();
+        };
+        const int a0off = t4 * 16 + (g ^ (((t4 >> 1) & 1) << 3));
+        // B fragment: element (k, sample) = tile[sample * RS + DOF*k + j]; k = 16q + 8ks + t4 (+4), sample = 8n + g
+        const float* ebase = tile + g * RS + DOF * t4 + j;
+        issue(0);
+        for (int q = 0; q < nchunks; ++q) {
+            cp_async_wait_all();
+            __syncwarp();
+            if (q + 1 < nchunks) issue(q + 1);
+            const float* lb = lbuf + (q & 1) * 256;
+            const float* eb = ebase + q * 16 * DOF;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint32_t ahi[4], alo[4];
+                split_tf32(lb[ks * 128 + a0off], ahi[0], alo[0]);
+                split_tf32(lb[ks * 128 + (a0off ^ 8)], ahi[1], alo[1]);
+                split_tf32(lb[ks * 128 + 64 + a0off], ahi[2], alo[2]);
+                split_tf32(lb[ks * 128 + 64 + (a0off ^ 8)], ahi[3], alo[3]);
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const float* e0 = eb + ks * 8 * DOF + n * 8 * RS;
+                    uint32_t bhi0, blo0, bhi1, blo1;
+                    split_tf32(e0[0], bhi0, blo0);
+                    split_tf32(e0[4 * DOF], bhi1, blo1);
+                    mma_tf32(acc[n], alo, bhi0, bhi1);
+                    mma_tf32(acc[n], ahi, blo0, blo1);
+                    mma_tf32(acc[n], ahi, bhi0, bhi1);
+                }
+            }
+        }
+        __syncwarp();
+    };
+    auto put = [&](int blk, const float (&acc)[4][4]) {
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            float* col = tile + DOF * (16 * blk + g + 8 * hrow) + j + 2 * t4 * RS;   // == (i>>1)*D + (i&1)*DOF + j
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                col[(8 * n) * RS] = acc[n][2 * hrow];
+                col[(8 * n + 1) * RS] = acc[n][2 * hrow + 1];
+            }
+        }
+    };
+
+    int t = blockIdx.x;
+    int buf = 0;
+    if (t < ntiles) {
+        if (threadIdx.x < kTileRows) row_table(t, 0);
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < Cfg::IPT; ++it) {
+            const int e = threadIdx.x + it * THREADS;
+            fill_slot(0, e / Cfg::V4_PER_ROW, e % Cfg::V4_PER_ROW);
+        }
+        cp_async_commit();
+    }
+    for (; t < ntiles; t += gridDim.x, buf ^= 1) {
+        const int tn = t + gridDim.x;
+        cp_async_wait_all();
+        __syncthreads();                               // tile t has landed
+        float acc0[4][4], acc1[4][4];
+        contract(a, acc0);
+        contract(NB - 1 - a, acc1);
+        if (tn < ntiles && threadIdx.x < kTileRows) row_table(tn, buf ^ 1);
+        __syncthreads();                               // every read of the noise tile is done: overwrite it in place
+        put(a, acc0);
+        put(NB - 1 - a, acc1);
+        __syncthreads();
+        const long long n0 = (long long)t * kTileRows;
+#pragma unroll
+        for (int it = 0; it < Cfg::IPT; ++it) {
+            const int e = threadIdx.x + it * THREADS;
+            const int r = e / Cfg::V4_PER_ROW, v = e % Cfg::V4_PER_ROW;
+            if (n0 + r < Ntot) {
+                const float4 nz = *reinterpret_cast<const float4*>(tile + r * RS + 4 * v);
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu + (size_t)rows[buf * kTileRows + r].p * M + 4 * v));
+                float4 o;
+                o.x = m4.x + nz.x; o.y = m4.y + nz.y; o.z = m4.z + nz.z; o.w = m4.w + nz.w;
+                *reinterpret_cast<float4*>(x + (size_t)(n0 + r) * M + 4 * v) = o;
+            }
+            if (tn < ntiles) fill_slot(buf ^ 1, r, v);   // same thread, same slot: ordered after its own read above
+        }
+        cp_async_commit();
+    }
+    cp_async_wait_all();
+}
+
+// LkT[j][k][i] = L[(t,a,j),(t',b,j)] with i = 2t+a, k = 2t'+b;  *bad |= 1 if any entry that the structured sampler
+// drops (different dof, or above the diagonal) is not exactly zero.
+__global__ void kron_pack_kernel(const float* __restrict__ L, float* __restrict__ LkT, int* __restrict__ bad, int H, int dof) {
+    const int D = 2 * dof, M = H * D, N = 2 * H;
+    const long long total = (long long)M * M;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(idx / M), col = (int)(idx - (long long)row * M);
+        const int t = row / D, rr = row - t * D, a = rr / dof, j = rr - a * dof;
+        const int t2 = col / D, cc = col - t2 * D, b = cc / dof, j2 = cc - b * dof;
+        const float v = L[idx];
+        if (j == j2) {
+            const int i = 2 * t + a, k = 2 * t2 + b;
+            if (k > i) {
+                if (v != 0.f) atomicOr(bad, 1);
+                LkT[((size_t)j * N + k) * N + i] = 0.f;
+            } else {
+                LkT[((size_t)j * N + k) * N + i] = v;
+            }
+        } else if (v != 0.f) {
+            atomicOr(bad, 1);
+        }
+    }
+}
+
+template <int DOF, int H, bool MMA>
+static int launch_kron(const float* LkT, const float* mu, const float* eps, float* x, int P, int S, cudaStream_t st) {
+    using Cfg = KronCfg<DOF, H>;
+    auto kern = MMA ? sample_gp_kron_mma_kernel<DOF, H> : sample_gp_kron_kernel<DOF, H>;
+    const size_t smem_bytes = MMA ? KronMmaCfg<DOF, H>::SMEM : Cfg::SMEM;
+    static thread_local int cached_dev = -1, per_sm = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) { set_error("mpb_sample_gp_kron: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+        int n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, Cfg::THREADS, smem_bytes);
+        if (e != cudaSuccess || n < 1) { set_error("mpb_sample_gp_kron: kernel does not fit on this device"); return MPB_ECUDA; }
+        per_sm = n;
+        cached_dev = dev;
+    }
+    const long long ntiles = ((long long)P * S + kTileRows - 1) / kTileRows;
+    const long long cap = (long long)sm_count() * per_sm;
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+    kern<<<grid, Cfg::THREADS, smem_bytes, st>>>(LkT, mu, eps, x, P, S);
+    return check_launch("mpb_sample_gp_kron");
+}
+
+}  // namespace mpb
+
+#define MPB_KRON_SHAPES(X) X(2, 32) X(2, 64) X(2, 128) X(3, 32) X(3, 64) X(3, 128) X(7, 32) X(7, 64)
+
+extern "C" int mpb_sample_gp_kron_supported(int H, int dof) {
+#define X(d, h) if (dof == d && H == h) return 1;
+    MPB_KRON_SHAPES(X)
+#undef X
+    return 0;
+}
+
+extern "C" int mpb_sample_gp_kron_pack(const float* L, float* LkT, int H, int dof, int* structured, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(L && LkT && structured, "mpb_sample_gp_kron_pack: null pointer");
+    MPB_REQUIRE(H >= 1 && dof >= 1 && (long long)H * dof <= 16384, "mpb_sample_gp_kron_pack: bad sizes H=%d dof=%d", H, dof);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int* bad = nullptr;
+    cudaError_t e = cudaMalloc(&bad, sizeof(int));
+    if (e != cudaSuccess) { set_error("mpb_sample_gp_kron_pack: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+    int h_bad = 1;
+    e = cudaMemsetAsync(bad, 0, sizeof(int), st);
+    if (e == cudaSuccess) {
+        const long long total = (long long)H * 2 * dof * H * 2 * dof;
+        const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+        kron_pack_kernel<<<grid, 256, 0, st>>>(L, LkT, bad, H, dof);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(bad);
+    if (e != cudaSuccess) { set_error("mpb_sample_gp_kron_pack: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+    *structured = h_bad ? 0 : 1;
+    return MPB_OK;
+}
+
+static int sample_gp_kron_any(bool mma, const float* LkT, const float* mu, const float* eps, float* x, int P, int S, int H,
+                              int dof, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(LkT && mu && eps && x, "mpb_sample_gp_kron: null pointer");
+    MPB_REQUIRE(P >= 0 && S >= 0, "mpb_sample_gp_kron: bad sizes P=%d S=%d", P, S);
+    MPB_REQUIRE(mpb_sample_gp_kron_supported(H, dof), "mpb_sample_gp_kron: shape H=%d dof=%d has no structured kernel", H, dof);
+    MPB_REQUIRE(((uintptr_t)LkT | (uintptr_t)mu | (uintptr_t)eps | (uintptr_t)x) % 16 == 0, "mpb_sample_gp_kron: pointers must be 16-byte aligned");
+    if (P == 0 || S == 0) return MPB_OK;
+    MPB_REQUIRE((long long)P * S <= 0x7fffffffLL / 2, "mpb_sample_gp_kron: P*S too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define X(d, h) if (dof == d && H == h) return mma ? launch_kron<d, h, true>(LkT, mu, eps, x, P, S, st) : launch_kron<d, h, false>(LkT, mu, eps, x, P, S, st);
+    MPB_KRON_SHAPES(X)
+#undef X
+    return MPB_EINVAL;
+}
+
+extern "C" int mpb_sample_gp_kron(const float* LkT, const float* mu, const float* eps, float* x, int P, int S, int H,
+                                  int dof, void* stream) {
+    return sample_gp_kron_any(false, LkT, mu, eps, x, P, S, H, dof, stream);
+}
+
+extern "C" int mpb_sample_gp_kron_tc(const float* LkT, const float* mu, const float* eps, float* x, int P, int S, int H,
+                                     int dof, void* stream) {
+    return sample_gp_kron_any(true, LkT, mu, eps, x, P, S, H, dof, stream);
+}

@@ -8,6 +8,7 @@ CPU in the working dtype), so that the fused sampler multiplies by bit-identical
 part -- drawing samples every iteration -- runs in the mpb_sample_gp kernel, and ``set_mean`` only
 swaps the mean: the factor of an unchanged precision is never recomputed (reference quirk B4).
 """
+import ctypes as C
 import os
 
 import torch
@@ -88,9 +89,22 @@ class MultiMPPrior:
         self.scale_tril = dist.MultivariateNormal(torch.zeros(self.M), precision_matrix=Sinv_cpu).scale_tril \
             .to(**tensor_args).contiguous()
         self.Sigma_inv = Sinv_cpu.to(**tensor_args).contiguous()
-        # tensor-core sampler operands: L pre-split into two TF32-representable parts (3xTF32 scheme)
+        # Sampler selection (MPB_SAMPLE_GP = kron | tc | simt forces one; default: the first that applies).
+        #  kron: the factor decouples over the dofs (verified bit-exactly on the device) -> per-dof [2H,2H] blocks
+        #  tc  : dense tcgen05 3xTF32 sampler; L pre-split into two TF32-representable parts
+        #  simt: dense FP32 sampler
+        mode = os.environ.get('MPB_SAMPLE_GP', 'auto')
+        H = num_steps + 1
+        self.scale_tril_kron = None
+        if mode in ('auto', 'kron') and state_dim == 2 * dof and _lib.lib().mpb_sample_gp_kron_supported(H, dof):
+            packed = torch.empty(dof, 2 * H, 2 * H, **tensor_args)
+            ok = C.c_int(0)
+            _lib.check(_lib.lib().mpb_sample_gp_kron_pack(_lib.ptr(self.scale_tril), _lib.ptr(packed), H, dof,
+                                                          C.byref(ok), _lib.stream_ptr()))
+            if ok.value:
+                self.scale_tril_kron = packed
         self.scale_tril_split = None
-        if os.environ.get('MPB_SAMPLE_GP', 'tc') != 'simt' and _lib.lib().mpb_sample_gp_tc_supported(1, 1, self.M):
+        if self.scale_tril_kron is None and mode != 'simt' and _lib.lib().mpb_sample_gp_tc_supported(1, 1, self.M):
             self.scale_tril_split = torch.empty(2, self.M, self.M, **tensor_args)
             _lib.check(_lib.lib().mpb_split_tf32(_lib.ptr(self.scale_tril), _lib.ptr(self.scale_tril_split[0]),
                                                  _lib.ptr(self.scale_tril_split[1]), self.M * self.M, _lib.stream_ptr()))
@@ -133,7 +147,10 @@ class MultiMPPrior:
         assert eps.shape == (S, P, M)
         x = out if out is not None else torch.empty(P, S, M, **self.tensor_args)
         eps = eps.contiguous()
-        if self.scale_tril_split is not None:
+        if self.scale_tril_kron is not None:
+            _lib.check(_lib.lib().mpb_sample_gp_kron(_lib.ptr(self.scale_tril_kron), _lib.ptr(self.means), _lib.ptr(eps),
+                                                     _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))
+        elif self.scale_tril_split is not None:
             _lib.check(_lib.lib().mpb_sample_gp_tc(_lib.ptr(self.scale_tril_split[0]), _lib.ptr(self.scale_tril_split[1]),
                                                    _lib.ptr(self.means), _lib.ptr(eps), _lib.ptr(x), P, S, M, _lib.stream_ptr()))
         else:
