@@ -145,9 +145,14 @@ int mpb_sample_gp_kron_supported(int H, int dof);
 int mpb_sample_gp_kron_pack(const float* L, float* LkT, int H, int dof, int* structured, void* stream);
 int mpb_sample_gp_kron(const float* LkT, const float* mu, const float* eps, float* x,
                        int P, int S, int H, int dof, void* stream);
-/* Tensor-core variant (warp-level m16n8k8 TF32 MMA, 3xTF32 split of both operands, fp32 accumulation): same
- * contract; agrees with mpb_sample_gp_kron to ~1e-6 of the noise amplitude. */
-int mpb_sample_gp_kron_tc(const float* LkT, const float* mu, const float* eps, float* x,
+/* Tensor-core variant (warp-level m16n8k16 MMA, two-term fp16 split of both operands = 22 significant bits, fp32
+ * accumulation): same contract as mpb_sample_gp_kron; agrees with it to ~2e-6 of the noise amplitude.
+ *   mpb_sample_gp_kron_tc_prepare : LkT (from mpb_sample_gp_kron_pack) -> LkF, the per-dof power-of-two scaled,
+ *                                   fragment-ordered fp16 hi/lo operand; LkF must hold mpb_sample_gp_kron_tc_bytes(H, dof)
+ *                                   bytes, 16-byte aligned.  One-off setup, stream-ordered. */
+long long mpb_sample_gp_kron_tc_bytes(int H, int dof);
+int mpb_sample_gp_kron_tc_prepare(const float* LkT, void* LkF, int H, int dof, void* stream);
+int mpb_sample_gp_kron_tc(const void* LkF, const float* mu, const float* eps, float* x,
                           int P, int S, int H, int dof, void* stream);
 
 /* STOMP noise: x[p,s,h,j] = mu[p,h,j] + (h==0||h==H-1 ? 0 : sum_k L_R[h,k] eps[s,j,p,k])
@@ -205,8 +210,9 @@ int mpb_softmax_update(const float* cost, const float* x, float* mu, float* weig
  * Replaces the body of StochGPMP.optimize (stoch_gpmp.py:291-299).
  * L_split: NULL (FP32 SIMT sampler) or the [2,M,M] output of mpb_split_tf32 (tensor-core sampler).
  * workspace: x [P,S,H,D], cost [P,S], weights [P,S], is_vec [P,M]; free_flag [P*S] may be NULL.
- * mpb_stoch_gpmp_iter_kron: same, sampling through mpb_sample_gp_kron with the packed factor L_kron. */
-int mpb_stoch_gpmp_iter_kron(const float* L_kron, const float* Sigma_inv, const float* eps,
+ * mpb_stoch_gpmp_iter_kron: same, sampling through mpb_sample_gp_kron_tc (L_kron_tc != NULL) or mpb_sample_gp_kron
+ * with the packed factor. */
+int mpb_stoch_gpmp_iter_kron(const float* L_kron, const void* L_kron_tc, const float* Sigma_inv, const float* eps,
                              float* mu, float* x, float* cost, float* weights, float* is_vec,
                              uint8_t* free_flag,
                              int P, int S, int H,

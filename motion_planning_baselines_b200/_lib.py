@@ -62,6 +62,8 @@ _SIGNATURES = {
     'mpb_sample_gp_kron_supported': (C.c_int, [_i, _i]),
     'mpb_sample_gp_kron_pack': (C.c_int, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _vp]),
     'mpb_sample_gp_kron': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'mpb_sample_gp_kron_tc_bytes': (C.c_longlong, [_i, _i]),
+    'mpb_sample_gp_kron_tc_prepare': (C.c_int, [_vp, _vp, _i, _i, _vp]),
     'mpb_sample_gp_kron_tc': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'mpb_sample_stomp': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'mpb_prior_matvec': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -74,7 +76,7 @@ _SIGNATURES = {
     'mpb_stoch_gpmp_iter': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                       C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
                                       _f, _f, _vp]),
-    'mpb_stoch_gpmp_iter_kron': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+    'mpb_stoch_gpmp_iter_kron': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                            C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
                                            _f, _f, _vp]),
     'mpb_chomp_run': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _f, _f, _f, _i, _vp]),

@@ -18,6 +18,8 @@
 // double-buffered cp.async ring (16 k x 16 rows per chunk), no CTA barrier inside the contraction.  Results go back
 // into the tile in place; the store phase adds mu_p and writes full 32-byte sectors; the next tile's rows are already
 // in flight in registers while the current tile is stored.  Bound: FP32 FMA issue (16 FFMA per 2 LDS.128).
+#include <cuda_fp16.h>
+
 #include "mpb_common.cuh"
 
 namespace mpb {
@@ -203,18 +205,23 @@ sample_gp_kron_kernel(const float* __restrict__ LkT, const float* __restrict__ m
     }
 }
 
-// ---- tensor-core variant (legacy warp-level MMA, 3xTF32) -------------------------------------------------------------
+// ---- tensor-core variant (warp-level MMA, two-term fp16 split) ---------------------------------------------------------
 // Same work split (one warp group per dof, warp a owns the 16-row blocks a and NB-1-a, per-warp cp.async ring for the
-// factor block); the 16-row x 32-sample output block of a warp is four m16n8k8 TF32 MMAs per 8 k.  Both operands are
-// split into a TF32-representable high part (mantissa truncated to 10 bits) and the exact fp32 remainder;
-// lo*hi + hi*lo + hi*hi accumulate in fp32 (the dropped lo*lo term is 2^-20 relative).  Fragments are gathered by the
-// threads themselves, so the per-dof column stride of the noise rows costs nothing -- which is why this kernel uses
-// mma.sync and not tcgen05: a tcgen05 formulation needs the factor block resident next to a >= 128-sample tile in
-// canonical core-matrix layout, and a 32-row tile of all dofs already fills shared memory.
+// factor block); the 16-row x 32-sample output block of a warp is four m16n8k16 MMAs per 16 k.  Both operands are split
+// into two fp16 terms, v = hi + lo with hi = fp16(v), lo = fp16(v - hi) (22 significant bits); lo*hi + hi*lo + hi*hi
+// accumulate in fp32 (the dropped lo*lo term is 2^-22 relative).  The factor block is scaled per dof by a power of two
+// so that its largest entry sits at 2^13 (entries below 2^-37 of the largest flush to zero); noise is O(1) by contract
+// (|eps| < 65504; entries below 2^-14 keep an absolute precision of 2^-25).  An fp16 MMA moves twice the k of a TF32
+// MMA per issue, so this needs half the tensor-pipe time of a 3xTF32 split for the same accuracy.
+// Fragments are gathered by the threads themselves, so the per-dof column stride of the noise rows costs nothing --
+// which is why this kernel uses mma.sync and not tcgen05: a tcgen05 formulation needs the factor block resident next
+// to a >= 128-sample tile in canonical core-matrix layout, and a 32-row tile of all dofs already fills shared memory.
 // The tile keeps the rows in their NATURAL layout [32 rows][M + 4]: rows are copied global->shared with coalesced
-// 16-byte cp.async (no registers), the padded stride (= 4 mod 32) makes the B-fragment gathers and the accumulator
-// scatter bank-conflict free, and the store phase is a coalesced row copy that adds mu_p and immediately refills the
-// slot it has just read with the next tile's noise, so the next tile streams in while this one is written out.
+// 16-byte cp.async (no registers) and converted in place to packed (hi | lo << 16) words by the thread that copied
+// them; the padded stride (= 4 mod 32) makes the B-fragment gathers and the accumulator scatter bank-conflict free
+// (the MMA's k slots are permuted so that the four lanes of a fragment row read consecutive k); the store phase is a
+// coalesced row copy that adds mu_p and immediately refills the slot it has just read with the next tile's noise, so
+// the next tile streams in while this one is written out.
 template <int DOF, int H>
 struct KronMmaCfg : KronCfg<DOF, H> {
     using Base = KronCfg<DOF, H>;
@@ -231,14 +238,16 @@ __device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) 
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(v) & 0xffffe000u;
-    lo = __float_as_uint(__fsub_rn(v, __uint_as_float(hi)));
+// v -> (fp16(v) | fp16(v - fp16(v)) << 16)
+__device__ __forceinline__ uint32_t split_f16(float v) {
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(__fsub_rn(v, __half2float(hi)));
+    return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
 }
 
 struct KronRow {            // per tile row: where its noise comes from and which particle it belongs to
@@ -248,7 +257,7 @@ struct KronRow {            // per tile row: where its noise comes from and whic
 
 template <int DOF, int H>
 __global__ void __launch_bounds__(KronCfg<DOF, H>::THREADS, 1)
-sample_gp_kron_mma_kernel(const float* __restrict__ LkT, const float* __restrict__ mu, const float* __restrict__ eps,
+sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restrict__ mu, const float* __restrict__ eps,
                           float* __restrict__ x, int P, int S) {
     using Cfg = KronMmaCfg<DOF, H>;
     constexpr int M = Cfg::M, N = Cfg::N, NB = Cfg::NB, WPD = Cfg::WPD, RS = Cfg::RS, THREADS = Cfg::THREADS;
@@ -263,7 +272,8 @@ sample_gp_kron_mma_kernel(const float* __restrict__ LkT, const float* __restrict
 
     const int j = warp / WPD, a = warp - j * WPD;
     const int g = lane >> 2, t4 = lane & 3;
-    const float* Lj = LkT + (size_t)j * N * N;
+    const uint32_t* Lj = LkF + (size_t)j * N * N;                      // [blk][q][hi|lo][lane][4]
+    const float inv_scale = reinterpret_cast<const float*>(LkF + (size_t)DOF * N * N)[j];
 
     auto row_table = [&](int t, int buf) {          // threads 0..31
         const long long n = (long long)t * kTileRows + threadIdx.x;
@@ -290,47 +300,37 @@ sample_gp_kron_mma_kernel(const float* __restrict__ LkT, const float* __restrict
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
         const int nchunks = blk + 1;
-        // staging: lane -> (k row kk = lane>>2 (+8), 4-row part = lane&3); 16-byte chunks XOR-swizzled by bit 1 of kk
-        const int skk = lane >> 2, spart = lane & 3;
-        const float* lsrc = Lj + (size_t)skk * N + 16 * blk + 4 * spart;
-        float* ldst = lbuf + skk * 16 + ((4 * spart) ^ (((skk >> 1) & 1) << 3));
+        // staging: every lane copies exactly the 2 x 16 bytes (hi and lo A fragments) it reads back itself
+        const uint32_t* lsrc = Lj + (size_t)blk * NB * 256 + lane * 4;
+        float* ldst = lbuf + lane * 4;
         auto issue = [&](int q) {
             float* dst = ldst + (q & 1) * 256;
-            const float* s0 = lsrc + (size_t)q * 16 * N;
+            const uint32_t* s0 = lsrc + (size_t)q * 256;
             cp_async16(dst, s0);
-            cp_async16(dst + 8 * 16, s0 + (size_t)8 * N);     // kk + 8 has the same swizzle bit
+            cp_async16(dst + 128, s0 + 128);
             cp_async_commit();
         };
-        const int a0off = t4 * 16 + (g ^ (((t4 >> 1) & 1) << 3));
-        // B fragment: element (k, sample) = tile[sample * RS + DOF*k + j]; k = 16q + 8ks + t4 (+4), sample = 8n + g
-        const float* ebase = tile + g * RS + DOF * t4 + j;
+        // B fragment: element (k, sample) = tile[sample * RS + DOF*k + j]; MMA k slots (2*t4, 2*t4+1, 2*t4+8, 2*t4+9) hold
+        // k = 16q + t4 + (0, 4, 8, 12) -- the same permutation is baked into the packed A fragments
+        const uint32_t* ebase = reinterpret_cast<const uint32_t*>(tile) + g * RS + DOF * t4 + j;
         issue(0);
         for (int q = 0; q < nchunks; ++q) {
             cp_async_wait_all();
-            __syncwarp();
             if (q + 1 < nchunks) issue(q + 1);
-            const float* lb = lbuf + (q & 1) * 256;
-            const float* eb = ebase + q * 16 * DOF;
+            const uint4 ahi = *reinterpret_cast<const uint4*>(ldst + (q & 1) * 256);
+            const uint4 alo = *reinterpret_cast<const uint4*>(ldst + (q & 1) * 256 + 128);
+            const uint32_t* eb = ebase + q * 16 * DOF;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                uint32_t ahi[4], alo[4];
-                split_tf32(lb[ks * 128 + a0off], ahi[0], alo[0]);
-                split_tf32(lb[ks * 128 + (a0off ^ 8)], ahi[1], alo[1]);
-                split_tf32(lb[ks * 128 + 64 + a0off], ahi[2], alo[2]);
-                split_tf32(lb[ks * 128 + 64 + (a0off ^ 8)], ahi[3], alo[3]);
-#pragma unroll
-                for (int n = 0; n < 4; ++n) {
-                    const float* e0 = eb + ks * 8 * DOF + n * 8 * RS;
-                    uint32_t bhi0, blo0, bhi1, blo1;
-                    split_tf32(e0[0], bhi0, blo0);
-                    split_tf32(e0[4 * DOF], bhi1, blo1);
-                    mma_tf32(acc[n], alo, bhi0, bhi1);
-                    mma_tf32(acc[n], ahi, blo0, blo1);
-                    mma_tf32(acc[n], ahi, bhi0, bhi1);
-                }
+            for (int n = 0; n < 4; ++n) {
+                const uint32_t* e0 = eb + n * 8 * RS;
+                const uint32_t w0 = e0[0], w1 = e0[4 * DOF], w2 = e0[8 * DOF], w3 = e0[12 * DOF];
+                const uint32_t bhi0 = __byte_perm(w0, w1, 0x5410), blo0 = __byte_perm(w0, w1, 0x7632);
+                const uint32_t bhi1 = __byte_perm(w2, w3, 0x5410), blo1 = __byte_perm(w2, w3, 0x7632);
+                mma_f16(acc[n], alo, bhi0, bhi1);
+                mma_f16(acc[n], ahi, blo0, blo1);
+                mma_f16(acc[n], ahi, bhi0, bhi1);
             }
         }
-        __syncwarp();
     };
     auto put = [&](int blk, const float (&acc)[4][4]) {
 #pragma unroll
@@ -338,8 +338,8 @@ sample_gp_kron_mma_kernel(const float* __restrict__ LkT, const float* __restrict
             float* col = tile + DOF * (16 * blk + g + 8 * hrow) + j + 2 * t4 * RS;   // == (i>>1)*D + (i&1)*DOF + j
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
-                col[(8 * n) * RS] = acc[n][2 * hrow];
-                col[(8 * n + 1) * RS] = acc[n][2 * hrow + 1];
+                col[(8 * n) * RS] = acc[n][2 * hrow] * inv_scale;
+                col[(8 * n + 1) * RS] = acc[n][2 * hrow + 1] * inv_scale;
             }
         }
     };
@@ -359,7 +359,16 @@ sample_gp_kron_mma_kernel(const float* __restrict__ LkT, const float* __restrict
     for (; t < ntiles; t += gridDim.x, buf ^= 1) {
         const int tn = t + gridDim.x;
         cp_async_wait_all();
-        __syncthreads();                               // tile t has landed
+#pragma unroll
+        for (int it = 0; it < Cfg::IPT; ++it) {        // own slots only: fp32 -> packed (fp16 hi | fp16 lo << 16)
+            const int e = threadIdx.x + it * THREADS;
+            float4* slot = reinterpret_cast<float4*>(tile + (e / Cfg::V4_PER_ROW) * RS + 4 * (e % Cfg::V4_PER_ROW));
+            const float4 v = *slot;
+            uint4 w;
+            w.x = split_f16(v.x); w.y = split_f16(v.y); w.z = split_f16(v.z); w.w = split_f16(v.w);
+            *reinterpret_cast<uint4*>(slot) = w;
+        }
+        __syncthreads();                               // tile t has landed and is converted
         float acc0[4][4], acc1[4][4];
         contract(a, acc0);
         contract(NB - 1 - a, acc1);
@@ -411,10 +420,43 @@ __global__ void kron_pack_kernel(const float* __restrict__ L, float* __restrict_
     }
 }
 
+// Tensor-core operand: per dof the largest |entry| (kron_max_kernel, bit pattern of a non-negative float), then the
+// fragment-ready fp16 hi/lo words  LkF[j][blk][q][hi|lo][lane][4]  of the scaled block and the inverse scales.
+__global__ void kron_max_kernel(const float* __restrict__ LkT, unsigned* __restrict__ maxbits, int N, int dof) {
+    const long long total = (long long)dof * N * N;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+        atomicMax(maxbits + (int)(idx / ((long long)N * N)), __float_as_uint(fabsf(LkT[idx])));
+}
+__global__ void kron_frag_kernel(const float* __restrict__ LkT, uint32_t* __restrict__ LkF, const unsigned* __restrict__ maxbits,
+                                 int N, int dof) {
+    const int NB = N / 16;
+    const long long total = (long long)dof * N * N;
+    float* inv_scale = reinterpret_cast<float*>(LkF + total);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        long long r = idx;
+        const int reg = (int)(r & 3); r >>= 2;
+        const int lane = (int)(r & 31); r >>= 5;
+        const int hl = (int)(r & 1); r >>= 1;
+        const int q = (int)(r % NB); r /= NB;
+        const int blk = (int)(r % NB);
+        const int j = (int)(r / NB);
+        const float mx = __uint_as_float(maxbits[j]);
+        const float scale = mx > 0.f ? exp2f((float)(13 - ilogbf(mx))) : 1.f;
+        if (blk == 0 && q == 0 && hl == 0 && lane == 0 && reg == 0) inv_scale[j] = 1.f / scale;
+        const int g = lane >> 2, t4 = lane & 3;
+        const int i = 16 * blk + g + 8 * (reg & 1);
+        const int k0 = 16 * q + t4 + (reg >= 2 ? 8 : 0);
+        const float* Lj = LkT + (size_t)j * N * N;
+        const uint32_t w0 = split_f16(Lj[(size_t)k0 * N + i] * scale);
+        const uint32_t w1 = split_f16(Lj[(size_t)(k0 + 4) * N + i] * scale);
+        LkF[idx] = hl ? ((w0 >> 16) | (w1 & 0xffff0000u)) : ((w0 & 0xffffu) | (w1 << 16));
+    }
+}
+
 template <int DOF, int H, bool MMA>
-static int launch_kron(const float* LkT, const float* mu, const float* eps, float* x, int P, int S, cudaStream_t st) {
+static int launch_kron(const void* Lp, const float* mu, const float* eps, float* x, int P, int S, cudaStream_t st) {
     using Cfg = KronCfg<DOF, H>;
-    auto kern = MMA ? sample_gp_kron_mma_kernel<DOF, H> : sample_gp_kron_kernel<DOF, H>;
+    const void* kern = MMA ? (const void*)sample_gp_kron_mma_kernel<DOF, H> : (const void*)sample_gp_kron_kernel<DOF, H>;
     const size_t smem_bytes = MMA ? KronMmaCfg<DOF, H>::SMEM : Cfg::SMEM;
     static thread_local int cached_dev = -1, per_sm = 0;
     int dev = 0;
@@ -431,7 +473,9 @@ static int launch_kron(const float* LkT, const float* mu, const float* eps, floa
     const long long ntiles = ((long long)P * S + kTileRows - 1) / kTileRows;
     const long long cap = (long long)sm_count() * per_sm;
     const int grid = (int)(ntiles < cap ? ntiles : cap);
-    kern<<<grid, Cfg::THREADS, smem_bytes, st>>>(LkT, mu, eps, x, P, S);
+    void* args[] = {(void*)&Lp, (void*)&mu, (void*)&eps, (void*)&x, (void*)&P, (void*)&S};
+    cudaError_t le = cudaLaunchKernel(kern, dim3(grid), dim3(Cfg::THREADS), args, smem_bytes, st);
+    if (le != cudaSuccess) { set_error("mpb_sample_gp_kron: %s", cudaGetErrorString(le)); return MPB_ECUDA; }
     return check_launch("mpb_sample_gp_kron");
 }
 
@@ -470,7 +514,7 @@ extern "C" int mpb_sample_gp_kron_pack(const float* L, float* LkT, int H, int do
     return MPB_OK;
 }
 
-static int sample_gp_kron_any(bool mma, const float* LkT, const float* mu, const float* eps, float* x, int P, int S, int H,
+static int sample_gp_kron_any(bool mma, const void* LkT, const float* mu, const float* eps, float* x, int P, int S, int H,
                               int dof, void* stream) {
     using namespace mpb;
     MPB_REQUIRE(LkT && mu && eps && x, "mpb_sample_gp_kron: null pointer");
@@ -491,7 +535,28 @@ extern "C" int mpb_sample_gp_kron(const float* LkT, const float* mu, const float
     return sample_gp_kron_any(false, LkT, mu, eps, x, P, S, H, dof, stream);
 }
 
-extern "C" int mpb_sample_gp_kron_tc(const float* LkT, const float* mu, const float* eps, float* x, int P, int S, int H,
+extern "C" long long mpb_sample_gp_kron_tc_bytes(int H, int dof) {
+    return (long long)dof * 2 * H * 2 * H * 4 + 64 * 4;        // fragments + inverse scales (16) + scratch (48 words)
+}
+
+extern "C" int mpb_sample_gp_kron_tc_prepare(const float* LkT, void* LkF, int H, int dof, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(LkT && LkF, "mpb_sample_gp_kron_tc_prepare: null pointer");
+    MPB_REQUIRE(mpb_sample_gp_kron_supported(H, dof) && dof <= 16, "mpb_sample_gp_kron_tc_prepare: shape H=%d dof=%d has no structured kernel", H, dof);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int N = 2 * H;
+    const long long total = (long long)dof * N * N;
+    uint32_t* frag = static_cast<uint32_t*>(LkF);
+    unsigned* maxbits = frag + total + 16;
+    cudaError_t e = cudaMemsetAsync(frag + total, 0, 64 * 4, st);
+    if (e != cudaSuccess) { set_error("mpb_sample_gp_kron_tc_prepare: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+    const int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+    kron_max_kernel<<<grid, 256, 0, st>>>(LkT, maxbits, N, dof);
+    kron_frag_kernel<<<grid, 256, 0, st>>>(LkT, frag, maxbits, N, dof);
+    return check_launch("mpb_sample_gp_kron_tc_prepare");
+}
+
+extern "C" int mpb_sample_gp_kron_tc(const void* LkF, const float* mu, const float* eps, float* x, int P, int S, int H,
                                      int dof, void* stream) {
-    return sample_gp_kron_any(true, LkT, mu, eps, x, P, S, H, dof, stream);
+    return sample_gp_kron_any(true, LkF, mu, eps, x, P, S, H, dof, stream);
 }

@@ -157,7 +157,8 @@ class StochGPMP(OptimizationPlanner):
                 vel_mean = self._particle_means[..., -self.n_dof:].clone()
             if self._sample_dist.scale_tril_kron is not None:
                 _lib.check(lib.mpb_stoch_gpmp_iter_kron(
-                    _lib.ptr(self._sample_dist.scale_tril_kron), _lib.ptr(self.Sigma_inv), _lib.ptr(e),
+                    _lib.ptr(self._sample_dist.scale_tril_kron), _lib.ptr(self._sample_dist.scale_tril_kron_tc),
+                    _lib.ptr(self.Sigma_inv), _lib.ptr(e),
                     _lib.ptr(self._particle_means), _lib.ptr(self.state_samples), _lib.ptr(self.costs), _lib.ptr(self._w_buf),
                     _lib.ptr(self._is_vec), _lib.ptr(self.free_flags), P, S, H,
                     C.byref(self.robot.desc), fields, nf, C.byref(gp), self.temperature, self.step_size, _lib.stream_ptr()))
@@ -198,7 +199,10 @@ class StochGPMP(OptimizationPlanner):
         rec = (lambda i: events[i].record()) if events is not None else (lambda i: None)
         rec(0)
         split = self._sample_dist.scale_tril_split
-        if self._sample_dist.scale_tril_kron is not None:
+        if self._sample_dist.scale_tril_kron_tc is not None:
+            _lib.check(lib.mpb_sample_gp_kron_tc(_lib.ptr(self._sample_dist.scale_tril_kron_tc), _lib.ptr(self._particle_means),
+                                                 _lib.ptr(eps), _lib.ptr(self.state_samples), P, S, H, self.n_dof, st))
+        elif self._sample_dist.scale_tril_kron is not None:
             _lib.check(lib.mpb_sample_gp_kron(_lib.ptr(self._sample_dist.scale_tril_kron), _lib.ptr(self._particle_means),
                                               _lib.ptr(eps), _lib.ptr(self.state_samples), P, S, H, self.n_dof, st))
         elif split is not None:

@@ -20,9 +20,13 @@ assert ok.value == 1
 mu = torch.randn(P, M, generator=gen, **dev)
 eps = [torch.randn(S, P, M, generator=gen, **dev) for _ in range(4)]
 x = torch.empty(P, S, M, **dev)
-fn = lib.mpb_sample_gp_kron_tc if os.environ.get('KRON', 'tc') == 'tc' else lib.mpb_sample_gp_kron
+LkF = torch.empty(lib.mpb_sample_gp_kron_tc_bytes(H, dof), device=dev['device'], dtype=torch.uint8)
+_lib.check(lib.mpb_sample_gp_kron_tc_prepare(_lib.ptr(LkT), _lib.ptr(LkF), H, dof, _lib.stream_ptr()))
+tc = os.environ.get('KRON', 'tc') == 'tc'
+fn = lib.mpb_sample_gp_kron_tc if tc else lib.mpb_sample_gp_kron
+Lop = LkF if tc else LkT
 def run(i):
-    _lib.check(fn(_lib.ptr(LkT), _lib.ptr(mu), _lib.ptr(eps[i % 4]), _lib.ptr(x), P, S, H, dof, _lib.stream_ptr()))
+    _lib.check(fn(_lib.ptr(Lop), _lib.ptr(mu), _lib.ptr(eps[i % 4]), _lib.ptr(x), P, S, H, dof, _lib.stream_ptr()))
 for i in range(3): run(i)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

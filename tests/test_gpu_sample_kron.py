@@ -115,7 +115,11 @@ def test_reference_prior_is_structured_and_sampler_matches(name, dev):
     prior.means = torch.randn(P, M, generator=gen, **dev)
     prior.num_modes = P
     eps = torch.randn(S, P, M, generator=gen, **dev)
-    x = prior.sample(S, eps=eps).reshape(P, S, M)
+    x_tc = prior.sample(S, eps=eps).reshape(P, S, M).clone()       # default: tensor-core variant
+    assert prior.scale_tril_kron_tc is not None
+    tc_operand, prior.scale_tril_kron_tc = prior.scale_tril_kron_tc, None
+    x = prior.sample(S, eps=eps).reshape(P, S, M)                    # exact FP32 variant
+    prior.scale_tril_kron_tc = tc_operand
     xd = torch.empty(P, S, M, **dev)
     _lib.check(_lib.lib().mpb_sample_gp(_lib.ptr(prior.scale_tril), _lib.ptr(prior.means), _lib.ptr(eps), _lib.ptr(xd),
                                         P, S, M, _lib.stream_ptr()))
@@ -123,6 +127,7 @@ def test_reference_prior_is_structured_and_sampler_matches(name, dev):
     ref = prior.means.double().unsqueeze(1) + torch.einsum('ik,spk->psi', prior.scale_tril.double(), eps.double())
     noise = (ref - prior.means.double().unsqueeze(1)).abs().max()
     assert float((x.double() - ref).abs().max()) <= 2e-6 * float(noise) + 1e-6
+    assert float((x_tc.double() - ref).abs().max()) <= 5e-6 * float(noise) + 1e-6
 
 
 def test_kron_full_size_properties(dev):
@@ -150,7 +155,7 @@ def test_kron_full_size_properties(dev):
 @pytest.mark.parametrize('dof,H,P,S', [(2, 32, 3, 7), (2, 64, 1, 64), (2, 128, 5, 13), (3, 32, 4, 8), (3, 64, 7, 33),
                                        (3, 128, 2, 31), (7, 32, 3, 11), (7, 64, 5, 13), (7, 64, 16, 64), (7, 64, 1, 1)])
 def test_kron_tc_matches_fp64(dof, H, P, S, dev):
-    """Tensor-core variant (3xTF32 warp MMA): within 5e-6 of the noise amplitude of an fp64 product, zero noise
+    """Tensor-core variant (warp MMA, two-term fp16 split): within 5e-6 of the noise amplitude of an fp64 product, zero noise
     returns the means exactly, and rows past the ragged end are untouched."""
     from motion_planning_baselines_b200 import _lib
     gen = torch.Generator(device='cuda').manual_seed(7 * dof + H + S)
@@ -161,8 +166,10 @@ def test_kron_tc_matches_fp64(dof, H, P, S, dev):
     mu = torch.randn(P, M, generator=gen, **dev)
     eps = torch.randn(S, P, M, generator=gen, **dev)
     lib = _lib.lib()
+    LkF = torch.empty(lib.mpb_sample_gp_kron_tc_bytes(H, dof), device=dev['device'], dtype=torch.uint8)
+    _lib.check(lib.mpb_sample_gp_kron_tc_prepare(_lib.ptr(LkT), _lib.ptr(LkF), H, dof, _lib.stream_ptr()))
     x = torch.full((P * S + 3, M), float('nan'), **dev)
-    _lib.check(lib.mpb_sample_gp_kron_tc(_lib.ptr(LkT), _lib.ptr(mu), _lib.ptr(eps), _lib.ptr(x), P, S, H, dof, _lib.stream_ptr()))
+    _lib.check(lib.mpb_sample_gp_kron_tc(_lib.ptr(LkF), _lib.ptr(mu), _lib.ptr(eps), _lib.ptr(x), P, S, H, dof, _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert torch.isnan(x[P * S:]).all(), 'wrote past the last row'
     x = x[:P * S].view(P, S, M)
@@ -171,5 +178,5 @@ def test_kron_tc_matches_fp64(dof, H, P, S, dev):
     err = (x.double() - (mu.double().unsqueeze(1) + noise)).abs().max()
     assert float(err) <= 5e-6 * float(noise.abs().max()), (float(err), float(noise.abs().max()))
     xz = torch.empty(P, S, M, **dev)
-    _lib.check(lib.mpb_sample_gp_kron_tc(_lib.ptr(LkT), _lib.ptr(mu), _lib.ptr(torch.zeros_like(eps)), _lib.ptr(xz), P, S, H, dof, _lib.stream_ptr()))
+    _lib.check(lib.mpb_sample_gp_kron_tc(_lib.ptr(LkF), _lib.ptr(mu), _lib.ptr(torch.zeros_like(eps)), _lib.ptr(xz), P, S, H, dof, _lib.stream_ptr()))
     assert torch.equal(xz, mu.unsqueeze(1).expand(P, S, M))
