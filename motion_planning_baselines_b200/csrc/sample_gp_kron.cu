@@ -293,53 +293,58 @@ sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restr
         else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     };
 
-    // acc[n][.] : m16n8 accumulator of n-tile n (samples 8n..8n+7) for rows 16*blk .. 16*blk+15
-    auto contract = [&](int blk, float (&acc)[4][4]) {
+    // Factor staging: every lane copies exactly the 2 x 16 bytes (hi and lo A fragments of one 16-row x 16-k chunk) it
+    // reads back itself, so the ring needs no warp synchronisation.  The chunks of the two blocks of a warp form ONE
+    // sequence u = 0 .. NB (block a: q = 0..a, then block NB-1-a: q = 0..NB-1-a); chunk u+1 is in flight while u runs.
+    float* ldst = lbuf + lane * 4;
+    auto issue = [&](int blk, int q, int stage) {
+        const uint32_t* s0 = Lj + ((size_t)blk * NB + q) * 256 + lane * 4;
+        float* dst = ldst + stage * 256;
+        cp_async16(dst, s0);
+        cp_async16(dst + 128, s0 + 128);
+        cp_async_commit();
+    };
+    // B fragment: element (k, sample) = tile[sample * RS + DOF*k + j]; MMA k slots (2*t4, 2*t4+1, 2*t4+8, 2*t4+9) hold
+    // k = 16q + t4 + (0, 4, 8, 12) -- the same permutation is baked into the packed A fragments
+    const uint32_t* ebase = reinterpret_cast<const uint32_t*>(tile) + g * RS + DOF * t4 + j;
+    // acc[n][.] : m16n8 accumulator of n-tile n (samples 8n..8n+7) of the current 16-row block
+    auto step = [&](int q, int stage, float (&acc)[4][4]) {
+        const uint4 ahi = *reinterpret_cast<const uint4*>(ldst + stage * 256);
+        const uint4 alo = *reinterpret_cast<const uint4*>(ldst + stage * 256 + 128);
+        const uint32_t* eb = ebase + q * 16 * DOF;
 #pragma unroll
-        for (int n = 0; n < 4; ++n)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
-        const int nchunks = blk + 1;
-        // staging: every lane copies exactly the 2 x 16 bytes (hi and lo A fragments) it reads back itself
-        const uint32_t* lsrc = Lj + (size_t)blk * NB * 256 + lane * 4;
-        float* ldst = lbuf + lane * 4;
-        auto issue = [&](int q) {
-            float* dst = ldst + (q & 1) * 256;
-            const uint32_t* s0 = lsrc + (size_t)q * 256;
-            cp_async16(dst, s0);
-            cp_async16(dst + 128, s0 + 128);
-            cp_async_commit();
-        };
-        // B fragment: element (k, sample) = tile[sample * RS + DOF*k + j]; MMA k slots (2*t4, 2*t4+1, 2*t4+8, 2*t4+9) hold
-        // k = 16q + t4 + (0, 4, 8, 12) -- the same permutation is baked into the packed A fragments
-        const uint32_t* ebase = reinterpret_cast<const uint32_t*>(tile) + g * RS + DOF * t4 + j;
-        issue(0);
-        for (int q = 0; q < nchunks; ++q) {
-            cp_async_wait_all();
-            if (q + 1 < nchunks) issue(q + 1);
-            const uint4 ahi = *reinterpret_cast<const uint4*>(ldst + (q & 1) * 256);
-            const uint4 alo = *reinterpret_cast<const uint4*>(ldst + (q & 1) * 256 + 128);
-            const uint32_t* eb = ebase + q * 16 * DOF;
-#pragma unroll
-            for (int n = 0; n < 4; ++n) {
-                const uint32_t* e0 = eb + n * 8 * RS;
-                const uint32_t w0 = e0[0], w1 = e0[4 * DOF], w2 = e0[8 * DOF], w3 = e0[12 * DOF];
-                const uint32_t bhi0 = __byte_perm(w0, w1, 0x5410), blo0 = __byte_perm(w0, w1, 0x7632);
-                const uint32_t bhi1 = __byte_perm(w2, w3, 0x5410), blo1 = __byte_perm(w2, w3, 0x7632);
-                mma_f16(acc[n], alo, bhi0, bhi1);
-                mma_f16(acc[n], ahi, blo0, blo1);
-                mma_f16(acc[n], ahi, bhi0, bhi1);
-            }
+        for (int n = 0; n < 4; ++n) {
+            const uint32_t* e0 = eb + n * 8 * RS;
+            const uint32_t w0 = e0[0], w1 = e0[4 * DOF], w2 = e0[8 * DOF], w3 = e0[12 * DOF];
+            const uint32_t bhi0 = __byte_perm(w0, w1, 0x5410), blo0 = __byte_perm(w0, w1, 0x7632);
+            const uint32_t bhi1 = __byte_perm(w2, w3, 0x5410), blo1 = __byte_perm(w2, w3, 0x7632);
+            mma_f16(acc[n], alo, bhi0, bhi1);
+            mma_f16(acc[n], ahi, blo0, blo1);
+            mma_f16(acc[n], ahi, bhi0, bhi1);
         }
     };
-    auto put = [&](int blk, const float (&acc)[4][4]) {
+    // x = mu_p + noise: the mean of the particle every row of the tile belongs to (one particle per tile when S % 32 == 0)
+    const bool one_particle = (S % kTileRows) == 0;
+    auto put = [&](int blk, const float (&acc)[4][4], int buf, const float (&mrow)[2]) {
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow) {
-            float* col = tile + DOF * (16 * blk + g + 8 * hrow) + j + 2 * t4 * RS;   // == (i>>1)*D + (i&1)*DOF + j
+            const int c = DOF * (16 * blk + g + 8 * hrow) + j;                       // == (i>>1)*D + (i&1)*DOF + j
+            float* col = tile + c + 2 * t4 * RS;
+            if (one_particle) {
+                const float m = mrow[hrow];
 #pragma unroll
-            for (int n = 0; n < 4; ++n) {
-                col[(8 * n) * RS] = acc[n][2 * hrow] * inv_scale;
-                col[(8 * n + 1) * RS] = acc[n][2 * hrow + 1] * inv_scale;
+                for (int n = 0; n < 4; ++n) {
+                    col[(8 * n) * RS] = m + acc[n][2 * hrow] * inv_scale;
+                    col[(8 * n + 1) * RS] = m + acc[n][2 * hrow + 1] * inv_scale;
+                }
+            } else {
+#pragma unroll
+                for (int n = 0; n < 4; ++n)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int p = rows[buf * kTileRows + 8 * n + 2 * t4 + e].p;
+                        col[(8 * n + e) * RS] = __ldg(mu + (size_t)p * M + c) + acc[n][2 * hrow + e] * inv_scale;
+                    }
             }
         }
     };
@@ -359,39 +364,75 @@ sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restr
     for (; t < ntiles; t += gridDim.x, buf ^= 1) {
         const int tn = t + gridDim.x;
         cp_async_wait_all();
+        issue(a, 0, 0);                                // first factor chunk flies during the conversion pass
+        float m0[2] = {0.f, 0.f}, m1[2] = {0.f, 0.f};  // means of this thread's four output rows (one particle per tile)
+        if (one_particle) {
+            const float* mp = mu + (size_t)(((long long)t * kTileRows) / S) * M + j;
+            m0[0] = __ldg(mp + DOF * (16 * a + g));
+            m0[1] = __ldg(mp + DOF * (16 * a + g + 8));
+            m1[0] = __ldg(mp + DOF * (16 * (NB - 1 - a) + g));
+            m1[1] = __ldg(mp + DOF * (16 * (NB - 1 - a) + g + 8));
+        }
 #pragma unroll
         for (int it = 0; it < Cfg::IPT; ++it) {        // own slots only: fp32 -> packed (fp16 hi | fp16 lo << 16)
             const int e = threadIdx.x + it * THREADS;
             float4* slot = reinterpret_cast<float4*>(tile + (e / Cfg::V4_PER_ROW) * RS + 4 * (e % Cfg::V4_PER_ROW));
             const float4 v = *slot;
+            const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(__fsub_rn(v.x, f01.x), __fsub_rn(v.y, f01.y));
+            const __half2 l23 = __floats2half2_rn(__fsub_rn(v.z, f23.x), __fsub_rn(v.w, f23.y));
+            const uint32_t uh01 = *reinterpret_cast<const uint32_t*>(&h01), ul01 = *reinterpret_cast<const uint32_t*>(&l01);
+            const uint32_t uh23 = *reinterpret_cast<const uint32_t*>(&h23), ul23 = *reinterpret_cast<const uint32_t*>(&l23);
             uint4 w;
-            w.x = split_f16(v.x); w.y = split_f16(v.y); w.z = split_f16(v.z); w.w = split_f16(v.w);
+            w.x = __byte_perm(uh01, ul01, 0x5410); w.y = __byte_perm(uh01, ul01, 0x7632);
+            w.z = __byte_perm(uh23, ul23, 0x5410); w.w = __byte_perm(uh23, ul23, 0x7632);
             *reinterpret_cast<uint4*>(slot) = w;
         }
         __syncthreads();                               // tile t has landed and is converted
         float acc0[4][4], acc1[4][4];
-        contract(a, acc0);
-        contract(NB - 1 - a, acc1);
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc0[n][e] = acc1[n][e] = 0.f;
+        int u = 0;
+        for (int q = 0; q <= a; ++q, ++u) {
+            cp_async_wait_all();
+            if (q < a) issue(a, q + 1, (u + 1) & 1); else issue(NB - 1 - a, 0, (u + 1) & 1);
+            step(q, u & 1, acc0);
+        }
+        for (int q = 0; q < NB - a; ++q, ++u) {
+            cp_async_wait_all();
+            if (q + 1 < NB - a) issue(NB - 1 - a, q + 1, (u + 1) & 1);
+            step(q, u & 1, acc1);
+        }
         if (tn < ntiles && threadIdx.x < kTileRows) row_table(tn, buf ^ 1);
         __syncthreads();                               // every read of the noise tile is done: overwrite it in place
-        put(a, acc0);
-        put(NB - 1 - a, acc1);
+        put(a, acc0, buf, m0);
+        put(NB - 1 - a, acc1, buf, m1);
         __syncthreads();
+        // store phase: read this thread's slots, refill them with the next tile's noise (in flight while the rows go out)
         const long long n0 = (long long)t * kTileRows;
+        float4 out[Cfg::IPT];
+#pragma unroll
+        for (int it = 0; it < Cfg::IPT; ++it) {
+            const int e = threadIdx.x + it * THREADS;
+            out[it] = *reinterpret_cast<const float4*>(tile + (e / Cfg::V4_PER_ROW) * RS + 4 * (e % Cfg::V4_PER_ROW));
+        }
+        if (tn < ntiles) {
+#pragma unroll
+            for (int it = 0; it < Cfg::IPT; ++it) {
+                const int e = threadIdx.x + it * THREADS;
+                fill_slot(buf ^ 1, e / Cfg::V4_PER_ROW, e % Cfg::V4_PER_ROW);   // same thread, same slot as the read above
+            }
+        }
+        cp_async_commit();
 #pragma unroll
         for (int it = 0; it < Cfg::IPT; ++it) {
             const int e = threadIdx.x + it * THREADS;
             const int r = e / Cfg::V4_PER_ROW, v = e % Cfg::V4_PER_ROW;
-            if (n0 + r < Ntot) {
-                const float4 nz = *reinterpret_cast<const float4*>(tile + r * RS + 4 * v);
-                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu + (size_t)rows[buf * kTileRows + r].p * M + 4 * v));
-                float4 o;
-                o.x = m4.x + nz.x; o.y = m4.y + nz.y; o.z = m4.z + nz.z; o.w = m4.w + nz.w;
-                *reinterpret_cast<float4*>(x + (size_t)(n0 + r) * M + 4 * v) = o;
-            }
-            if (tn < ntiles) fill_slot(buf ^ 1, r, v);   // same thread, same slot: ordered after its own read above
+            if (n0 + r < Ntot) *reinterpret_cast<float4*>(x + (size_t)(n0 + r) * M + 4 * v) = out[it];
         }
-        cp_async_commit();
     }
     cp_async_wait_all();
 }
