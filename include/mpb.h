@@ -166,6 +166,14 @@ int mpb_sample_stomp(const float* L_R, const float* mu, const float* eps, float*
 int mpb_prior_matvec(const float* Sigma_inv, const float* mu, float* y,
                      int P, int M, int half_bw, void* stream);
 
+/* Structured variant for a precision that couples only entries of the same dof (the reference's A^T Q^-1 A,
+ * mp_priors_multi.py:213-251: at most 7 non-zeros per row, at columns i + m*dof, m = -3..3, in the state order
+ * (t,[pos|vel],j)).  mpb_prior_dof_structured checks the zero pattern of Sigma_inv [M,M], M = 2*H*dof, bit-exactly
+ * (*structured = 1, host int; synchronises `stream`, one-off setup); mpb_prior_matvec_dof is then bit-identical to
+ * mpb_prior_matvec with half_bw = 2D-1. */
+int mpb_prior_dof_structured(const float* Sigma_inv, int H, int dof, int* structured, void* stream);
+int mpb_prior_matvec_dof(const float* Sigma_inv, const float* mu, float* y, int P, int H, int dof, void* stream);
+
 /* Fused FK + collision + GP/goal cost (+ importance-sampling term) of B trajectories.
  * Replaces CostComposite.eval over {CostGP, CostGoalPrior, CostCollision...}
  * (cost_functions.py:70-87,171-189,271-289,523-536), Cost.get_q_pos_vel_and_fk_map (:41-53),
@@ -211,8 +219,8 @@ int mpb_softmax_update(const float* cost, const float* x, float* mu, float* weig
  * L_split: NULL (FP32 SIMT sampler) or the [2,M,M] output of mpb_split_tf32 (tensor-core sampler).
  * workspace: x [P,S,H,D], cost [P,S], weights [P,S], is_vec [P,M]; free_flag [P*S] may be NULL.
  * mpb_stoch_gpmp_iter_kron: same, sampling through mpb_sample_gp_kron_tc (L_kron_tc != NULL) or mpb_sample_gp_kron
- * with the packed factor. */
-int mpb_stoch_gpmp_iter_kron(const float* L_kron, const void* L_kron_tc, const float* Sigma_inv, const float* eps,
+ * with the packed factor; sigma_inv_structured != 0 (mpb_prior_dof_structured) selects mpb_prior_matvec_dof. */
+int mpb_stoch_gpmp_iter_kron(const float* L_kron, const void* L_kron_tc, const float* Sigma_inv, int sigma_inv_structured, const float* eps,
                              float* mu, float* x, float* cost, float* weights, float* is_vec,
                              uint8_t* free_flag,
                              int P, int S, int H,

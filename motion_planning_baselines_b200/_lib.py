@@ -76,7 +76,9 @@ _SIGNATURES = {
     'mpb_stoch_gpmp_iter': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                       C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
                                       _f, _f, _vp]),
-    'mpb_stoch_gpmp_iter_kron': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+    'mpb_prior_dof_structured': (C.c_int, [_vp, _i, _i, C.POINTER(C.c_int), _vp]),
+    'mpb_prior_matvec_dof': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    'mpb_stoch_gpmp_iter_kron': (C.c_int, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                            C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
                                            _f, _f, _vp]),
     'mpb_chomp_run': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _f, _f, _f, _i, _vp]),

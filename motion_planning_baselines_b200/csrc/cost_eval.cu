@@ -342,11 +342,21 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
             }
             // ---- importance-sampling dot  x . (Sigma^-1 mu_p) ---------------------------
             if (isv && valid) {
+                // terms reach 1e7 and cancel: double-float accumulation (error-free TwoProd / TwoSum in fp32; the FP64
+                // pipe is slow on this part), rounded into the fp64 running sum once per waypoint
                 const float* yv = isv + t * D;
-                double s = 0.0;
+                float hi = 0.f, lo = 0.f;
 #pragma unroll 2
-                for (int k = 0; k < D; ++k) s = fma((double)xt[k], (double)__ldg(yv + k), s);
-                acc_is += s;
+                for (int k = 0; k < D; ++k) {
+                    const float xv = xt[k], yk = __ldg(yv + k);
+                    const float p = __fmul_rn(xv, yk);
+                    const float e = fmaf(xv, yk, -p);                     // xv*yk = p + e exactly
+                    const float s = __fadd_rn(hi, p);
+                    const float z = __fsub_rn(s, hi);
+                    lo = __fadd_rn(lo, __fadd_rn(__fadd_rn(__fsub_rn(hi, __fsub_rn(s, z)), __fsub_rn(p, z)), e));
+                    hi = s;
+                }
+                acc_is += (double)hi + (double)lo;
             }
             // ---- collision (warp-synchronous: every lane takes part, results masked) -------
             if (nf > 0) {

@@ -218,6 +218,59 @@ __global__ void __launch_bounds__(256) prior_matvec_kernel(const float* __restri
         if (p0 + q < P) y[(size_t)(p0 + q) * M + i] = __fadd_rn(hi[q], lo[q]);
 }
 
+// Structured variant of prior_matvec_kernel.  With the state order (t, [pos|vel], j) the index is (2t+a)*dof + j, and the
+// reference's precision A^T Q^-1 A (mp_priors_multi.py:213-251) couples only entries of the same dof j whose block
+// indices 2t+a differ by at most 3: row i has at most 7 non-zeros, at columns i + m*dof, m = -3..3, instead of the
+// 2*(2D-1)+1 = 55 the band walk visits.  mpb_prior_dof_structured verifies the zero pattern bit-exactly; skipping exact
+// zeros leaves every double-float partial sum unchanged, so the result is bit-identical to prior_matvec_kernel.
+constexpr int kMvDofP = 4;
+__global__ void __launch_bounds__(256) prior_matvec_dof_kernel(const float* __restrict__ Sinv, const float* __restrict__ mu,
+                                                               float* __restrict__ y, int P, int M, int dof) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p0 = blockIdx.y * kMvDofP;
+    if (i >= M) return;
+    float sv[7];
+#pragma unroll
+    for (int m = 0; m < 7; ++m) {
+        const int j = i + (m - 3) * dof;
+        sv[m] = (j >= 0 && j < M) ? __ldg(Sinv + (size_t)j * M + i) : 0.f;      // symmetric: column i read row-wise (coalesced)
+    }
+    float mv[kMvDofP][7];
+#pragma unroll
+    for (int q = 0; q < kMvDofP; ++q) {
+        const float* mrow = mu + (size_t)min(p0 + q, P - 1) * M;
+#pragma unroll
+        for (int m = 0; m < 7; ++m) {
+            const int j = i + (m - 3) * dof;
+            mv[q][m] = (j >= 0 && j < M) ? __ldg(mrow + j) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kMvDofP; ++q) {
+        float hi = 0.f, lo = 0.f;
+#pragma unroll
+        for (int m = 0; m < 7; ++m) {
+            const float p = __fmul_rn(sv[m], mv[q][m]);
+            const float e = fmaf(sv[m], mv[q][m], -p);
+            const float t = __fadd_rn(hi, p);
+            const float z = __fsub_rn(t, hi);
+            lo = __fadd_rn(lo, __fadd_rn(__fadd_rn(__fsub_rn(hi, __fsub_rn(t, z)), __fsub_rn(p, z)), e));
+            hi = t;
+        }
+        if (p0 + q < P) y[(size_t)(p0 + q) * M + i] = __fadd_rn(hi, lo);
+    }
+}
+
+// *bad |= 1 if Sinv[r][c] != 0 for some pair that the structured mat-vec skips
+__global__ void prior_dof_check_kernel(const float* __restrict__ Sinv, int* __restrict__ bad, int M, int dof) {
+    const long long total = (long long)M * M;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / M), c = (int)(idx - (long long)r * M);
+        const int dj = (r % dof) - (c % dof), db = r / dof - c / dof;
+        if ((dj != 0 || db > 3 || db < -3) && Sinv[idx] != 0.f) atomicOr(bad, 1);
+    }
+}
+
 }  // namespace mpb
 
 extern "C" int mpb_sample_gp(const float* L, const float* mu, const float* eps, float* x, int P, int S, int M,
@@ -260,4 +313,40 @@ extern "C" int mpb_prior_matvec(const float* Sigma_inv, const float* mu, float* 
     MPB_REQUIRE(smem <= 48 * 1024, "mpb_prior_matvec: half bandwidth %d too large", half_bw);
     prior_matvec_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(Sigma_inv, mu, y, P, M, half_bw);
     return check_launch("mpb_prior_matvec");
+}
+
+extern "C" int mpb_prior_dof_structured(const float* Sigma_inv, int H, int dof, int* structured, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(Sigma_inv && structured, "mpb_prior_dof_structured: null pointer");
+    MPB_REQUIRE(H >= 1 && dof >= 1 && (long long)H * dof <= 16384, "mpb_prior_dof_structured: bad sizes H=%d dof=%d", H, dof);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int M = 2 * H * dof;
+    int* bad = nullptr;
+    cudaError_t e = cudaMalloc(&bad, sizeof(int));
+    if (e != cudaSuccess) { set_error("mpb_prior_dof_structured: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+    int h_bad = 1;
+    e = cudaMemsetAsync(bad, 0, sizeof(int), st);
+    if (e == cudaSuccess) {
+        const long long total = (long long)M * M;
+        prior_dof_check_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, st>>>(Sigma_inv, bad, M, dof);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(bad);
+    if (e != cudaSuccess) { set_error("mpb_prior_dof_structured: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+    *structured = h_bad ? 0 : 1;
+    return MPB_OK;
+}
+
+extern "C" int mpb_prior_matvec_dof(const float* Sigma_inv, const float* mu, float* y, int P, int H, int dof, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(Sigma_inv && mu && y, "mpb_prior_matvec_dof: null pointer");
+    MPB_REQUIRE(P >= 0 && H >= 1 && dof >= 1, "mpb_prior_matvec_dof: bad sizes");
+    if (P == 0) return MPB_OK;
+    const int M = 2 * H * dof;
+    MPB_REQUIRE(P <= 65535 * kMvDofP, "mpb_prior_matvec_dof: too many particles per call");
+    dim3 grid((M + 255) / 256, (P + kMvDofP - 1) / kMvDofP);
+    prior_matvec_dof_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(Sigma_inv, mu, y, P, M, dof);
+    return check_launch("mpb_prior_matvec_dof");
 }

@@ -96,6 +96,11 @@ class StochGPMP(OptimizationPlanner):
                                                 self.start_state, particle_means=self._particle_means,
                                                 goal_states=self.multi_goal_states)
         self.Sigma_inv = self._sample_dist.Sigma_inv
+        # the reference's precision couples only equal dofs (<= 7 non-zeros per row): verified bit-exactly, once
+        ok = C.c_int(0)
+        _lib.check(_lib.lib().mpb_prior_dof_structured(_lib.ptr(self.Sigma_inv), self.n_support_points, self.n_dof,
+                                                       C.byref(ok), _lib.stream_ptr()))
+        self._sinv_structured = bool(ok.value)
         P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
         ta = self.tensor_args
         self.state_samples = torch.empty(P, S, H, D, **ta)
@@ -109,11 +114,20 @@ class StochGPMP(OptimizationPlanner):
     def _get_costs(self, **observation):
         """cost.eval + importance-sampling ratio term (stoch_gpmp.py:235-242) on self.state_samples."""
         P, S, M = self.num_particles, self.num_samples, self.n_support_points * self.d_state_opt
-        _lib.check(_lib.lib().mpb_prior_matvec(_lib.ptr(self.Sigma_inv), _lib.ptr(self._particle_means),
-                                               _lib.ptr(self._is_vec), P, M, 2 * self.d_state_opt - 1, _lib.stream_ptr()))
+        self._prior_matvec(_lib.stream_ptr())
         self.cost.eval(self.state_samples, is_vec=self._is_vec, samples_per_particle=S, is_scale=self.temperature,
                        out=self.costs.view(-1), free_flag=self.free_flags, **observation)
         return self.costs
+
+    def _prior_matvec(self, st):
+        """is_vec[p] = Sigma_inv @ mu_p (first half of the IS term, stoch_gpmp.py:239-241)."""
+        P, H, D = self.num_particles, self.n_support_points, self.d_state_opt
+        if self._sinv_structured:
+            _lib.check(_lib.lib().mpb_prior_matvec_dof(_lib.ptr(self.Sigma_inv), _lib.ptr(self._particle_means),
+                                                       _lib.ptr(self._is_vec), P, H, self.n_dof, st))
+        else:
+            _lib.check(_lib.lib().mpb_prior_matvec(_lib.ptr(self.Sigma_inv), _lib.ptr(self._particle_means),
+                                                   _lib.ptr(self._is_vec), P, H * D, 2 * D - 1, st))
 
     def sample_and_eval(self, eps=None, **observation):
         P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
@@ -158,7 +172,7 @@ class StochGPMP(OptimizationPlanner):
             if self._sample_dist.scale_tril_kron is not None:
                 _lib.check(lib.mpb_stoch_gpmp_iter_kron(
                     _lib.ptr(self._sample_dist.scale_tril_kron), _lib.ptr(self._sample_dist.scale_tril_kron_tc),
-                    _lib.ptr(self.Sigma_inv), _lib.ptr(e),
+                    _lib.ptr(self.Sigma_inv), int(self._sinv_structured), _lib.ptr(e),
                     _lib.ptr(self._particle_means), _lib.ptr(self.state_samples), _lib.ptr(self.costs), _lib.ptr(self._w_buf),
                     _lib.ptr(self._is_vec), _lib.ptr(self.free_flags), P, S, H,
                     C.byref(self.robot.desc), fields, nf, C.byref(gp), self.temperature, self.step_size, _lib.stream_ptr()))
@@ -212,8 +226,7 @@ class StochGPMP(OptimizationPlanner):
             _lib.check(lib.mpb_sample_gp(_lib.ptr(self._sample_dist.scale_tril), _lib.ptr(self._particle_means), _lib.ptr(eps),
                                          _lib.ptr(self.state_samples), P, S, M, st))
         rec(1)
-        _lib.check(lib.mpb_prior_matvec(_lib.ptr(self.Sigma_inv), _lib.ptr(self._particle_means), _lib.ptr(self._is_vec),
-                                        P, M, 2 * D - 1, st))
+        self._prior_matvec(st)
         rec(2)
         _lib.check(lib.mpb_cost_eval(_lib.ptr(self.state_samples), P * S, H, C.byref(self.robot.desc), fields, nf,
                                      C.byref(gp), _lib.ptr(self._is_vec), S, self.temperature, _lib.ptr(self.costs), None,

@@ -180,3 +180,38 @@ def test_kron_tc_matches_fp64(dof, H, P, S, dev):
     xz = torch.empty(P, S, M, **dev)
     _lib.check(lib.mpb_sample_gp_kron_tc(_lib.ptr(LkF), _lib.ptr(mu), _lib.ptr(torch.zeros_like(eps)), _lib.ptr(xz), P, S, H, dof, _lib.stream_ptr()))
     assert torch.equal(xz, mu.unsqueeze(1).expand(P, S, M))
+
+
+@pytest.mark.parametrize('name,P', [('C3', 37), ('C4', 512), ('C4', 3)])
+def test_structured_prior_matvec_bit_identical(name, P, dev):
+    """mpb_prior_matvec_dof (7 non-zeros per row) == mpb_prior_matvec (55-entry band walk), bit for bit, on the
+    reference's precision matrix; a precision that couples dofs is rejected by mpb_prior_dof_structured."""
+    from motion_planning_baselines_b200 import _lib
+    from motion_planning_baselines_b200.factors import GPFactor, MultiMPPrior, UnaryFactor
+    cfg = configs.config(name)
+    prm, H, dof = cfg['params'], cfg['H'], cfg['robot'].q_dim
+    D, M = 2 * dof, 2 * dof * H
+    start = torch.cat((torch.tensor(cfg['start']), torch.zeros(dof))).to(**dev)
+    goal = torch.cat((torch.tensor(cfg['goal']), torch.zeros(dof))).to(**dev).unsqueeze(0)
+    prior = MultiMPPrior(H - 1, cfg['dt'], D, dof,
+                         UnaryFactor(D, prm['sigma_start_sample'], tensor_args=dev).K,
+                         GPFactor(dof, prm['sigma_gp_sample'], cfg['dt'], H - 1, tensor_args=dev).Q_inv[0],
+                         start, K_g_inv=UnaryFactor(D, prm['sigma_goal_sample'], tensor_args=dev).K, goal_states=goal,
+                         tensor_args=dev)
+    lib = _lib.lib()
+    ok = C.c_int(-1)
+    _lib.check(lib.mpb_prior_dof_structured(_lib.ptr(prior.Sigma_inv), H, dof, C.byref(ok), _lib.stream_ptr()))
+    assert ok.value == 1
+    gen = torch.Generator(device='cuda').manual_seed(P)
+    mu = torch.randn(P, M, generator=gen, **dev)
+    y_dof = torch.full((P, M), float('nan'), **dev)
+    y_band = torch.full((P, M), float('nan'), **dev)
+    _lib.check(lib.mpb_prior_matvec_dof(_lib.ptr(prior.Sigma_inv), _lib.ptr(mu), _lib.ptr(y_dof), P, H, dof, _lib.stream_ptr()))
+    _lib.check(lib.mpb_prior_matvec(_lib.ptr(prior.Sigma_inv), _lib.ptr(mu), _lib.ptr(y_band), P, M, 2 * D - 1, _lib.stream_ptr()))
+    assert torch.equal(y_dof, y_band)
+    ref = mu.double() @ prior.Sigma_inv.double().t()
+    assert float((y_dof.double() - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
+    bad = prior.Sigma_inv.clone()
+    bad[D + 1, 0] = 1.0          # (t=1, pos, j=1) x (t=0, pos, j=0): couples two dofs
+    _lib.check(lib.mpb_prior_dof_structured(_lib.ptr(bad), H, dof, C.byref(ok), _lib.stream_ptr()))
+    assert ok.value == 0
