@@ -50,6 +50,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 template <int DOF, int H>
 __global__ void __launch_bounds__(KronCfg<DOF, H>::THREADS, 1)
@@ -223,15 +224,24 @@ sample_gp_kron_kernel(const float* __restrict__ LkT, const float* __restrict__ m
 // coalesced row copy that adds mu_p and immediately refills the slot it has just read with the next tile's noise, so
 // the next tile streams in while this one is written out.
 template <int DOF, int H>
-struct KronMmaCfg : KronCfg<DOF, H> {
-    using Base = KronCfg<DOF, H>;
-    static constexpr int RS = Base::M + 4;                         // padded row stride in floats
-    static constexpr int TILE_FLOATS = kTileRows * RS;
-    static constexpr int V4_PER_ROW = Base::M / 4;
-    static constexpr int IPT = kTileRows * V4_PER_ROW / Base::THREADS;   // float4 slots per thread = 8
-    static constexpr size_t SMEM = (size_t)(TILE_FLOATS + Base::WARPS * Base::LBUF_FLOATS) * sizeof(float) + 2 * kTileRows * 16;
+struct KronMmaCfg {
+    static constexpr int D = 2 * DOF, M = H * D, N = 2 * H;       // N = rows/cols of one per-dof block
+    static constexpr int NB = N / 16;                              // 16-row output blocks per dof
+    static constexpr int ROWS = 32, NT = ROWS / 8;                 // sample rows per tile, m16n8 n-tiles per warp
+    static constexpr int PPW = 1;                                  // block pairs (a, NB-1-a) per warp
+    static constexpr int STAGES = 3;                               // factor-chunk ring: two chunks in flight
+    static constexpr int WPD = NB / 2 / PPW;                       // warps per dof
+    static constexpr int WARPS = DOF * WPD, THREADS = WARPS * 32;
+    static constexpr int CTAS_PER_SM = 1;
+    static constexpr int RS = M + 4;                               // padded row stride in floats
+    static constexpr int TILE_FLOATS = ROWS * RS;
+    static constexpr int V4_PER_ROW = M / 4;
+    static constexpr int IPT = ROWS * V4_PER_ROW / THREADS;        // float4 slots per thread = 8
+    static constexpr int LBUF_FLOATS = STAGES * 256;               // per warp: STAGES x (hi + lo A fragments of one chunk)
+    static constexpr size_t SMEM = (size_t)(TILE_FLOATS + WARPS * LBUF_FLOATS) * sizeof(float) + 2 * ROWS * 16;
+    static_assert(H % 16 == 0 && (NB / 2) % PPW == 0, "H must be a multiple of 16 * PPW");
     static_assert(RS % 32 == 4, "row stride must be 4 mod 32");
-    static_assert(kTileRows * V4_PER_ROW % Base::THREADS == 0, "tile copy mapping");
+    static_assert(ROWS * V4_PER_ROW % THREADS == 0 && IPT == 8, "tile copy mapping");
 };
 
 __device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
@@ -256,27 +266,28 @@ struct KronRow {            // per tile row: where its noise comes from and whic
 };
 
 template <int DOF, int H>
-__global__ void __launch_bounds__(KronCfg<DOF, H>::THREADS, 1)
+__global__ void __launch_bounds__(KronMmaCfg<DOF, H>::THREADS, KronMmaCfg<DOF, H>::CTAS_PER_SM)
 sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restrict__ mu, const float* __restrict__ eps,
                           float* __restrict__ x, int P, int S) {
     using Cfg = KronMmaCfg<DOF, H>;
     constexpr int M = Cfg::M, N = Cfg::N, NB = Cfg::NB, WPD = Cfg::WPD, RS = Cfg::RS, THREADS = Cfg::THREADS;
+    constexpr int ROWS = Cfg::ROWS, NT = Cfg::NT, PPW = Cfg::PPW;
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* lbuf = smem + Cfg::TILE_FLOATS + warp * Cfg::LBUF_FLOATS;
-    KronRow* rows = reinterpret_cast<KronRow*>(smem + Cfg::TILE_FLOATS + Cfg::WARPS * Cfg::LBUF_FLOATS);   // [2][32]
+    KronRow* rows = reinterpret_cast<KronRow*>(smem + Cfg::TILE_FLOATS + Cfg::WARPS * Cfg::LBUF_FLOATS);   // [2][ROWS]
 
     const long long Ntot = (long long)P * S;
-    const int ntiles = (int)((Ntot + kTileRows - 1) / kTileRows);
+    const int ntiles = (int)((Ntot + ROWS - 1) / ROWS);
 
-    const int j = warp / WPD, a = warp - j * WPD;
+    const int j = warp / WPD, a0 = (warp - j * WPD) * PPW;       // this warp owns the block pairs a0 .. a0+PPW-1 of dof j
     const int g = lane >> 2, t4 = lane & 3;
     const uint32_t* Lj = LkF + (size_t)j * N * N;                      // [blk][q][hi|lo][lane][4]
     const float inv_scale = reinterpret_cast<const float*>(LkF + (size_t)DOF * N * N)[j];
 
-    auto row_table = [&](int t, int buf) {          // threads 0..31
-        const long long n = (long long)t * kTileRows + threadIdx.x;
+    auto row_table = [&](int t, int buf) {          // threads 0..ROWS-1
+        const long long n = (long long)t * ROWS + threadIdx.x;
         KronRow r;
         r.src = -1; r.p = 0; r.pad = 0;
         if (n < Ntot) {
@@ -284,36 +295,42 @@ sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restr
             r.src = ((long long)s * P + p) * M;
             r.p = p;
         }
-        rows[buf * kTileRows + threadIdx.x] = r;
+        rows[buf * ROWS + threadIdx.x] = r;
     };
     auto fill_slot = [&](int buf, int r, int v) {   // float4 slot (row r, 4-column group v) <- next tile's noise
-        const long long src = rows[buf * kTileRows + r].src;
+        const long long src = rows[buf * ROWS + r].src;
         float* dst = tile + r * RS + 4 * v;
         if (src >= 0) cp_async16_cg(dst, eps + src + 4 * v);
         else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     };
 
     // Factor staging: every lane copies exactly the 2 x 16 bytes (hi and lo A fragments of one 16-row x 16-k chunk) it
-    // reads back itself, so the ring needs no warp synchronisation.  The chunks of the two blocks of a warp form ONE
-    // sequence u = 0 .. NB (block a: q = 0..a, then block NB-1-a: q = 0..NB-1-a); chunk u+1 is in flight while u runs.
+    // reads back itself, so the ring needs no warp synchronisation.  All chunks of a warp form ONE sequence (per pair:
+    // block a with q = 0..a, then block NB-1-a with q = 0..NB-1-a -- NB+1 chunks whatever a is); chunk u+1 is in flight
+    // while chunk u runs, across block, pair and tile boundaries.
     float* ldst = lbuf + lane * 4;
-    auto issue = [&](int blk, int q, int stage) {
-        const uint32_t* s0 = Lj + ((size_t)blk * NB + q) * 256 + lane * 4;
-        float* dst = ldst + stage * 256;
-        cp_async16(dst, s0);
-        cp_async16(dst + 128, s0 + 128);
+    constexpr int SEQ = PPW * (NB + 1);                // chunks per warp and tile
+    auto issue = [&](int v, int stage) {               // chunk v of the sequence (v >= SEQ: nothing, but keep the group count)
+        if (v < SEQ) {
+            const int i = v / (NB + 1), r = v - i * (NB + 1), a = a0 + i;
+            const int blk = r <= a ? a : NB - 1 - a, q = r <= a ? r : r - a - 1;
+            const uint32_t* s0 = Lj + ((size_t)blk * NB + q) * 256 + lane * 4;
+            float* dst = ldst + stage * 256;
+            cp_async16(dst, s0);
+            cp_async16(dst + 128, s0 + 128);
+        }
         cp_async_commit();
     };
     // B fragment: element (k, sample) = tile[sample * RS + DOF*k + j]; MMA k slots (2*t4, 2*t4+1, 2*t4+8, 2*t4+9) hold
     // k = 16q + t4 + (0, 4, 8, 12) -- the same permutation is baked into the packed A fragments
     const uint32_t* ebase = reinterpret_cast<const uint32_t*>(tile) + g * RS + DOF * t4 + j;
     // acc[n][.] : m16n8 accumulator of n-tile n (samples 8n..8n+7) of the current 16-row block
-    auto step = [&](int q, int stage, float (&acc)[4][4]) {
+    auto step = [&](int q, int stage, float (&acc)[NT][4]) {
         const uint4 ahi = *reinterpret_cast<const uint4*>(ldst + stage * 256);
         const uint4 alo = *reinterpret_cast<const uint4*>(ldst + stage * 256 + 128);
         const uint32_t* eb = ebase + q * 16 * DOF;
 #pragma unroll
-        for (int n = 0; n < 4; ++n) {
+        for (int n = 0; n < NT; ++n) {
             const uint32_t* e0 = eb + n * 8 * RS;
             const uint32_t w0 = e0[0], w1 = e0[4 * DOF], w2 = e0[8 * DOF], w3 = e0[12 * DOF];
             const uint32_t bhi0 = __byte_perm(w0, w1, 0x5410), blo0 = __byte_perm(w0, w1, 0x7632);
@@ -323,9 +340,9 @@ sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restr
             mma_f16(acc[n], ahi, bhi0, bhi1);
         }
     };
-    // x = mu_p + noise: the mean of the particle every row of the tile belongs to (one particle per tile when S % 32 == 0)
-    const bool one_particle = (S % kTileRows) == 0;
-    auto put = [&](int blk, const float (&acc)[4][4], int buf, const float (&mrow)[2]) {
+    // x = mu_p + noise: the mean of the particle every row of the tile belongs to (one particle per tile when S % ROWS == 0)
+    const bool one_particle = (S % ROWS) == 0;
+    auto put = [&](int blk, const float (&acc)[NT][4], int buf, const float (&mrow)[2]) {
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow) {
             const int c = DOF * (16 * blk + g + 8 * hrow) + j;                       // == (i>>1)*D + (i&1)*DOF + j
@@ -333,16 +350,16 @@ sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restr
             if (one_particle) {
                 const float m = mrow[hrow];
 #pragma unroll
-                for (int n = 0; n < 4; ++n) {
+                for (int n = 0; n < NT; ++n) {
                     col[(8 * n) * RS] = m + acc[n][2 * hrow] * inv_scale;
                     col[(8 * n + 1) * RS] = m + acc[n][2 * hrow + 1] * inv_scale;
                 }
             } else {
 #pragma unroll
-                for (int n = 0; n < 4; ++n)
+                for (int n = 0; n < NT; ++n)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int p = rows[buf * kTileRows + 8 * n + 2 * t4 + e].p;
+                        const int p = rows[buf * ROWS + 8 * n + 2 * t4 + e].p;
                         col[(8 * n + e) * RS] = __ldg(mu + (size_t)p * M + c) + acc[n][2 * hrow + e] * inv_scale;
                     }
             }
@@ -351,8 +368,9 @@ sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restr
 
     int t = blockIdx.x;
     int buf = 0;
+    unsigned u = 0;                                    // running chunk counter (selects the ring stage)
     if (t < ntiles) {
-        if (threadIdx.x < kTileRows) row_table(t, 0);
+        if (threadIdx.x < ROWS) row_table(t, 0);
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < Cfg::IPT; ++it) {
@@ -364,15 +382,18 @@ sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restr
     for (; t < ntiles; t += gridDim.x, buf ^= 1) {
         const int tn = t + gridDim.x;
         cp_async_wait_all();
-        issue(a, 0, 0);                                // first factor chunk flies during the conversion pass
-        float m0[2] = {0.f, 0.f}, m1[2] = {0.f, 0.f};  // means of this thread's four output rows (one particle per tile)
-        if (one_particle) {
-            const float* mp = mu + (size_t)(((long long)t * kTileRows) / S) * M + j;
-            m0[0] = __ldg(mp + DOF * (16 * a + g));
-            m0[1] = __ldg(mp + DOF * (16 * a + g + 8));
-            m1[0] = __ldg(mp + DOF * (16 * (NB - 1 - a) + g));
-            m1[1] = __ldg(mp + DOF * (16 * (NB - 1 - a) + g + 8));
-        }
+        issue(0, u % Cfg::STAGES);                     // the first two factor chunks fly during the conversion pass
+        issue(1, (u + 1) % Cfg::STAGES);
+        float mrow[PPW][2][2];                         // means of this thread's output rows (one particle per tile)
+#pragma unroll
+        for (int i = 0; i < PPW; ++i)
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb)
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int blk = hb ? NB - 1 - (a0 + i) : a0 + i;
+                    mrow[i][hb][hrow] = one_particle ? __ldg(mu + (size_t)(((long long)t * ROWS) / S) * M + DOF * (16 * blk + g + 8 * hrow) + j) : 0.f;
+                }
 #pragma unroll
         for (int it = 0; it < Cfg::IPT; ++it) {        // own slots only: fp32 -> packed (fp16 hi | fp16 lo << 16)
             const int e = threadIdx.x + it * THREADS;
@@ -390,29 +411,40 @@ sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restr
             *reinterpret_cast<uint4*>(slot) = w;
         }
         __syncthreads();                               // tile t has landed and is converted
-        float acc0[4][4], acc1[4][4];
+        float acc[PPW][2][NT][4];
 #pragma unroll
-        for (int n = 0; n < 4; ++n)
+        for (int i = 0; i < PPW; ++i)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc0[n][e] = acc1[n][e] = 0.f;
-        int u = 0;
-        for (int q = 0; q <= a; ++q, ++u) {
-            cp_async_wait_all();
-            if (q < a) issue(a, q + 1, (u + 1) & 1); else issue(NB - 1 - a, 0, (u + 1) & 1);
-            step(q, u & 1, acc0);
+            for (int hb = 0; hb < 2; ++hb)
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[i][hb][n][e] = 0.f;
+        int v = 0;                                     // chunk index within this tile's sequence
+#pragma unroll
+        for (int i = 0; i < PPW; ++i) {
+            const int a = a0 + i;
+            for (int q = 0; q <= a; ++q, ++u, ++v) {
+                cp_async_wait_1();
+                issue(v + 2, (u + 2) % Cfg::STAGES);
+                step(q, u % Cfg::STAGES, acc[i][0]);
+            }
+            for (int q = 0; q < NB - a; ++q, ++u, ++v) {
+                cp_async_wait_1();
+                issue(v + 2, (u + 2) % Cfg::STAGES);
+                step(q, u % Cfg::STAGES, acc[i][1]);
+            }
         }
-        for (int q = 0; q < NB - a; ++q, ++u) {
-            cp_async_wait_all();
-            if (q + 1 < NB - a) issue(NB - 1 - a, q + 1, (u + 1) & 1);
-            step(q, u & 1, acc1);
-        }
-        if (tn < ntiles && threadIdx.x < kTileRows) row_table(tn, buf ^ 1);
+        if (tn < ntiles && threadIdx.x < ROWS) row_table(tn, buf ^ 1);
         __syncthreads();                               // every read of the noise tile is done: overwrite it in place
-        put(a, acc0, buf, m0);
-        put(NB - 1 - a, acc1, buf, m1);
+#pragma unroll
+        for (int i = 0; i < PPW; ++i) {
+            put(a0 + i, acc[i][0], buf, mrow[i][0]);
+            put(NB - 1 - (a0 + i), acc[i][1], buf, mrow[i][1]);
+        }
         __syncthreads();
         // store phase: read this thread's slots, refill them with the next tile's noise (in flight while the rows go out)
-        const long long n0 = (long long)t * kTileRows;
+        const long long n0 = (long long)t * ROWS;
         float4 out[Cfg::IPT];
 #pragma unroll
         for (int it = 0; it < Cfg::IPT; ++it) {
@@ -496,26 +528,28 @@ __global__ void kron_frag_kernel(const float* __restrict__ LkT, uint32_t* __rest
 
 template <int DOF, int H, bool MMA>
 static int launch_kron(const void* Lp, const float* mu, const float* eps, float* x, int P, int S, cudaStream_t st) {
-    using Cfg = KronCfg<DOF, H>;
     const void* kern = MMA ? (const void*)sample_gp_kron_mma_kernel<DOF, H> : (const void*)sample_gp_kron_kernel<DOF, H>;
-    const size_t smem_bytes = MMA ? KronMmaCfg<DOF, H>::SMEM : Cfg::SMEM;
+    const size_t smem_bytes = MMA ? KronMmaCfg<DOF, H>::SMEM : KronCfg<DOF, H>::SMEM;
+    const int threads = MMA ? KronMmaCfg<DOF, H>::THREADS : KronCfg<DOF, H>::THREADS;
+    const int tile_rows = MMA ? KronMmaCfg<DOF, H>::ROWS : kTileRows;
     static thread_local int cached_dev = -1, per_sm = 0;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != cached_dev) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) { set_error("mpb_sample_gp_kron: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+        if (MMA) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int n = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, Cfg::THREADS, smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem_bytes);
         if (e != cudaSuccess || n < 1) { set_error("mpb_sample_gp_kron: kernel does not fit on this device"); return MPB_ECUDA; }
         per_sm = n;
         cached_dev = dev;
     }
-    const long long ntiles = ((long long)P * S + kTileRows - 1) / kTileRows;
+    const long long ntiles = ((long long)P * S + tile_rows - 1) / tile_rows;
     const long long cap = (long long)sm_count() * per_sm;
     const int grid = (int)(ntiles < cap ? ntiles : cap);
     void* args[] = {(void*)&Lp, (void*)&mu, (void*)&eps, (void*)&x, (void*)&P, (void*)&S};
-    cudaError_t le = cudaLaunchKernel(kern, dim3(grid), dim3(Cfg::THREADS), args, smem_bytes, st);
+    cudaError_t le = cudaLaunchKernel(kern, dim3(grid), dim3(threads), args, smem_bytes, st);
     if (le != cudaSuccess) { set_error("mpb_sample_gp_kron: %s", cudaGetErrorString(le)); return MPB_ECUDA; }
     return check_launch("mpb_sample_gp_kron");
 }
