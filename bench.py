@@ -350,7 +350,8 @@ def main():
     kernels = []
     flops = [FLOP_SAMPLING, None, FLOP_FK + FLOP_SDF + FLOP_GP + FLOP_IS, None]
     sd = planner._sample_dist
-    k1_name = ('sample_gp_kron_mma_kernel (K1, structured, warp MMA fp16x2 split)' if sd.scale_tril_kron_tc is not None else
+    k1_name = ('sample_gp_kron_umma_kernel (K1, structured, tcgen05 3xTF32)' if sd.kron_tc_kind == 2 else
+               'sample_gp_kron_mma_kernel (K1, structured, warp MMA fp16x2 split)' if sd.kron_tc_kind == 1 else
                'sample_gp_kron_kernel (K1, structured FP32)' if sd.scale_tril_kron is not None else
                'sample_gp_tc_kernel (K1, tcgen05 3xTF32)' if sd.scale_tril_split is not None else 'sample_gp_simt_kernel (K1)')
     if sd.scale_tril_kron is not None:

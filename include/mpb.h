@@ -155,6 +155,18 @@ int mpb_sample_gp_kron_tc_prepare(const float* LkT, void* LkF, int H, int dof, v
 int mpb_sample_gp_kron_tc(const void* LkF, const float* mu, const float* eps, float* x,
                           int P, int S, int H, int dof, void* stream);
 
+/* tcgen05 variant of the structured sampler (csrc/sample_gp_tc.cu, sample_gp_kron_umma_kernel): TMA -> per-dof
+ * gather + 3xTF32 split into tensor memory -> one M128 x N32 tcgen05.mma chain per dof with TMEM accumulators -> dofs
+ * interleaved back in the epilogue.  Same contract as mpb_sample_gp_kron; agrees with it to ~2e-6 of the noise amplitude.
+ *   mpb_sample_gp_kron_umma_prepare : LkT (from mpb_sample_gp_kron_pack) -> Lp, the TF32 hi / lo factor tiles in the
+ *                                     order the kernel's TMA boxes read them; Lp holds mpb_sample_gp_kron_umma_floats(H, dof)
+ *                                     floats, 16-byte aligned.  One-off setup, stream-ordered. */
+int mpb_sample_gp_kron_umma_supported(int H, int dof);
+long long mpb_sample_gp_kron_umma_floats(int H, int dof);
+int mpb_sample_gp_kron_umma_prepare(const float* LkT, float* Lp, int H, int dof, void* stream);
+int mpb_sample_gp_kron_umma(const float* Lp, const float* mu, const float* eps, float* x,
+                            int P, int S, int H, int dof, void* stream);
+
 /* STOMP noise: x[p,s,h,j] = mu[p,h,j] + (h==0||h==H-1 ? 0 : sum_k L_R[h,k] eps[s,j,p,k])
  * Replaces STOMP.sample (mp_baselines/planners/stomp.py:97-108); eps is [S,D,P,H]. */
 int mpb_sample_stomp(const float* L_R, const float* mu, const float* eps, float* x,
@@ -218,9 +230,9 @@ int mpb_softmax_update(const float* cost, const float* x, float* mu, float* weig
  * Replaces the body of StochGPMP.optimize (stoch_gpmp.py:291-299).
  * L_split: NULL (FP32 SIMT sampler) or the [2,M,M] output of mpb_split_tf32 (tensor-core sampler).
  * workspace: x [P,S,H,D], cost [P,S], weights [P,S], is_vec [P,M]; free_flag [P*S] may be NULL.
- * mpb_stoch_gpmp_iter_kron: same, sampling through mpb_sample_gp_kron_tc (L_kron_tc != NULL) or mpb_sample_gp_kron
- * with the packed factor; sigma_inv_structured != 0 (mpb_prior_dof_structured) selects mpb_prior_matvec_dof. */
-int mpb_stoch_gpmp_iter_kron(const float* L_kron, const void* L_kron_tc, const float* Sigma_inv, int sigma_inv_structured, const float* eps,
+ * mpb_stoch_gpmp_iter_kron: same, sampling through mpb_sample_gp_kron_umma (tc_kind 2, L_kron_tc = Lp),
+ * mpb_sample_gp_kron_tc (tc_kind 1, L_kron_tc = LkF) or mpb_sample_gp_kron (tc_kind 0) with the packed factor; sigma_inv_structured != 0 (mpb_prior_dof_structured) selects mpb_prior_matvec_dof. */
+int mpb_stoch_gpmp_iter_kron(const float* L_kron, const void* L_kron_tc, int tc_kind, const float* Sigma_inv, int sigma_inv_structured, const float* eps,
                              float* mu, float* x, float* cost, float* weights, float* is_vec,
                              uint8_t* free_flag,
                              int P, int S, int H,

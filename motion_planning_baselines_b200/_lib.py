@@ -78,7 +78,11 @@ _SIGNATURES = {
                                       _f, _f, _vp]),
     'mpb_prior_dof_structured': (C.c_int, [_vp, _i, _i, C.POINTER(C.c_int), _vp]),
     'mpb_prior_matvec_dof': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
-    'mpb_stoch_gpmp_iter_kron': (C.c_int, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+    'mpb_sample_gp_kron_umma_supported': (C.c_int, [_i, _i]),
+    'mpb_sample_gp_kron_umma_floats': (C.c_longlong, [_i, _i]),
+    'mpb_sample_gp_kron_umma_prepare': (C.c_int, [_vp, _vp, _i, _i, _vp]),
+    'mpb_sample_gp_kron_umma': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'mpb_stoch_gpmp_iter_kron': (C.c_int, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                            C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
                                            _f, _f, _vp]),
     'mpb_chomp_run': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _vp, _f, _f, _f, _i, _vp]),

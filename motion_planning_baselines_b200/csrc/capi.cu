@@ -91,15 +91,16 @@ extern "C" int mpb_stoch_gpmp_iter(const float* L, const float* L_split, const f
     return mpb_softmax_update(cost, x, mu, weights, nullptr, temp, step, nullptr, P, S, H, D, stream);
 }
 
-extern "C" int mpb_stoch_gpmp_iter_kron(const float* L_kron, const void* L_kron_tc, const float* Sigma_inv, int sigma_inv_structured,
+extern "C" int mpb_stoch_gpmp_iter_kron(const float* L_kron, const void* L_kron_tc, int tc_kind, const float* Sigma_inv, int sigma_inv_structured,
                                         const float* eps, float* mu, float* x,
                                         float* cost, float* weights, float* is_vec, uint8_t* free_flag, int P, int S,
                                         int H, const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
                                         const mpb_gp_desc* gp, float temp, float step, void* stream) {
     MPB_REQUIRE(robot, "mpb_stoch_gpmp_iter_kron: robot is null");
     const int D = 2 * robot->q_dim, M = H * D;
-    int rc = L_kron_tc ? mpb_sample_gp_kron_tc(L_kron_tc, mu, eps, x, P, S, H, robot->q_dim, stream)
-                       : mpb_sample_gp_kron(L_kron, mu, eps, x, P, S, H, robot->q_dim, stream);
+    int rc = (tc_kind == 2 && L_kron_tc) ? mpb_sample_gp_kron_umma(static_cast<const float*>(L_kron_tc), mu, eps, x, P, S, H, robot->q_dim, stream)
+             : (tc_kind == 1 && L_kron_tc) ? mpb_sample_gp_kron_tc(L_kron_tc, mu, eps, x, P, S, H, robot->q_dim, stream)
+                                           : mpb_sample_gp_kron(L_kron, mu, eps, x, P, S, H, robot->q_dim, stream);
     if (rc) return rc;
     rc = sigma_inv_structured ? mpb_prior_matvec_dof(Sigma_inv, mu, is_vec, P, H, robot->q_dim, stream)
                               : mpb_prior_matvec(Sigma_inv, mu, is_vec, P, M, 2 * D - 1, stream);

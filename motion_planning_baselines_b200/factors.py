@@ -89,26 +89,35 @@ class MultiMPPrior:
         self.scale_tril = dist.MultivariateNormal(torch.zeros(self.M), precision_matrix=Sinv_cpu).scale_tril \
             .to(**tensor_args).contiguous()
         self.Sigma_inv = Sinv_cpu.to(**tensor_args).contiguous()
-        # Sampler selection (MPB_SAMPLE_GP = kron | kron_fp32 | tc | simt forces one; default: the first that applies).
+        # Sampler selection (MPB_SAMPLE_GP = kron | kron_mma | kron_fp32 | tc | simt forces one; default: the first that applies).
         #  kron: the factor decouples over the dofs (verified bit-exactly on the device) -> per-dof [2H,2H] blocks
         #  tc  : dense tcgen05 3xTF32 sampler; L pre-split into two TF32-representable parts
         #  simt: dense FP32 sampler
         mode = os.environ.get('MPB_SAMPLE_GP', 'auto')
         H = num_steps + 1
         self.scale_tril_kron = None
-        self.scale_tril_kron_tc = None
-        if mode in ('auto', 'kron', 'kron_fp32') and state_dim == 2 * dof and _lib.lib().mpb_sample_gp_kron_supported(H, dof):
+        self.scale_tril_kron_tc, self.kron_tc_kind = None, 0
+        if mode in ('auto', 'kron', 'kron_mma', 'kron_fp32') and state_dim == 2 * dof and _lib.lib().mpb_sample_gp_kron_supported(H, dof):
             packed = torch.empty(dof, 2 * H, 2 * H, **tensor_args)
             ok = C.c_int(0)
             _lib.check(_lib.lib().mpb_sample_gp_kron_pack(_lib.ptr(self.scale_tril), _lib.ptr(packed), H, dof,
                                                           C.byref(ok), _lib.stream_ptr()))
             if ok.value:
                 self.scale_tril_kron = packed
-                if mode != 'kron_fp32':     # tensor-core operand (fp16 hi/lo fragments); 'kron_fp32' keeps the exact FP32 kernel
-                    nbytes = _lib.lib().mpb_sample_gp_kron_tc_bytes(H, dof)
-                    self.scale_tril_kron_tc = torch.empty(nbytes, device=tensor_args['device'], dtype=torch.uint8)
-                    _lib.check(_lib.lib().mpb_sample_gp_kron_tc_prepare(_lib.ptr(packed), _lib.ptr(self.scale_tril_kron_tc),
-                                                                        H, dof, _lib.stream_ptr()))
+                # tensor-core operand: tcgen05 tiles ('kron', default) or warp-MMA fp16 fragments ('kron_mma');
+                # 'kron_fp32' keeps the exact FP32 kernel
+                lib = _lib.lib()
+                if mode in ('auto', 'kron') and lib.mpb_sample_gp_kron_umma_supported(H, dof):
+                    self.scale_tril_kron_tc = torch.empty(lib.mpb_sample_gp_kron_umma_floats(H, dof), **tensor_args)
+                    _lib.check(lib.mpb_sample_gp_kron_umma_prepare(_lib.ptr(packed), _lib.ptr(self.scale_tril_kron_tc),
+                                                                   H, dof, _lib.stream_ptr()))
+                    self.kron_tc_kind = 2
+                elif mode != 'kron_fp32':
+                    self.scale_tril_kron_tc = torch.empty(lib.mpb_sample_gp_kron_tc_bytes(H, dof), device=tensor_args['device'],
+                                                          dtype=torch.uint8)
+                    _lib.check(lib.mpb_sample_gp_kron_tc_prepare(_lib.ptr(packed), _lib.ptr(self.scale_tril_kron_tc),
+                                                                 H, dof, _lib.stream_ptr()))
+                    self.kron_tc_kind = 1
         self.scale_tril_split = None
         if self.scale_tril_kron is None and mode != 'simt' and _lib.lib().mpb_sample_gp_tc_supported(1, 1, self.M):
             self.scale_tril_split = torch.empty(2, self.M, self.M, **tensor_args)
@@ -153,7 +162,10 @@ class MultiMPPrior:
         assert eps.shape == (S, P, M)
         x = out if out is not None else torch.empty(P, S, M, **self.tensor_args)
         eps = eps.contiguous()
-        if self.scale_tril_kron_tc is not None:
+        if self.kron_tc_kind == 2:
+            _lib.check(_lib.lib().mpb_sample_gp_kron_umma(_lib.ptr(self.scale_tril_kron_tc), _lib.ptr(self.means), _lib.ptr(eps),
+                                                          _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))
+        elif self.kron_tc_kind == 1:
             _lib.check(_lib.lib().mpb_sample_gp_kron_tc(_lib.ptr(self.scale_tril_kron_tc), _lib.ptr(self.means), _lib.ptr(eps),
                                                         _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))
         elif self.scale_tril_kron is not None:

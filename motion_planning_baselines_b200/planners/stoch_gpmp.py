@@ -172,7 +172,7 @@ class StochGPMP(OptimizationPlanner):
             if self._sample_dist.scale_tril_kron is not None:
                 _lib.check(lib.mpb_stoch_gpmp_iter_kron(
                     _lib.ptr(self._sample_dist.scale_tril_kron), _lib.ptr(self._sample_dist.scale_tril_kron_tc),
-                    _lib.ptr(self.Sigma_inv), int(self._sinv_structured), _lib.ptr(e),
+                    self._sample_dist.kron_tc_kind, _lib.ptr(self.Sigma_inv), int(self._sinv_structured), _lib.ptr(e),
                     _lib.ptr(self._particle_means), _lib.ptr(self.state_samples), _lib.ptr(self.costs), _lib.ptr(self._w_buf),
                     _lib.ptr(self._is_vec), _lib.ptr(self.free_flags), P, S, H,
                     C.byref(self.robot.desc), fields, nf, C.byref(gp), self.temperature, self.step_size, _lib.stream_ptr()))
@@ -213,7 +213,10 @@ class StochGPMP(OptimizationPlanner):
         rec = (lambda i: events[i].record()) if events is not None else (lambda i: None)
         rec(0)
         split = self._sample_dist.scale_tril_split
-        if self._sample_dist.scale_tril_kron_tc is not None:
+        if self._sample_dist.kron_tc_kind == 2:
+            _lib.check(lib.mpb_sample_gp_kron_umma(_lib.ptr(self._sample_dist.scale_tril_kron_tc), _lib.ptr(self._particle_means),
+                                                   _lib.ptr(eps), _lib.ptr(self.state_samples), P, S, H, self.n_dof, st))
+        elif self._sample_dist.kron_tc_kind == 1:
             _lib.check(lib.mpb_sample_gp_kron_tc(_lib.ptr(self._sample_dist.scale_tril_kron_tc), _lib.ptr(self._particle_means),
                                                  _lib.ptr(eps), _lib.ptr(self.state_samples), P, S, H, self.n_dof, st))
         elif self._sample_dist.scale_tril_kron is not None:

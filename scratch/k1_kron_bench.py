@@ -22,9 +22,11 @@ eps = [torch.randn(S, P, M, generator=gen, **dev) for _ in range(4)]
 x = torch.empty(P, S, M, **dev)
 LkF = torch.empty(lib.mpb_sample_gp_kron_tc_bytes(H, dof), device=dev['device'], dtype=torch.uint8)
 _lib.check(lib.mpb_sample_gp_kron_tc_prepare(_lib.ptr(LkT), _lib.ptr(LkF), H, dof, _lib.stream_ptr()))
-tc = os.environ.get('KRON', 'tc') == 'tc'
-fn = lib.mpb_sample_gp_kron_tc if tc else lib.mpb_sample_gp_kron
-Lop = LkF if tc else LkT
+mode = os.environ.get('KRON', 'tc')
+Lp = torch.empty(lib.mpb_sample_gp_kron_umma_floats(H, dof), **dev)
+_lib.check(lib.mpb_sample_gp_kron_umma_prepare(_lib.ptr(LkT), _lib.ptr(Lp), H, dof, _lib.stream_ptr()))
+fn = {'tc': lib.mpb_sample_gp_kron_tc, 'umma': lib.mpb_sample_gp_kron_umma}.get(mode, lib.mpb_sample_gp_kron)
+Lop = {'tc': LkF, 'umma': Lp}.get(mode, LkT)
 def run(i):
     _lib.check(fn(_lib.ptr(Lop), _lib.ptr(mu), _lib.ptr(eps[i % 4]), _lib.ptr(x), P, S, H, dof, _lib.stream_ptr()))
 for i in range(3): run(i)

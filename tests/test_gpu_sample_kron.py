@@ -117,9 +117,10 @@ def test_reference_prior_is_structured_and_sampler_matches(name, dev):
     eps = torch.randn(S, P, M, generator=gen, **dev)
     x_tc = prior.sample(S, eps=eps).reshape(P, S, M).clone()       # default: tensor-core variant
     assert prior.scale_tril_kron_tc is not None
-    tc_operand, prior.scale_tril_kron_tc = prior.scale_tril_kron_tc, None
+    kind, prior.kron_tc_kind = prior.kron_tc_kind, 0
+    assert kind == 2, 'the default sampler of a structured prior is the tcgen05 variant'
     x = prior.sample(S, eps=eps).reshape(P, S, M)                    # exact FP32 variant
-    prior.scale_tril_kron_tc = tc_operand
+    prior.kron_tc_kind = kind
     xd = torch.empty(P, S, M, **dev)
     _lib.check(_lib.lib().mpb_sample_gp(_lib.ptr(prior.scale_tril), _lib.ptr(prior.means), _lib.ptr(eps), _lib.ptr(xd),
                                         P, S, M, _lib.stream_ptr()))
@@ -215,3 +216,34 @@ def test_structured_prior_matvec_bit_identical(name, P, dev):
     bad[D + 1, 0] = 1.0          # (t=1, pos, j=1) x (t=0, pos, j=0): couples two dofs
     _lib.check(lib.mpb_prior_dof_structured(_lib.ptr(bad), H, dof, C.byref(ok), _lib.stream_ptr()))
     assert ok.value == 0
+
+
+@pytest.mark.parametrize('dof,H,P,S', [(2, 32, 3, 7), (2, 64, 1, 64), (2, 128, 5, 13), (3, 32, 4, 8), (3, 64, 7, 33), (3, 16, 9, 5),
+                                       (3, 128, 2, 31), (7, 32, 3, 11), (7, 64, 5, 13), (7, 64, 16, 64), (7, 64, 1, 1), (7, 64, 37, 23)])
+def test_kron_umma_matches_fp64(dof, H, P, S, dev):
+    """tcgen05 variant (3xTF32, per-dof M128xN32 MMA chains): within 5e-6 of the noise amplitude of an fp64 product, zero
+    noise returns the means exactly, rows past the ragged end are untouched."""
+    from motion_planning_baselines_b200 import _lib
+    lib = _lib.lib()
+    assert lib.mpb_sample_gp_kron_umma_supported(H, dof)
+    gen = torch.Generator(device='cuda').manual_seed(13 * dof + H + S)
+    M = 2 * H * dof
+    L = structured_factor(H, dof, gen, dev)
+    LkT, ok = pack(L, H, dof, dev)              # packing has no shape restriction
+    assert ok == 1
+    Lp = torch.empty(lib.mpb_sample_gp_kron_umma_floats(H, dof), **dev)
+    _lib.check(lib.mpb_sample_gp_kron_umma_prepare(_lib.ptr(LkT), _lib.ptr(Lp), H, dof, _lib.stream_ptr()))
+    mu = torch.randn(P, M, generator=gen, **dev)
+    eps = torch.randn(S, P, M, generator=gen, **dev)
+    x = torch.full((P * S + 3, M), float('nan'), **dev)
+    _lib.check(lib.mpb_sample_gp_kron_umma(_lib.ptr(Lp), _lib.ptr(mu), _lib.ptr(eps), _lib.ptr(x), P, S, H, dof, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.isnan(x[P * S:]).all(), 'wrote past the last row'
+    x = x[:P * S].view(P, S, M)
+    assert not torch.isnan(x).any()
+    noise = torch.einsum('ik,spk->psi', L.double(), eps.double())
+    err = (x.double() - (mu.double().unsqueeze(1) + noise)).abs().max()
+    assert float(err) <= 5e-6 * float(noise.abs().max()), (float(err), float(noise.abs().max()))
+    xz = torch.empty(P, S, M, **dev)
+    _lib.check(lib.mpb_sample_gp_kron_umma(_lib.ptr(Lp), _lib.ptr(mu), _lib.ptr(torch.zeros_like(eps)), _lib.ptr(xz), P, S, H, dof, _lib.stream_ptr()))
+    assert torch.equal(xz, mu.unsqueeze(1).expand(P, S, M))
