@@ -399,37 +399,39 @@ static bool make_map(CUtensorMap* map, const float* base, int rows, int cols, in
 // =====================================================================================================================
 // Structured tcgen05 sampler: the factor decouples over the dofs (see sample_gp_kron.cu), so  x = mu + L @ eps  is `dof`
 // independent [2H,2H] lower-triangular products.  Same warp-specialised pipeline as above; what changes:
-//   * an output tile is 8 waypoints = 16 outputs of each dof = 16*DOF contiguous columns of x; its accumulator holds the
-//     dofs side by side (TMEM column j*16 + i_local), one M128 x N16 MMA chain per dof; two accumulators (double
-//     buffered against the epilogue) leave 512 - 2*16*DOF columns for a DEEP A ring: every A slot feeds only six small
-//     MMAs, so the transform <-> MMA handshake latency (~1000 cycles per slot measured with a 2-slot ring) is hidden by
-//     ring depth, not by MMA work per slot as in the dense kernel;
+//   * an output tile is 16 waypoints = 32 outputs of each dof = 32*DOF contiguous columns of x; its accumulator holds the
+//     dofs side by side (TMEM column j*32 + i_local), one M128 x N32 MMA chain per dof.  ONE accumulator, and the other
+//     512 - 32*DOF columns are a deep A ring (>= DOF slots): a slot feeds only six small MMAs, and tcgen05.st + wait::st
+//     + the mbarrier handshake cost ~900 cycles per round trip, so the transform writes the slots of ALL dofs of a stage,
+//     waits once, and releases them together (measured: per-dof waits made a stage cost 6-7k cycles whatever N was);
 //   * a stage is one k-chunk of 8 waypoints = 16 k of every dof: DOF raw eps boxes [128 x 16] (the 16*DOF contiguous raw
-//     columns) + the packed factor tiles L_hi / L_lo [16*DOF x 16] of (output tile, k-chunk); triangular: output tile `to`
-//     needs the k-chunks 0 .. to only;
+//     columns) + the packed factor tiles L_hi / L_lo [32*DOF x 16] of (output tile, k-chunk); triangular: output tile `to`
+//     needs the k-chunks 0 .. 2*to+1 only;
 //   * the transform thread of a row reads its 16*DOF raw values once (conflict-free 128-bit loads), and per dof gathers
 //     the 16 values (raw column DOF*kk + j), splits them into hi | lo and writes them into the TMEM A ring -- the stride-DOF
 //     gather happens in registers, no shared-memory transpose;
-//   * the epilogue interleaves the dofs back (4 outputs x DOF dofs = 4*DOF contiguous floats of the row of x), stages the
-//     warp's 32 rows in shared memory, releases the accumulator, and writes the rows out COALESCED with mu_p added (a
-//     thread-per-row store touches 32 cache lines per instruction and made the epilogue the bottleneck).
+//   * the epilogue interleaves the dofs back (4 outputs x DOF dofs = 4*DOF contiguous floats of the row of x), stages a
+//     quarter of the columns of the warp's 32 rows in shared memory at a time and writes them out COALESCED with mu_p
+//     added (a thread-per-row store touches 32 cache lines per instruction and made the epilogue the bottleneck).
 template <int DOF>
 struct KtCfg {
-    static constexpr int OW = 16;                                // outputs of one dof per tile (UMMA N)
+    static constexpr int OW = 32;                                // outputs of one dof per tile (UMMA N)
     static constexpr int BN = OW * DOF;                          // accumulator columns per output tile
     static constexpr uint32_t EPS_BYTES = DOF * A_TILE_BYTES;    // DOF boxes [128 x 16] fp32
     static constexpr uint32_t L_BYTES = BN * TC_BK * 4;          // one packed factor tile
     static constexpr uint32_t STAGE = EPS_BYTES + 2 * L_BYTES;
     static constexpr int STAGES = 2;
-    static constexpr int ASLOTS = (512 - 2 * BN) / (2 * TC_BK) < 10 ? (512 - 2 * BN) / (2 * TC_BK) : 10;
-    static constexpr uint32_t A_COL0 = 2 * BN;
-    static constexpr int EPI_STRIDE = BN + 4;                    // floats per staged row (keeps 128-bit accesses conflict-free)
+    static constexpr int ASLOTS = (512 - BN) / (2 * TC_BK) < 12 ? (512 - BN) / (2 * TC_BK) : 12;
+    static constexpr uint32_t A_COL0 = BN;
+    static constexpr int EPI_PASSES = 4, EPI_COLS = BN / EPI_PASSES;   // columns staged per pass (2 groups of 4 outputs x DOF)
+    static constexpr int EPI_STRIDE = EPI_COLS + 4;              // floats per staged row (keeps 128-bit accesses conflict-free)
     static constexpr uint32_t EPI_WARP_BYTES = 32 * EPI_STRIDE * 4 + 32 * 16;     // staged rows + per-row (x offset, mu offset)
     static constexpr uint32_t BAR_BYTES = 512;
     static constexpr uint32_t SMEM = STAGES * STAGE + 4 * EPI_WARP_BYTES + 1024 + BAR_BYTES;
-    static_assert(2 * BN + ASLOTS * 2 * TC_BK <= 512 && ASLOTS >= 2, "tensor memory budget");
+    static_assert(BN + ASLOTS * 2 * TC_BK <= 512 && ASLOTS >= DOF, "tensor memory budget");
+    static_assert(EPI_COLS % (4 * DOF) == 0, "epilogue pass = whole groups of 4 outputs");
     static_assert(STAGE % 1024 == 0 && L_BYTES % 512 == 0, "swizzle atom alignment");
-    static_assert((2 * STAGES + 2 * ASLOTS + 4) * 8 + 4 <= BAR_BYTES, "barrier block too small");
+    static_assert((2 * STAGES + 2 * ASLOTS + 2) * 8 + 4 <= BAR_BYTES, "barrier block too small");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -437,7 +439,7 @@ struct KtArgs {
     const float* mu;
     float* x;
     int P, S, M, N;             // N = P*S rows
-    int n_row_tiles, n_to;      // n_to output tiles = k-chunks per dof (8 waypoints each)
+    int n_row_tiles, n_to, n_kc;   // output tiles (16 waypoints) and k-chunks (8 waypoints) per dof
 };
 
 __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&r)[4]) {
@@ -461,9 +463,9 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
     uint64_t* empty = bars + STAGES;                         // [STAGES] MMAs that read the stage completed
     uint64_t* a_full = bars + 2 * STAGES;                    // [ASLOTS] E_hi | E_lo of one dof written to tensor memory
     uint64_t* a_empty = a_full + ASLOTS;                     // [ASLOTS] MMAs that read the A slot completed
-    uint64_t* tmem_full = a_empty + ASLOTS;                  // [2] accumulator ready
-    uint64_t* tmem_empty = tmem_full + 2;                    // [2] accumulator drained
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* tmem_full = a_empty + ASLOTS;                  // accumulator ready
+    uint64_t* tmem_empty = tmem_full + 1;                    // accumulator drained
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -476,10 +478,8 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
             mbar_init(&a_full[s], 4);
             mbar_init(&a_empty[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 4);
-        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_base_slot, 512);
@@ -490,10 +490,12 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
 
     const int n_tiles = a.n_row_tiles * a.n_to;
     // tile t -> (output tile to, row tile r); output tiles are visited from the last (longest k range) first
-    auto tile_coords = [&](int t, int& r, int& to) {
-        const int jj = t / a.n_row_tiles;
-        r = t - jj * a.n_row_tiles;
-        to = a.n_to - 1 - jj;
+    // tile t -> (row tile r, output tile to).  The output tiles of one row tile are adjacent tiles, i.e. they run on adjacent
+    // CTAs at the same time and share their eps chunks through L2; the rotation by r gives every CTA all tile sizes.
+    auto tile_coords = [&](int t, int& r, int& to, int& n_kc) {
+        r = t / a.n_to;
+        to = (t + r) % a.n_to;
+        n_kc = 2 * to + 2;
     };
 
     if (warp == 0) {
@@ -502,16 +504,16 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                int r, to;
-                tile_coords(t, r, to);
-                for (int kc = 0; kc <= to; ++kc) {
+                int r, to, n_kc;
+                tile_coords(t, r, to, n_kc);
+                for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* st = tiles + stage * Cfg::STAGE;
                     mbar_expect_tx(&full[stage], Cfg::STAGE);
 #pragma unroll
                     for (int b = 0; b < DOF; ++b)
                         tma_load_2d(&map_eps, &full[stage], st + b * A_TILE_BYTES, (kc * DOF + b) * TC_BK, r * TC_BM);
-                    const int lrow = (to * a.n_to + kc) * BN;
+                    const int lrow = (to * a.n_kc + kc) * BN;
                     tma_load_2d(&map_lhi, &full[stage], st + Cfg::EPS_BYTES, 0, lrow);
                     tma_load_2d(&map_llo, &full[stage], st + Cfg::EPS_BYTES + Cfg::L_BYTES, 0, lrow);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -521,42 +523,58 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         if (lane == 0) {
-            int stage = 0, slot = 0, acc = 0;
+            int stage = 0, slot = 0;
             uint32_t phase = 0, slot_phase = 0, acc_phase = 0;
             constexpr uint32_t idesc = make_idesc_tf32(TC_BM, OW);
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                int r, to;
-                tile_coords(t, r, to);
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                int r, to, n_kc;
+                tile_coords(t, r, to, n_kc);
+                mbar_wait(tmem_empty, acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kc = 0; kc <= to; ++kc) {
+                const uint32_t d_tmem = tmem_base;
+                for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(&full[stage], phase);                // factor tiles landed
                     const uint32_t st = smem_u32(tiles + stage * Cfg::STAGE);
-#pragma unroll 1
-                    for (int j = 0; j < DOF; ++j) {
-                        mbar_wait(&a_full[slot], slot_phase);      // E_hi / E_lo of dof j in tensor memory
-                        tc_fence_after();
-                        const uint64_t b_hi = make_sw128_desc(st + Cfg::EPS_BYTES + j * OW * TC_SWIZZLE_BYTES);
-                        const uint64_t b_lo = make_sw128_desc(st + Cfg::EPS_BYTES + Cfg::L_BYTES + j * OW * TC_SWIZZLE_BYTES);
-                        const uint32_t a_hi = tmem_base + Cfg::A_COL0 + (uint32_t)(slot * 2 * TC_BK);
-                        const uint32_t a_lo = a_hi + TC_BK;
-                        const uint32_t dj = d_tmem + (uint32_t)(j * OW);
+                    // The six MMAs of one dof accumulate into the same 32 columns, i.e. they form a dependent chain through the
+                    // tensor pipe; consecutive MMAs therefore go to DIFFERENT dofs (independent accumulator columns).
+                    uint32_t a_hi[DOF];
+                    {
+                        int sl = slot;
+                        uint32_t ph = slot_phase;
 #pragma unroll
-                        for (int k = 0; k < TC_BK / 8; ++k) {
-                            const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);      // +32 B per k-step inside the swizzle row
-                            umma_tf32_ts(dj, a_lo + 8 * k, b_hi + koff, idesc, (kc | k) ? 1u : 0u);   // small terms first
-                            umma_tf32_ts(dj, a_hi + 8 * k, b_lo + koff, idesc, 1u);
-                            umma_tf32_ts(dj, a_hi + 8 * k, b_hi + koff, idesc, 1u);
+                        for (int j = 0; j < DOF; ++j) {
+                            mbar_wait(&a_full[sl], ph);            // E_hi / E_lo of dof j in tensor memory
+                            a_hi[j] = tmem_base + Cfg::A_COL0 + (uint32_t)(sl * 2 * TC_BK);
+                            if (++sl == ASLOTS) { sl = 0; ph ^= 1; }
                         }
+                    }
+                    tc_fence_after();
+                    const uint64_t b_hi0 = make_sw128_desc(st + Cfg::EPS_BYTES);
+                    const uint64_t b_lo0 = make_sw128_desc(st + Cfg::EPS_BYTES + Cfg::L_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);          // +32 B per k-step inside the swizzle row
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {                       // lo*hi, hi*lo, hi*hi (small terms first)
+#pragma unroll
+                            for (int j = 0; j < DOF; ++j) {
+                                const uint64_t joff = (uint64_t)((j * OW * TC_SWIZZLE_BYTES) >> 4);
+                                const uint32_t av = a_hi[j] + (term == 0 ? TC_BK : 0) + 8 * k;
+                                const uint64_t bv = (term == 1 ? b_lo0 : b_hi0) + joff + koff;
+                                umma_tf32_ts(d_tmem + (uint32_t)(j * OW), av, bv, idesc, (term == 0 && k == 0 && kc == 0) ? 0u : 1u);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < DOF; ++j) {
                         umma_commit(&a_empty[slot]);
                         if (++slot == ASLOTS) { slot = 0; slot_phase ^= 1; }
                     }
                     umma_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                umma_commit(tmem_full);
+                acc_phase ^= 1;
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -569,9 +587,9 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
         int stage = 0, slot = 0;
         uint32_t phase = 0, slot_phase = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            int r, to;
-            tile_coords(t, r, to);
-            for (int kc = 0; kc <= to; ++kc) {
+            int r, to, n_kc;
+            tile_coords(t, r, to, n_kc);
+            for (int kc = 0; kc < n_kc; ++kc) {
                 mbar_wait(&full[stage], phase);
                 const unsigned char* rowp = tiles + stage * Cfg::STAGE + row_off;
                 float raw[16 * DOF];                  // raw column c = DOF*kk + j  (kk = 2*waypoint + [pos|vel])
@@ -583,24 +601,40 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
                         raw[16 * b + 4 * c + 0] = v.x; raw[16 * b + 4 * c + 1] = v.y;
                         raw[16 * b + 4 * c + 2] = v.z; raw[16 * b + 4 * c + 3] = v.w;
                     }
+                // all DOF slots of this stage: wait for them, write them, ONE wait::st, release them together
+                {
+                    int sl = slot;
+                    uint32_t ph = slot_phase;
+#pragma unroll
+                    for (int j = 0; j < DOF; ++j) {
+                        mbar_wait(&a_empty[sl], ph ^ 1);
+                        if (++sl == ASLOTS) { sl = 0; ph ^= 1; }
+                    }
+                }
+                tc_fence_after();
+                {
+                    int sl = slot;
+#pragma unroll
+                    for (int j = 0; j < DOF; ++j) {
+                        float hi[16], lo[16];
+#pragma unroll
+                        for (int kk = 0; kk < 16; ++kk) {
+                            const float e = raw[DOF * kk + j];
+                            const float h = __uint_as_float(__float_as_uint(e) & 0xffffe000u);
+                            hi[kk] = h;
+                            lo[kk] = e - h;
+                        }
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0 + (uint32_t)(sl * 2 * TC_BK);
+                        tmem_st16(taddr, hi);
+                        tmem_st16(taddr + TC_BK, lo);
+                        if (++sl == ASLOTS) sl = 0;
+                    }
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
 #pragma unroll
                 for (int j = 0; j < DOF; ++j) {
-                    float hi[16], lo[16];
-#pragma unroll
-                    for (int kk = 0; kk < 16; ++kk) {
-                        const float e = raw[DOF * kk + j];
-                        const float h = __uint_as_float(__float_as_uint(e) & 0xffffe000u);
-                        hi[kk] = h;
-                        lo[kk] = e - h;
-                    }
-                    mbar_wait(&a_empty[slot], slot_phase ^ 1);
-                    tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0 + (uint32_t)(slot * 2 * TC_BK);
-                    tmem_st16(taddr, hi);
-                    tmem_st16(taddr + TC_BK, lo);
-                    tmem_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
                     if (lane == 0) mbar_arrive(&a_full[slot]);
                     if (++slot == ASLOTS) { slot = 0; slot_phase ^= 1; }
                 }
@@ -613,11 +647,10 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
         float* stg = reinterpret_cast<float*>(epi + q * Cfg::EPI_WARP_BYTES);                  // [32][EPI_STRIDE]
         long long* xoff = reinterpret_cast<long long*>(stg + 32 * Cfg::EPI_STRIDE);             // [32] float offset of the x row, -1 = none
         long long* moff = xoff + 32;                                                            // [32] float offset of the mu row
-        int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            int r, to;
-            tile_coords(t, r, to);
+            int r, to, n_kc;
+            tile_coords(t, r, to, n_kc);
             {
                 const int m = r * TC_BM + q * 32 + lane;            // row of eps: m = s*P + p
                 long long xo = -1, mo = 0;
@@ -629,44 +662,70 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
                 xoff[lane] = xo;
                 moff[lane] = mo;
             }
-            mbar_wait(&tmem_full[acc], acc_phase);
+            mbar_wait(tmem_full, acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int pass = 0; pass < Cfg::EPI_PASSES; ++pass) {
+                constexpr int GPP = Cfg::EPI_COLS / (4 * DOF);      // groups of 4 outputs per pass
 #pragma unroll
-            for (int g4 = 0; g4 < OW / 4; ++g4) {               // outputs i_local = 4*g4 .. 4*g4+3 of every dof
-                uint32_t v[DOF][4];
+                for (int gl = 0; gl < GPP; ++gl) {                  // outputs i_local = 4*g4 .. 4*g4+3 of every dof
+                    const int g4 = pass * GPP + gl;
+                    uint32_t v[DOF][4];
 #pragma unroll
-                for (int j = 0; j < DOF; ++j) tmem_ld4_nowait(taddr + (uint32_t)(j * OW + 4 * g4), v[j]);
-                tmem_wait_ld();
-                float o[4 * DOF];                                // x column DOF*i_local + j
+                    for (int j = 0; j < DOF; ++j) tmem_ld4_nowait(taddr + (uint32_t)(j * OW + 4 * g4), v[j]);
+                    tmem_wait_ld();
+                    float o[4 * DOF];                                // x column DOF*i_local + j
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
+                    for (int e = 0; e < 4; ++e)
 #pragma unroll
-                    for (int j = 0; j < DOF; ++j) o[DOF * e + j] = __uint_as_float(v[j][e]);
+                        for (int j = 0; j < DOF; ++j) o[DOF * e + j] = __uint_as_float(v[j][e]);
 #pragma unroll
-                for (int c = 0; c < DOF; ++c)
-                    *reinterpret_cast<float4*>(stg + lane * Cfg::EPI_STRIDE + 4 * DOF * g4 + 4 * c) =
-                        make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);       // accumulator drained: the next tile's MMAs may start
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            // coalesced write-out of the warp's 32 rows x BN columns (+ mu_p)
-            constexpr int V4 = BN / 4;
-#pragma unroll 4
-            for (int idx = lane; idx < 32 * V4; idx += 32) {
-                const int row = idx / V4, c4 = idx - row * V4;
-                const long long xo = xoff[row];
-                if (xo >= 0) {
-                    const float4 nz = *reinterpret_cast<const float4*>(stg + row * Cfg::EPI_STRIDE + 4 * c4);
-                    const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.mu + moff[row] + 4 * c4));
-                    float4 w;
-                    w.x = m4.x + nz.x; w.y = m4.y + nz.y; w.z = m4.z + nz.z; w.w = m4.w + nz.w;
-                    *reinterpret_cast<float4*>(a.x + xo + 4 * c4) = w;
+                    for (int c = 0; c < DOF; ++c)
+                        *reinterpret_cast<float4*>(stg + lane * Cfg::EPI_STRIDE + 4 * DOF * gl + 4 * c) =
+                            make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
                 }
+                if (pass == Cfg::EPI_PASSES - 1) {                   // accumulator drained: the next tile's MMAs may start
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
+                    acc_phase ^= 1;
+                } else {
+                    __syncwarp();
+                }
+                // coalesced write-out of the warp's 32 rows x EPI_COLS columns (+ mu_p)
+                constexpr int V4 = Cfg::EPI_COLS / 4;            // 32 * V4 float4 per pass = V4 per lane
+                constexpr int UB = (V4 % 7 == 0) ? 7 : (V4 % 4 == 0 ? 4 : 2);   // loads in flight per batch
+                static_assert(V4 % UB == 0, "write-out batch");
+#pragma unroll 1
+                for (int i0 = 0; i0 < V4; i0 += UB) {
+                    float4 m4[UB];
+                    long long xo[UB];
+                    int so[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {               // all global loads of the batch first: one latency per batch
+                        const int idx = (i0 + u) * 32 + lane;
+                        const int row = idx / V4, c4 = idx - row * V4;
+                        xo[u] = xoff[row];
+                        so[u] = row * Cfg::EPI_STRIDE + 4 * c4;
+                        m4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (xo[u] >= 0) {
+                            m4[u] = __ldg(reinterpret_cast<const float4*>(a.mu + moff[row] + pass * Cfg::EPI_COLS + 4 * c4));
+                            xo[u] += pass * Cfg::EPI_COLS + 4 * c4;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        if (xo[u] >= 0) {
+                            const float4 nz = *reinterpret_cast<const float4*>(stg + so[u]);
+                            float4 w;
+                            w.x = m4[u].x + nz.x; w.y = m4[u].y + nz.y; w.z = m4[u].z + nz.z; w.w = m4[u].w + nz.w;
+                            *reinterpret_cast<float4*>(a.x + xo[u]) = w;
+                        }
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
 
@@ -678,18 +737,18 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
     }
 }
 
-// Lp_hi / Lp_lo [n_to][n_to][16*dof][16]: row j*16 + il, column kk  <-  LkT[j][16*kc + kk][16*to + il]  split like split_tf32_kernel
+// Lp_hi / Lp_lo [n_to][n_kc][32*dof][16]: row j*32 + il, column kk  <-  LkT[j][16*kc + kk][32*to + il]  split like split_tf32_kernel
 __global__ void kron_umma_pack_kernel(const float* __restrict__ LkT, float* __restrict__ hi, float* __restrict__ lo, int H, int dof) {
-    const int N = 2 * H, n_to = N / 16;
-    const long long total = (long long)n_to * n_to * 16 * dof * 16;
+    const int N = 2 * H, n_to = N / 32, n_kc = N / 16;
+    const long long total = (long long)n_to * n_kc * 32 * dof * 16;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         long long r = idx;
         const int kk = (int)(r & 15); r >>= 4;
-        const int il = (int)(r & 15); r >>= 4;
+        const int il = (int)(r & 31); r >>= 5;
         const int j = (int)(r % dof); r /= dof;
-        const int kc = (int)(r % n_to);
-        const int to = (int)(r / n_to);
-        const float v = LkT[((size_t)j * N + 16 * kc + kk) * N + 16 * to + il];
+        const int kc = (int)(r % n_kc);
+        const int to = (int)(r / n_kc);
+        const float v = LkT[((size_t)j * N + 16 * kc + kk) * N + 32 * to + il];
         const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
         hi[idx] = h;
         lo[idx] = __uint_as_float(__float_as_uint(v - h) & 0xffffe000u);
@@ -700,17 +759,17 @@ template <int DOF>
 static int launch_kron_umma(const float* Lp_hi, const float* Lp_lo, const float* mu, const float* eps, float* x, int P, int S,
                             int H, cudaStream_t st) {
     using Cfg = KtCfg<DOF>;
-    const int N = P * S, M = 2 * H * DOF, n_to = 2 * H / 16;
+    const int N = P * S, M = 2 * H * DOF, n_to = 2 * H / 32, n_kc = 2 * H / 16;
     CUtensorMap m_eps, m_hi, m_lo;
-    if (!make_map(&m_eps, eps, N, M, TC_BM) || !make_map(&m_hi, Lp_hi, n_to * n_to * Cfg::BN, TC_BK, Cfg::BN) ||
-        !make_map(&m_lo, Lp_lo, n_to * n_to * Cfg::BN, TC_BK, Cfg::BN)) {
+    if (!make_map(&m_eps, eps, N, M, TC_BM) || !make_map(&m_hi, Lp_hi, n_to * n_kc * Cfg::BN, TC_BK, Cfg::BN) ||
+        !make_map(&m_lo, Lp_lo, n_to * n_kc * Cfg::BN, TC_BK, Cfg::BN)) {
         set_error("mpb_sample_gp_kron_umma: cuTensorMapEncodeTiled failed");
         return MPB_ECUDA;
     }
     KtArgs a;
     a.mu = mu; a.x = x; a.P = P; a.S = S; a.M = M; a.N = N;
     a.n_row_tiles = (N + TC_BM - 1) / TC_BM;
-    a.n_to = n_to;
+    a.n_to = n_to; a.n_kc = n_kc;
     cudaError_t e = cudaFuncSetAttribute(sample_gp_kron_umma_kernel<DOF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) { set_error("mpb_sample_gp_kron_umma: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
     const int n_tiles = a.n_row_tiles * n_to;
@@ -762,12 +821,11 @@ extern "C" int mpb_sample_gp_tc(const float* L_hi, const float* L_lo, const floa
 }
 
 extern "C" int mpb_sample_gp_kron_umma_supported(int H, int dof) {
-    return (dof == 2 || dof == 3 || dof == 7) && H >= 8 && H % 8 == 0 && H <= 256 && mpb::get_encode() != nullptr;
+    return (dof == 2 || dof == 3 || dof == 7) && H >= 16 && H % 16 == 0 && H <= 256 && mpb::get_encode() != nullptr;
 }
 
 extern "C" long long mpb_sample_gp_kron_umma_floats(int H, int dof) {
-    const long long n_to = 2 * H / 16;
-    return 2LL * n_to * n_to * 16 * dof * 16;      // L_hi then L_lo
+    return 2LL * (2 * H / 32) * (2 * H / 16) * 32 * dof * 16;      // L_hi then L_lo
 }
 
 extern "C" int mpb_sample_gp_kron_umma_prepare(const float* LkT, float* Lp, int H, int dof, void* stream) {

@@ -89,7 +89,7 @@ class MultiMPPrior:
         self.scale_tril = dist.MultivariateNormal(torch.zeros(self.M), precision_matrix=Sinv_cpu).scale_tril \
             .to(**tensor_args).contiguous()
         self.Sigma_inv = Sinv_cpu.to(**tensor_args).contiguous()
-        # Sampler selection (MPB_SAMPLE_GP = kron | kron_mma | kron_fp32 | tc | simt forces one; default: the first that applies).
+        # Sampler selection (MPB_SAMPLE_GP = kron | kron_umma | kron_fp32 | tc | simt forces one; default: the first that applies).
         #  kron: the factor decouples over the dofs (verified bit-exactly on the device) -> per-dof [2H,2H] blocks
         #  tc  : dense tcgen05 3xTF32 sampler; L pre-split into two TF32-representable parts
         #  simt: dense FP32 sampler
@@ -97,17 +97,18 @@ class MultiMPPrior:
         H = num_steps + 1
         self.scale_tril_kron = None
         self.scale_tril_kron_tc, self.kron_tc_kind = None, 0
-        if mode in ('auto', 'kron', 'kron_mma', 'kron_fp32') and state_dim == 2 * dof and _lib.lib().mpb_sample_gp_kron_supported(H, dof):
+        if mode in ('auto', 'kron', 'kron_umma', 'kron_fp32') and state_dim == 2 * dof and _lib.lib().mpb_sample_gp_kron_supported(H, dof):
             packed = torch.empty(dof, 2 * H, 2 * H, **tensor_args)
             ok = C.c_int(0)
             _lib.check(_lib.lib().mpb_sample_gp_kron_pack(_lib.ptr(self.scale_tril), _lib.ptr(packed), H, dof,
                                                           C.byref(ok), _lib.stream_ptr()))
             if ok.value:
                 self.scale_tril_kron = packed
-                # tensor-core operand: tcgen05 tiles ('kron', default) or warp-MMA fp16 fragments ('kron_mma');
-                # 'kron_fp32' keeps the exact FP32 kernel
+                # tensor-core operand: warp-MMA fp16 fragments ('kron', default: fastest measured, 0.107 ms at C4) or
+                # tcgen05 tiles ('kron_umma': 0.173 ms, bound by the MMA-issue / TMEM-store handshakes of its many
+                # small N=32 MMAs); 'kron_fp32' keeps the exact FP32 kernel
                 lib = _lib.lib()
-                if mode in ('auto', 'kron') and lib.mpb_sample_gp_kron_umma_supported(H, dof):
+                if mode == 'kron_umma' and lib.mpb_sample_gp_kron_umma_supported(H, dof):
                     self.scale_tril_kron_tc = torch.empty(lib.mpb_sample_gp_kron_umma_floats(H, dof), **tensor_args)
                     _lib.check(lib.mpb_sample_gp_kron_umma_prepare(_lib.ptr(packed), _lib.ptr(self.scale_tril_kron_tc),
                                                                    H, dof, _lib.stream_ptr()))

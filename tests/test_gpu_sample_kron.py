@@ -118,7 +118,7 @@ def test_reference_prior_is_structured_and_sampler_matches(name, dev):
     x_tc = prior.sample(S, eps=eps).reshape(P, S, M).clone()       # default: tensor-core variant
     assert prior.scale_tril_kron_tc is not None
     kind, prior.kron_tc_kind = prior.kron_tc_kind, 0
-    assert kind == 2, 'the default sampler of a structured prior is the tcgen05 variant'
+    assert kind == 1, 'the default sampler of a structured prior is the warp-MMA tensor-core variant'
     x = prior.sample(S, eps=eps).reshape(P, S, M)                    # exact FP32 variant
     prior.kron_tc_kind = kind
     xd = torch.empty(P, S, M, **dev)
