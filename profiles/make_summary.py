@@ -17,7 +17,10 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__cycles_elapsed.avg.per_second', 'smsp__thread_inst_executed_per_inst_executed.ratio']
 STALL = 'smsp__average_warps_issue_stalled_'
-ALGO = {'cost_eval': 32768 * 3584 + 512 * 3584, 'sample_gp_tc': 32768 * 3584 * 2 + 2 * 896 * 896 * 4, 'softmax_update': 32768 * 3584}
+ALGO = {'cost_eval': 32768 * 3584 + 512 * 3584, 'sample_gp_tc': 32768 * 3584 * 2 + 2 * 896 * 896 * 4, 'softmax_update': 32768 * 3584,
+        'sample_gp_kron_mma': 32768 * 3584 * 2 + 7 * 128 * 128 * 4 + 512 * 3584,
+        'sample_gp_kron_umma': 32768 * 3584 * 2 + 2 * 4 * 8 * 224 * 16 * 4 + 512 * 3584,
+        'prior_matvec_dof': 2 * 512 * 3584 + 7 * 896 * 4}
 
 
 def main():
@@ -48,7 +51,12 @@ def main():
             pass
     open(out, 'w').write('\n'.join(lines) + '\n')
     if len(sys.argv) > 3:
-        json.dump(traffic, open(sys.argv[3], 'w'), indent=1)
+        try:
+            old = json.load(open(sys.argv[3]))
+        except Exception:
+            old = {}
+        old.update(traffic)
+        json.dump(old, open(sys.argv[3], 'w'), indent=1)
     print('\n'.join(lines[:4]))
 
 
