@@ -24,6 +24,8 @@
 // accumulator full/empty (MMA <-> epilogue).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "mpb_common.cuh"
 
 namespace mpb {
@@ -440,6 +442,7 @@ struct KtArgs {
     float* x;
     int P, S, M, N;             // N = P*S rows
     int n_row_tiles, n_to, n_kc;   // output tiles (16 waypoints) and k-chunks (8 waypoints) per dof
+    int dbg;                       // MPB_KRON_UMMA_DBG bit mask (timing experiments only): 1 no MMA, 2 no tcgen05.st, 4 no write-out
 };
 
 __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&r)[4]) {
@@ -561,7 +564,7 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
                                 const uint64_t joff = (uint64_t)((j * OW * TC_SWIZZLE_BYTES) >> 4);
                                 const uint32_t av = a_hi[j] + (term == 0 ? TC_BK : 0) + 8 * k;
                                 const uint64_t bv = (term == 1 ? b_lo0 : b_hi0) + joff + koff;
-                                umma_tf32_ts(d_tmem + (uint32_t)(j * OW), av, bv, idesc, (term == 0 && k == 0 && kc == 0) ? 0u : 1u);
+                                if (!(a.dbg & 1)) umma_tf32_ts(d_tmem + (uint32_t)(j * OW), av, bv, idesc, (term == 0 && k == 0 && kc == 0) ? 0u : 1u);
                             }
                         }
                     }
@@ -625,8 +628,10 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
                             lo[kk] = e - h;
                         }
                         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A_COL0 + (uint32_t)(sl * 2 * TC_BK);
-                        tmem_st16(taddr, hi);
-                        tmem_st16(taddr + TC_BK, lo);
+                        if (!(a.dbg & 2)) {
+                            tmem_st16(taddr, hi);
+                            tmem_st16(taddr + TC_BK, lo);
+                        }
                         if (++sl == ASLOTS) sl = 0;
                     }
                 }
@@ -698,7 +703,7 @@ sample_gp_kron_umma_kernel(const __grid_constant__ CUtensorMap map_eps, const __
                 constexpr int UB = (V4 % 7 == 0) ? 7 : (V4 % 4 == 0 ? 4 : 2);   // loads in flight per batch
                 static_assert(V4 % UB == 0, "write-out batch");
 #pragma unroll 1
-                for (int i0 = 0; i0 < V4; i0 += UB) {
+                for (int i0 = (a.dbg & 4) ? V4 : 0; i0 < V4; i0 += UB) {
                     float4 m4[UB];
                     long long xo[UB];
                     int so[UB];
@@ -770,6 +775,7 @@ static int launch_kron_umma(const float* Lp_hi, const float* Lp_lo, const float*
     a.mu = mu; a.x = x; a.P = P; a.S = S; a.M = M; a.N = N;
     a.n_row_tiles = (N + TC_BM - 1) / TC_BM;
     a.n_to = n_to; a.n_kc = n_kc;
+    { const char* v = getenv("MPB_KRON_UMMA_DBG"); a.dbg = v ? atoi(v) : 0; }
     cudaError_t e = cudaFuncSetAttribute(sample_gp_kron_umma_kernel<DOF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) { set_error("mpb_sample_gp_kron_umma: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
     const int n_tiles = a.n_row_tiles * n_to;
