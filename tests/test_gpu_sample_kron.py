@@ -247,3 +247,71 @@ def test_kron_umma_matches_fp64(dof, H, P, S, dev):
     xz = torch.empty(P, S, M, **dev)
     _lib.check(lib.mpb_sample_gp_kron_umma(_lib.ptr(Lp), _lib.ptr(mu), _lib.ptr(torch.zeros_like(eps)), _lib.ptr(xz), P, S, H, dof, _lib.stream_ptr()))
     assert torch.equal(xz, mu.unsqueeze(1).expand(P, S, M))
+
+
+def test_structured_entry_points_reject_bad_arguments(dev):
+    """Error behaviour at the C boundary: unsupported shapes, null / misaligned pointers -> MPB_EINVAL with a message;
+    empty batches are a no-op."""
+    from motion_planning_baselines_b200 import _lib
+    lib = _lib.lib()
+    assert lib.mpb_sample_gp_kron_supported(64, 7) == 1 and lib.mpb_sample_gp_kron_supported(48, 7) == 0
+    assert lib.mpb_sample_gp_kron_supported(64, 5) == 0 and lib.mpb_sample_gp_kron_umma_supported(24, 7) == 0
+    H, dof, P, S = 64, 7, 2, 4
+    M = 2 * H * dof
+    buf = torch.zeros(dof * 4 * H * H + 64, **dev)
+    mu, eps, x = torch.zeros(P, M, **dev), torch.zeros(S, P, M, **dev), torch.full((P, S, M), 7.0, **dev)
+    st = _lib.stream_ptr()
+    for fn in (lib.mpb_sample_gp_kron, lib.mpb_sample_gp_kron_tc, lib.mpb_sample_gp_kron_umma):
+        assert fn(_lib.ptr(buf), _lib.ptr(mu), _lib.ptr(eps), _lib.ptr(x), P, S, 40, dof, st) != 0        # unsupported H
+        assert b'H=40' in lib.mpb_last_error()
+        assert fn(None, _lib.ptr(mu), _lib.ptr(eps), _lib.ptr(x), P, S, H, dof, st) != 0                  # null factor
+        assert fn(_lib.ptr(buf), _lib.ptr(mu), _lib.ptr(eps), _lib.ptr(x), -1, S, H, dof, st) != 0        # negative size
+        assert fn(_lib.ptr(buf), _lib.ptr(mu), eps.data_ptr() + 4, _lib.ptr(x), P, S, H, dof, st) != 0    # misaligned eps
+        assert fn(_lib.ptr(buf), _lib.ptr(mu), _lib.ptr(eps), _lib.ptr(x), 0, S, H, dof, st) == 0         # empty batch
+    torch.cuda.synchronize()
+    assert bool((x == 7.0).all()), 'a rejected or empty call must not write'
+    ok = C.c_int(5)
+    assert lib.mpb_sample_gp_kron_pack(None, _lib.ptr(buf), H, dof, C.byref(ok), st) != 0
+    assert lib.mpb_prior_dof_structured(None, H, dof, C.byref(ok), st) != 0
+    assert lib.mpb_prior_matvec_dof(_lib.ptr(buf), _lib.ptr(mu), None, P, H, dof, st) != 0
+    assert lib.mpb_sample_gp_kron_tc_prepare(_lib.ptr(buf), _lib.ptr(buf), 40, dof, st) != 0
+    assert lib.mpb_sample_gp_kron_umma_prepare(_lib.ptr(buf), _lib.ptr(buf), 24, dof, st) != 0
+
+
+def test_planner_samplers_agree(dev, monkeypatch):
+    """StochGPMP at a C4-like shape: one iteration with the default (warp-MMA), the exact-FP32, the tcgen05 and the dense
+    samplers on identical injected noise gives the same costs (1e-5) and the same argmin sample per particle."""
+    from motion_planning_baselines_b200.fields import CollisionField
+    from motion_planning_baselines_b200.planners import StochGPMP
+    from motion_planning_baselines_b200.robots import Robot
+    cfg = configs.config('C4')
+    P, S, H = 8, 32, 64
+    gen = torch.Generator(device='cuda').manual_seed(77)
+    eps = torch.randn(S, P, H * 14, generator=gen, **dev)
+    out = {}
+    for mode in ('simt', 'kron', 'kron_fp32', 'kron_umma'):
+        monkeypatch.setenv('MPB_SAMPLE_GP', mode)
+        torch.manual_seed(5)
+        robot = Robot(cfg['robot'], dt=cfg['dt'], tensor_args=dev)
+        field = CollisionField(cfg['obstacles'], tensor_args=dev)
+        planner = StochGPMP(robot=robot, n_dof=7, n_support_points=H, num_particles_per_goal=P, opt_iters=1, dt=cfg['dt'],
+                            start_state=torch.tensor(cfg['start']).to(**dev),
+                            multi_goal_states=torch.tensor(cfg['goal']).to(**dev).unsqueeze(0),
+                            collision_fields=[field], tensor_args=dev, num_samples=S, **cfg['params'])
+        kinds = dict(kron=1, kron_fp32=0, kron_umma=2, simt=0)
+        assert planner._sample_dist.kron_tc_kind == kinds[mode]
+        assert (planner._sample_dist.scale_tril_kron is not None) == (mode != 'simt')
+        if mode == 'simt':
+            means0 = planner._particle_means.clone()
+        else:
+            planner._particle_means.copy_(means0)
+        traj = planner.optimize(opt_iters=1, eps=[eps])
+        out[mode] = (planner.costs.clone(), traj.clone(), planner.state_samples.clone())
+    ref_c, ref_t, ref_x = out['simt']
+    for mode in ('kron', 'kron_fp32', 'kron_umma'):
+        c, t, xs = out[mode]
+        assert float((xs - ref_x).abs().max()) <= 2e-6, mode
+        assert float(((c - ref_c).abs() / ref_c.abs().clamp_min(1e-6)).max()) <= 1e-5, mode
+        assert torch.equal(c.argmin(1), ref_c.argmin(1)), mode
+        assert float((t - ref_t).abs().max()) <= 1e-5 * float(ref_t.abs().max()), mode
+    assert torch.equal(out['kron_fp32'][2], ref_x), 'the exact-FP32 structured sampler is bit-identical to the dense FP32 one'
