@@ -331,12 +331,16 @@ def main():
     # (optimize() takes no noise argument in the reference); per step the problem -- the initial particle trajectories --
     # comes from pinned host memory and the optimised trajectories go back to it
     h_means = means0.cpu().pin_memory()
+
+    def dev_noise_steps(n):
+        for _ in range(n):
+            planner._particle_means.copy_(h_means, non_blocking=True)
+            traj = planner.optimize(opt_iters=1)
+            h_traj.copy_(traj, non_blocking=True)
+    dev_noise_steps(3)
     barrier()
     e0.record()
-    for i in range(Ke):
-        planner._particle_means.copy_(h_means, non_blocking=True)
-        traj = planner.optimize(opt_iters=1)
-        h_traj.copy_(traj, non_blocking=True)
+    dev_noise_steps(Ke)
     e1.record()
     barrier()
     ms_e2e_dev = e0.elapsed_time(e1)
