@@ -51,3 +51,23 @@ for j in range(7):
     active_pairs_lane += n * act.float().mean().item() * oc.shape[0]
     print(f'link {j}: n={n} R~{br.mean():.3f} active obstacles/warp {act_w.float().sum(-1).mean():.2f} of {oc.shape[0]} (per lane {act.float().sum(-1).mean():.2f})')
 print('total pairs', tot_pairs, 'after warp-level link culling', active_pairs_warp, 'per-lane', active_pairs_lane)
+
+# --- emulate the kernel's warp AABB broad phase (collision.cuh broad_phase) -----------------------------------------
+print('\nAABB broad phase as in the kernel (per warp = 32 consecutive waypoints):')
+tot_aabb = 0
+for j in range(7):
+    idx = (link == j).nonzero().flatten()
+    c = centers[:, :, idx]
+    bc = c.mean(2)                                           # stand-in for the link bounding-sphere centre
+    br = ((c - bc.unsqueeze(2)).norm(dim=-1) + rad[idx]).max(-1).values
+    Rm = br.max() + margin
+    bcw = bc.reshape(B, H // 32, 32, 3)
+    lo, hi = bcw.min(2).values, bcw.max(2).values            # [B,2,3]
+    dlo = (lo.unsqueeze(-2) - oc).clamp_min(0)               # [B,2,No,3]
+    dhi = (oc - hi.unsqueeze(-2)).clamp_min(0)
+    dd = torch.maximum(dlo, dhi).norm(dim=-1)
+    near = dd < (Rm + orad)
+    n_ls = near.float().sum(-1)
+    tot_aabb += len(idx) * n_ls.mean().item()
+    print(f'link {j}: n={len(idx)} AABB extent {float((hi - lo).mean()):.3f}  n_ls mean {n_ls.mean():.2f} max {int(n_ls.max())}  (links with empty list: {float((n_ls == 0).float().mean()):.2f})')
+print('sphere x obstacle pairs per waypoint after the AABB broad phase:', tot_aabb, ' vs exact per-warp bounding-sphere test', active_pairs_warp)
