@@ -380,6 +380,9 @@ def main():
         elif flops[j]:
             a = flops[j] * n_samp / (stage_ms[j] * 1e-3) / 1e12
             k.update(bound='fp32', achieved=a, peak=fp32_peak, unit='TFLOP/s', frac=a / fp32_peak)
+            if j == 2:      # the same kernel against the HBM roofline (it reads every sample row once): far from memory bound
+                gbs = M * 4 * n_samp / (stage_ms[j] * 1e-3) / 1e9
+                k.update(hbm_gbs=gbs, hbm_frac=gbs / pk['hbm'], hbm_peak=pk['hbm'], hbm_peak_source=pk['source'])
             if j == 0 and 'kron' in nm:
                 gbs = 2 * M * 4 * n_samp / (stage_ms[j] * 1e-3) / 1e9
                 k.update(hbm_gbs=gbs, hbm_frac=gbs / pk['hbm'],
@@ -396,7 +399,9 @@ def main():
                     traffic=ncu_traffic(dom['kernel']), kernel=dom['kernel'], ms_per_launch=dom['ms'],
                     peak_source=('nominal FP32 FMA rate 148 SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json holds only '
                                  'HBM and bf16 tensor peaks; this kernel is FP32-issue bound)') if dom['bound'] == 'fp32' else dom.get('note', pk['source']),
-                    algorithmic_flop_per_sample=flops[2] if 'K2' in dom['kernel'] else flops[0], kernels=kernels)
+                    algorithmic_flop_per_sample=flops[2] if 'K2' in dom['kernel'] else flops[0],
+                    hbm_view=dict(achieved=dom.get('hbm_gbs'), peak=pk['hbm'], unit='GB/s', frac=dom.get('hbm_frac'), peak_source=pk['source'],
+                                  algorithmic_bytes_per_sample=M * 4), kernels=kernels)
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
