@@ -232,7 +232,8 @@ struct KronMmaCfg {
     static constexpr int STAGES = 3;                               // factor-chunk ring: two chunks in flight
     static constexpr int WPD = NB / 2 / PPW;                       // warps per dof
     static constexpr int WARPS = DOF * WPD, THREADS = WARPS * 32;
-    static constexpr int CTAS_PER_SM = 1;
+    // resident CTAs the register file allows at 72 registers per thread (1 for the Panda's 896 threads, 2-4 for small robots)
+    static constexpr int CTAS_PER_SM = 65536 / (72 * THREADS) < 1 ? 1 : (65536 / (72 * THREADS) > 4 ? 4 : 65536 / (72 * THREADS));
     static constexpr int RS = M + 4;                               // padded row stride in floats
     static constexpr int TILE_FLOATS = ROWS * RS;
     static constexpr int V4_PER_ROW = M / 4;
