@@ -17,7 +17,11 @@
 // for every a); lanes = 4 row quads x 8 sample quads, 4x4 register tile.  The factor block streams through a per-warp
 // double-buffered cp.async ring (16 k x 16 rows per chunk), no CTA barrier inside the contraction.  Results go back
 // into the tile in place; the store phase adds mu_p and writes full 32-byte sectors; the next tile's rows are already
-// in flight in registers while the current tile is stored.  Bound: FP32 FMA issue (16 FFMA per 2 LDS.128).
+// in flight in registers while the current tile is stored.  Measured bound: the shared-memory data pipe, not FMA issue --
+// a 128-bit shared load is served per quarter-warp (4 wavefronts when the 8 lanes of a quarter read different addresses,
+// 2 when they read one), i.e. 6 wavefronts per 16 FFMA: 0.210 ms at C4.  This kernel is the exact-FP32 parity anchor of
+// the structured path (bit-identical to sample_gp_simt_kernel); the default is the tensor-core variant further down
+// (sample_gp_kron_mma_kernel, 0.107 ms), and sample_gp_tc.cu holds a tcgen05 variant (sample_gp_kron_umma_kernel).
 #include <cuda_fp16.h>
 
 #include "mpb_common.cuh"
