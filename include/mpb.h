@@ -7,9 +7,14 @@
  *     mpb_last_error() returns a thread-local message for the last failure.
  *   - all data pointers are DEVICE pointers on the current CUDA device unless
  *     the parameter name ends in _host; descriptor structs themselves live on the host.
- *   - fp32, row-major, contiguous.  The caller owns every buffer; the library
- *     allocates nothing persistent and keeps no global state (stream-ordered,
- *     re-entrant: one planner <-> one stream).
+ *   - fp32, row-major, contiguous.  The caller owns every data buffer.  The only
+ *     state the library keeps is one 512-byte pool of work-scheduler counters per
+ *     device (64 slots x 2 words, handed out round-robin to the persistent cost
+ *     kernel and re-armed by the kernel itself): created by mpb_init() -- or lazily
+ *     by the first launch, which is NOT capturable into a CUDA graph -- so call
+ *     mpb_init() once per device before capturing, and keep fewer than 64 cost
+ *     launches in flight concurrently per device.  Everything else is stream-ordered
+ *     and re-entrant (one planner <-> one stream).
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
  *
  * Symbols used below: P particles, S samples per particle, H waypoints, d dof,
@@ -111,6 +116,10 @@ typedef struct mpb_extra_cost_desc {
 
 const char* mpb_last_error(void);
 int mpb_version(void);
+/* Allocates and zeroes the work-scheduler slots of the CURRENT device (see "Conventions"; no counterpart in the
+ * reference, which has no native state).  Idempotent, synchronous, not capturable.  Also the recovery call after a
+ * failed launch: it re-arms every slot. */
+int mpb_init(void);
 /* sizeof(mpb_robot_desc | mpb_field_desc | mpb_gp_desc | mpb_extra_cost_desc) for which = 0 | 1 | 2 | 3: lets a foreign-language binding
  * verify its struct layout before the first call. */
 int mpb_sizeof_desc(int which);

@@ -54,6 +54,7 @@ _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 _SIGNATURES = {
     'mpb_last_error': (C.c_char_p, []),
     'mpb_version': (C.c_int, []),
+    'mpb_init': (C.c_int, []),
     'mpb_sizeof_desc': (C.c_int, [_i]),
     'mpb_sample_gp': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'mpb_split_tf32': (C.c_int, [_vp, _vp, _vp, C.c_longlong, _vp]),
@@ -115,6 +116,63 @@ def exported_symbols():
     return sorted(_SIGNATURES)
 
 
+class _StreamOfCall:
+    """Placeholder returned by stream_ptr(): resolved by the call wrapper to the CURRENT stream of the device the
+    call's tensors live on (not of whatever device happens to be current)."""
+
+
+_STREAM = _StreamOfCall()
+
+
+class DevPtr(C.c_void_p):
+    """c_void_p that remembers which CUDA device the tensor lives on (checked by the call wrapper)."""
+    mpb_device = None
+
+
+class _Fn:
+    """One C-ABI entry point.  Every tensor argument of a call must live on ONE device; the call runs with that
+    device current and on that device's current stream -- the library itself sizes grids and takes its scheduler
+    slot from cudaGetDevice() -- so a planner built on cuda:1 works while cuda:0 is current, as torch ops would."""
+    __slots__ = ('fn', 'name')
+
+    def __init__(self, fn, name):
+        self.fn, self.name = fn, name
+
+    def __call__(self, *args):
+        dev = None
+        has_stream = False
+        for a in args:
+            if a is _STREAM:
+                has_stream = True
+                continue
+            d = getattr(a, 'mpb_device', None)
+            if d is None:
+                continue
+            if dev is None:
+                dev = d
+            elif d != dev:
+                raise MpbError(f'{self.name}: tensors of one call live on different devices (cuda:{dev} and cuda:{d})')
+        if dev is None:
+            dev = torch.cuda.current_device() if has_stream else None
+        if has_stream:
+            sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            args = tuple(sp if a is _STREAM else a for a in args)
+        if dev is None or dev == torch.cuda.current_device():
+            return self.fn(*args)
+        with torch.cuda.device(dev):
+            return self.fn(*args)
+
+
+class _Lib:
+    def __init__(self, handle):
+        self._handle = handle
+
+    def __getattr__(self, name):
+        fn = _Fn(getattr(self._handle, name), name)
+        setattr(self, name, fn)
+        return fn
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -129,8 +187,23 @@ def lib():
             if handle.mpb_sizeof_desc(which) != C.sizeof(struct):
                 raise MpbError(f'{struct.__name__}: ctypes layout ({C.sizeof(struct)} B) differs from the library '
                                f'({handle.mpb_sizeof_desc(which)} B); rebuild with ./build.sh')
-        _lib = handle
+        _lib = _Lib(handle)
     return _lib
+
+
+_inited = set()
+
+
+def init_device(device):
+    """mpb_init() once per device (scheduler slots; must not happen lazily inside a CUDA-graph capture)."""
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx in _inited:
+        return
+    with torch.cuda.device(idx):
+        check(lib().mpb_init())
+    _inited.add(idx)
 
 
 def check(rc):
@@ -146,11 +219,14 @@ def ptr(t):
         raise MpbError('expected a CUDA tensor: the hot path has no CPU implementation')
     if not t.is_contiguous():
         raise MpbError('expected a contiguous tensor')
-    return C.c_void_p(t.data_ptr())
+    p = DevPtr(t.data_ptr())
+    p.mpb_device = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    return p
 
 
 def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The stream argument of a C-ABI call: the current stream of the device the call's tensors live on."""
+    return _STREAM
 
 
 def require_f32(*tensors):

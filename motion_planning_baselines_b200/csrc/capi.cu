@@ -39,29 +39,49 @@ int sm_count() {
     return cached;
 }
 
-unsigned* sched_slot() {
-    constexpr int kMaxDev = 64, kSlots = 64;
-    static std::mutex mtx;
-    static unsigned* pool[kMaxDev] = {};
-    static std::atomic<unsigned> seq{0};
+// Per-device pool of scheduler slots (the library's only persistent allocation: 64 x 8 bytes per device).
+namespace {
+constexpr int kMaxDev = 64, kSlots = 64;
+std::mutex g_pool_mtx;
+unsigned* g_pool[kMaxDev] = {};
+std::atomic<unsigned> g_slot_seq{0};
+
+// Allocates (first call per device) and zeroes the pool of the current device.  Not capturable: call mpb_init()
+// before capturing a CUDA graph that contains mpb_cost_eval.
+unsigned* pool_of_current_device(bool rezero) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
-    {
-        std::lock_guard<std::mutex> lk(mtx);
-        if (!pool[dev]) {
-            unsigned* p = nullptr;
-            if (cudaMalloc(&p, kSlots * 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
-            if (cudaMemset(p, 0, kSlots * 2 * sizeof(unsigned)) != cudaSuccess) { cudaFree(p); return nullptr; }
-            pool[dev] = p;
-        }
+    std::lock_guard<std::mutex> lk(g_pool_mtx);
+    if (!g_pool[dev]) {
+        unsigned* p = nullptr;
+        if (cudaMalloc(&p, kSlots * 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
+        if (cudaMemset(p, 0, kSlots * 2 * sizeof(unsigned)) != cudaSuccess) { cudaFree(p); return nullptr; }
+        g_pool[dev] = p;
+    } else if (rezero) {
+        if (cudaMemset(g_pool[dev], 0, kSlots * 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
     }
-    return pool[dev] + 2 * (seq.fetch_add(1u) % kSlots);
+    return g_pool[dev];
 }
+}  // namespace
+
+unsigned* sched_slot() {
+    unsigned* pool = pool_of_current_device(false);
+    return pool ? pool + 2 * (g_slot_seq.fetch_add(1u) % kSlots) : nullptr;
+}
+
+int init_current_device() { return pool_of_current_device(true) ? MPB_OK : MPB_ECUDA; }
 
 }  // namespace mpb
 
 extern "C" const char* mpb_last_error(void) { return mpb::g_err; }
-extern "C" int mpb_version(void) { return 101; }
+extern "C" int mpb_version(void) { return 200; }
+extern "C" int mpb_init(void) {
+    if (mpb::init_current_device() != MPB_OK) {
+        mpb::set_error("mpb_init: could not allocate / zero the scheduler slots of the current device");
+        return MPB_ECUDA;
+    }
+    return MPB_OK;
+}
 extern "C" int mpb_sizeof_desc(int which) {
     switch (which) {
         case 0: return (int)sizeof(mpb_robot_desc);

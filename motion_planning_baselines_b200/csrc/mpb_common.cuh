@@ -14,9 +14,11 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);     // cudaGetLastError() -> MPB_OK / MPB_ECUDA
 int sm_count();                         // SMs of the current device (cached per device)
 // Two zero-initialised device words for a self-resetting dynamic work counter (next index, finished CTAs).  Slots come
-// from a small per-device pool owned by the library (the only memory it ever allocates: 64 x 8 bytes per device) and
-// are handed out round-robin, so up to 64 launches may be in flight concurrently on different streams.
+// from a small per-device pool owned by the library (the only memory it ever allocates: 64 x 8 bytes per device,
+// created by mpb_init() or lazily by the first launch) and are handed out round-robin, so up to 64 launches may be in
+// flight concurrently on different streams of one device.  The last CTA of a launch re-arms its slot.
 unsigned* sched_slot();
+int init_current_device();              // allocate + zero the pool of the current device (mpb_init)
 
 #define MPB_REQUIRE(cond, ...)                       \
     do {                                             \

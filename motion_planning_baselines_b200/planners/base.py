@@ -14,6 +14,7 @@ class MPPlanner:
         if tensor_args.get('dtype', torch.float32) != torch.float32:
             raise _lib.MpbError('the fused hot path computes in float32')
         self.tensor_args = dict(device=torch.device(tensor_args['device']), dtype=torch.float32)
+        _lib.init_device(self.tensor_args['device'])
         self._kwargs = kwargs
 
     def optimize(self, opt_iters=1, **observation):

@@ -12,10 +12,12 @@ import torch
 from .. import _lib
 from ..costs import build_gpmp2_cost_composite
 from ..factors import GPFactor, MultiMPPrior, UnaryFactor
+from ..update import split_softmax_update
 from .base import OptimizationPlanner
 
 
 class StochGPMP(OptimizationPlanner):
+    SPLIT_THRESHOLD = 4096      # samples per particle above which the update is split over several CTAs (as STOMP)
 
     def __init__(self, robot=None, n_dof=None, n_support_points=None, num_particles_per_goal=None, opt_iters=None,
                  dt=None, start_state=None, step_size=1., multi_goal_states=None, initial_particle_means=None,
@@ -39,6 +41,7 @@ class StochGPMP(OptimizationPlanner):
         self._mean = None
         self._weights = None
         self._sample_dist = None
+        self._recent_state_particles = self._recent_control_particles = None
         self.costs = None
         self.free_flags = None
 
@@ -140,8 +143,14 @@ class StochGPMP(OptimizationPlanner):
 
     def _update_distribution(self, costs, traj_samples):
         P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
-        grad = torch.empty(P, H, D, **self.tensor_args)
         costs, traj_samples = costs.contiguous(), traj_samples.contiguous()         # named: temporaries must outlive the launch
+        if S > self.SPLIT_THRESHOLD:        # too many samples for one CTA's staging: partial records + fixed-order combine
+            r = split_softmax_update(costs.view(P, S), traj_samples.view(P, S, H, D), self._particle_means, self.temperature,
+                                     self.step_size, H, D, weights_out=self._w_buf, want_grad=True)
+            self._weights = r['weights'].view(P, S, 1, 1)
+            self._sample_dist.means = self._particle_means.view(P, -1)
+            return r['grad']
+        grad = torch.empty(P, H, D, **self.tensor_args)
         _lib.check(_lib.lib().mpb_softmax_update(_lib.ptr(costs), _lib.ptr(traj_samples),
                                                  _lib.ptr(self._particle_means), _lib.ptr(self._w_buf), _lib.ptr(grad),
                                                  self.temperature, self.step_size, None, P, S, H, D, _lib.stream_ptr()))
@@ -158,8 +167,11 @@ class StochGPMP(OptimizationPlanner):
         P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
         M = H * D
         gp, fields, nf, _ = self.cost._build()
-        if self.cost._extra is not None:      # extra_costs (joint limits, ...): the staged path carries them
+        if self.cost._extra is not None or S > self.SPLIT_THRESHOLD:
+            # extra_costs (joint limits, ...) or a sample count beyond the single-CTA update: the staged path carries them
             return self._optimize_staged(opt_iters, eps, **observation)
+        if opt_iters <= 0:
+            return self._get_traj()
         lib = _lib.lib()
         pos_mean = vel_mean = None
         for it in range(opt_iters):
@@ -195,6 +207,8 @@ class StochGPMP(OptimizationPlanner):
     def _optimize_staged(self, opt_iters, eps=None, **observation):
         """optimize() through sample_and_eval + _update_distribution (composites with extra cost terms)."""
         P, S, M = self.num_particles, self.num_samples, self.n_support_points * self.d_state_opt
+        if opt_iters <= 0:
+            return self._get_traj()
         for it in range(opt_iters):
             e = eps[it] if eps is not None else torch.randn(S, P, M, **self.tensor_args)
             (self._recent_control_samples, self._recent_state_trajectories, self._recent_control_particles,
@@ -240,6 +254,8 @@ class StochGPMP(OptimizationPlanner):
         rec(4)
 
     def get_recent_samples(self):
+        if self._recent_state_particles is None:
+            raise _lib.MpbError('get_recent_samples(): no optimize() iteration has run yet')
         return (self._recent_state_trajectories.detach().clone(), self._recent_state_particles.detach().clone(),
                 self._recent_control_samples.detach().clone(), self._recent_control_particles.detach().clone(),
                 self._recent_weights.detach().clone())

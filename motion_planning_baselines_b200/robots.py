@@ -19,6 +19,7 @@ class Robot:
             raise _lib.MpbError('the fused hot path computes in float32')
         self.model = model
         self.tensor_args = dict(device=dev, dtype=torch.float32)
+        _lib.init_device(dev)
         self.q_dim = model.q_dim
         self.ws_dim = model.ws_dim
         self.dt = dt

@@ -1,4 +1,4 @@
-"""Times mpb_sample_gp_kron alone at the C4 shape (and the dense samplers beside it). Usage: python scratch/k1_kron_bench.py [reps]"""
+"""Times mpb_sample_gp_kron alone at the C4 shape (and the dense samplers beside it). Usage: python profiles/tools/k1_kron_bench.py [reps]"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
