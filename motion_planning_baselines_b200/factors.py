@@ -71,7 +71,7 @@ class MultiMPPrior:
     (mp_priors_multi.py:15-259).  ``sample`` runs on the GPU (csrc/sample_gp.cu)."""
 
     def __init__(self, num_steps, dt, state_dim, dof, K_s_inv, K_gp_inv, start_state, means=None, K_g_inv=None,
-                 goal_states=None, use_numpy=False, tensor_args=None):
+                 goal_states=None, use_numpy=False, tensor_args=None, factor_dtype=torch.float32):
         self.state_dim, self.dof, self.num_steps = state_dim, dof, num_steps
         self.M = state_dim * (num_steps + 1)
         self.tensor_args = tensor_args
@@ -84,11 +84,19 @@ class MultiMPPrior:
         self.means = means.reshape(self.num_modes, -1).to(**tensor_args).contiguous()
 
         Sinv64 = _precision(num_steps, dt, state_dim, dof, K_s_inv, K_gp_inv, K_g_inv if self.goal_directed else None)
-        Sinv_cpu = Sinv64.to(torch.float32)
-        # the reference's own factorisation routine, once, on the CPU, in the working dtype
-        self.scale_tril = dist.MultivariateNormal(torch.zeros(self.M), precision_matrix=Sinv_cpu).scale_tril \
-            .to(**tensor_args).contiguous()
+        Sinv_cpu = Sinv64.to(factor_dtype)      # float64: the reference's init path (base.py:155-158, quirk B8)
         self.Sigma_inv = Sinv_cpu.to(**tensor_args).contiguous()
+        # the reference's own factorisation routine, once, on the CPU, in the working dtype.  NOTE (measured):
+        # at H = 64 this fp32 factor is accurate to ~5e-3 only (cond(Sigma^-1) ~ 2e6) and differs by ~1e-2 between LAPACK
+        # thread counts -- in the reference too -- so a bit-level replay of reference samples needs the reference's
+        # factor (set_scale_tril), not just its noise.
+        self.set_scale_tril(dist.MultivariateNormal(torch.zeros(self.M), precision_matrix=Sinv_cpu).scale_tril)
+
+    def set_scale_tril(self, scale_tril):
+        """Install a lower-triangular factor [M,M] and prepare the sampler operands for it (one-off, setup time)."""
+        tensor_args, state_dim, dof, num_steps = self.tensor_args, self.state_dim, self.dof, self.num_steps
+        assert scale_tril.shape == (self.M, self.M)
+        self.scale_tril = scale_tril.to(**tensor_args).contiguous()
         # Sampler selection (MPB_SAMPLE_GP = kron | kron_umma | kron_fp32 | tc | simt forces one; default: the first that applies).
         #  kron: the factor decouples over the dofs (verified bit-exactly on the device) -> per-dof [2H,2H] blocks
         #  tc  : dense tcgen05 3xTF32 sampler; L pre-split into two TF32-representable parts

@@ -72,19 +72,29 @@ class OptimizationPlanner(MPPlanner):
                             K_g_inv=goal_K, means=particle_means, goal_states=goal_states,
                             tensor_args=tensor_args or self.tensor_args)
 
-    def get_random_trajs(self):
-        """Initial particles ~ GP prior around the straight line (base.py:155-202).  The reference forces
-        fp64 here (quirk B8); we assemble the precision in fp64 and sample in fp32 on the device."""
+    def get_random_trajs(self, eps=None):
+        """Initial particles ~ GP prior around the straight line (base.py:155-202).  The reference forces fp64 for
+        this one-off step (quirk B8): factors, precision and the sampling factor are built in fp64 here too (host side,
+        once) and only rounded to fp32 for the device sampler, which keeps the particles within ~1e-6 of the
+        reference's (tests/test_gpu_init_path.py).  ``eps``: optional injected noise [P_per_goal, num_goals, M]."""
+        f64 = dict(device='cpu', dtype=torch.float64)
         start = torch.cat((self.start_state, torch.zeros_like(self.start_state)), dim=-1)
         goals = None
         if self.multi_goal_states is not None:
             goals = torch.cat((self.multi_goal_states, torch.zeros_like(self.multi_goal_states)), dim=-1)
-        D = 2 * self.n_dof
+        D, d, dt = 2 * self.n_dof, self.n_dof, self.dt
         self.start_prior_init = UnaryFactor(D, self.sigma_start_init, start, self.tensor_args)
         self.gp_prior_init = GPFactor(self.n_dof, self.sigma_gp_init, self.dt, self.n_support_points - 1, self.tensor_args)
-        goal_K = UnaryFactor(D, self.sigma_goal_init, None, self.tensor_args).K if goals is not None else None
-        prior = self.get_GP_prior(self.start_prior_init.K, self.gp_prior_init.Q_inv[0], goal_K, start, goal_states=goals)
-        particles = prior.sample(self.num_particles_per_goal)
+        K_s = torch.eye(D, **f64) / self.sigma_start_init ** 2
+        Qc = torch.eye(d, **f64) / self.sigma_gp_init ** 2
+        a, b, c = 12. * (dt ** -3.) * Qc, -6. * (dt ** -2.) * Qc, 4. * (dt ** -1.) * Qc
+        Q = torch.cat((torch.cat((a, b), dim=-1), torch.cat((b, c), dim=-1)), dim=-2)
+        K_g = torch.eye(D, **f64) / self.sigma_goal_init ** 2 if goals is not None else None
+        prior = MultiMPPrior(self.n_support_points - 1, self.dt, self.dim, self.n_dof, K_s, Q, start, K_g_inv=K_g,
+                             goal_states=goals, tensor_args=self.tensor_args, factor_dtype=torch.float64)
+        if eps is not None:
+            eps = eps.to(**self.tensor_args).contiguous()
+        particles = prior.sample(self.num_particles_per_goal, eps=eps)
         self.traj_dim = particles.shape
         return particles.flatten(0, 1).clone()
 

@@ -63,7 +63,7 @@ def save(name, **arrays):
 
 
 # ---------------------------------------------------------------------------- cases
-def gen_stoch_gpmp(tag, cfg_name, P, S, H, iters, sig, seed):
+def gen_stoch_gpmp(tag, cfg_name, P, S, H, iters, sig, seed, store_factor=True):
     from mp_baselines.planners.stoch_gpmp import StochGPMP
     cfg = configs.config(cfg_name)
     model, obst = cfg['robot'], cfg['obstacles']
@@ -78,7 +78,22 @@ def gen_stoch_gpmp(tag, cfg_name, P, S, H, iters, sig, seed):
         means0 = planner._particle_means.clone()
         L = planner._sample_dist.dist.scale_tril[0].clone()
         n_ctor = len(rec.draws)
-        out = dict(means0=means0, L=L, Sigma_inv=planner.Sigma_inv, eps_init=rec.draws[0])
+        if store_factor:
+            out = dict(means0=means0, L=L, Sigma_inv=planner.Sigma_inv, eps_init=rec.draws[0])
+        else:
+            # H = 64: the [M,M] factor and precision are 3.2 MB each.  The factor couples only entries of the same dof
+            # (exact zeros elsewhere, asserted here), so its d [2H,2H] lower-triangular blocks carry all of it; of the
+            # precision the main + first 2d sub-diagonals do.  NOTE: at H = 64 the reference's fp32 factorisation is only
+            # accurate to ~5e-3 and changes by ~1e-2 with the LAPACK thread count, so a replay needs THIS factor.
+            d_, M_ = model.q_dim, L.shape[0]
+            blocks = torch.stack([L[j::d_][:, j::d_] for j in range(d_)])
+            dense = torch.zeros_like(L)
+            for j in range(d_):
+                dense[j::d_, j::d_] = blocks[j]
+            assert torch.equal(dense, L), 'scale_tril must decouple over the dofs exactly'
+            Sinv = planner.Sigma_inv
+            out = dict(means0=means0, eps_init=rec.draws[0], L_blocks=blocks,
+                       Sinv_band=torch.stack([torch.nn.functional.pad(torch.diagonal(Sinv, -k), (0, k)) for k in range(2 * d_ + 1)]))
         for it in range(iters):
             planner.optimize(opt_iters=1)
             out[f'eps{it}'] = rec.draws[n_ctor + it]
