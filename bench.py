@@ -175,9 +175,14 @@ def run_reference(args):
     sample = (f'{P_cpu} particles x {S} samples x {H} waypoints Panda per step (of {P_PER_GPU}); {steps} timed steps, '
               f'{warmup} warm-up; oracle port in the reference cost model (per-particle scale_tril re-factorised every '
               f'iteration, batched mat-vec sampler, eager torch fp32)')
+    cfg = workload_config(args.gpus)
+    # the CPU arm times a BOUNDED sample of the workload: fewer particles per step (samples/s is flat in P on the CPU,
+    # BASELINE.md section 3.4; the full P = 512 needs a 1.64 GB factor re-factorised every iteration, ~2 min per step)
+    cfg.update(particles_timed=P_cpu, particles_per_gpu_workload=P_PER_GPU, noise='torch.randn on the host (outside the timed region)',
+               sharding='CPU only (rank 0)', global_samples_per_step=P_cpu * S)
     line = dict(impl='reference', metric=METRIC, value=r['value'], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup,
                 ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-                data='synthetic', config=workload_config(args.gpus),
+                data='synthetic', config=cfg,
                 cpu_baseline=dict(value=r['value'], unit=UNIT, cores=cores, kind='port', sample=sample),
                 e2e=dict(value=r['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -188,8 +193,54 @@ def workload_config(n):
                          'sphere obstacles, 512 particles x 64 samples x 64 waypoints per GPU',
                 particles_per_gpu=P_PER_GPU, samples=S, waypoints=H, dof=DOF, robot_spheres=NS, obstacles=NO,
                 global_samples_per_step=n * P_PER_GPU * S, sharding=f'particles x{n} (no data-path collective)',
-                noise='injected eps resident in HBM (8 rotating 117 MB buffers)',
-                l2='per-step inputs+outputs (235 MB) exceed the 126 MB L2; eps buffers rotate')
+                noise='drawn inside the sampling kernel (Philox4x32-10 keyed on the global element index), as the reference '
+                      'draws inside MultiMPPrior.sample; the injected-noise variant (8 rotating 117 MB buffers resident in HBM) '
+                      'is reported under "injected_noise"',
+                l2='per-step outputs (117 MB of samples; 235 MB with injected noise) exceed / fill the 126 MB L2 and every '
+                   'step overwrites them')
+
+
+def measure_fp32_peak(dev):
+    """Measured FFMA rate of this device (csrc/microbench.cu): best of 5 launches, CUDA events."""
+    import ctypes as C
+
+    from motion_planning_baselines_b200 import _lib
+    scratch = torch.empty(148 * 8 * 256 * 2, **dev)
+    iters, nthreads = 4096, C.c_longlong(0)
+    lib = _lib.lib()
+    best = None
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.mpb_bench_fp32_peak(_lib.ptr(scratch), iters, C.byref(nthreads), _lib.stream_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return 2.0 * 64 * iters * nthreads.value / (best * 1e-3) / 1e12
+
+
+def parity_check(planner, cfg, sig, means0, eps, n_particles=8):
+    """Replays the LAST benchmarked step of a particle subset through the CPU oracle (checker only, outside every timed
+    region): costs 1e-5, flags / argmin identical -- evidence that the timed kernels computed the right thing."""
+    from oracle import check
+    torch.set_num_threads(1)
+    P = planner.num_particles
+    rng = np.random.default_rng(0)
+    sub = sorted(rng.choice(P, n_particles, replace=False).tolist())
+    ref = check.stoch_gpmp_subset(cfg, H, sig, means0, planner._sample_dist.scale_tril, planner.Sigma_inv, eps, sub)
+    idx = torch.as_tensor(sub, device=means0.device)
+    amp = float((ref['samples'] - means0[idx].cpu().unsqueeze(1)).abs().max())
+    e_samples = float((planner.state_samples[idx].cpu() - ref['samples']).abs().max()) / max(amp, 1e-30)
+    e_cost = check.rel_err(planner.costs[idx], ref['costs'])
+    flags = bool(torch.equal(planner.free_flags.view(P, S)[idx].bool().cpu(), ref['free']))
+    argmin = bool(torch.equal(planner.costs[idx].argmin(1).cpu(), ref['costs'].argmin(1)))
+    torch.set_num_threads(os.cpu_count() or 1)
+    return dict(particles_checked=sub, samples_max_err_over_noise_amplitude=e_samples, costs_max_rel_err=e_cost,
+                collision_free_flags_identical=flags, argmin_identical=argmin,
+                ok=bool(e_samples < 1e-5 and e_cost < 1e-5 and flags and argmin),
+                against='oracle.check.stoch_gpmp_subset (CPU restatement of stoch_gpmp.py:235-279) on the noise the kernels drew '
+                        '(mpb_philox_normal dump of the last timed step)')
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -202,11 +253,10 @@ def main():
     ap.add_argument('--cpu-particles', type=int, default=32, help='particles per step of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-other-configs', action='store_true')
+    ap.add_argument('--no-parity-check', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
-
-    import ctypes as C
 
     import torch.distributed as dist
 
@@ -238,16 +288,18 @@ def main():
     K, W = args.steps, max(args.warmup, 3)
 
     cfg = configs.config('C4')
-    torch.manual_seed(1000 + rank)
+    sig = cfg['params']
+    torch.manual_seed(1000)
     robot = Robot(cfg['robot'], dt=cfg['dt'], tensor_args=dev)
     field = CollisionField(cfg['obstacles'], tensor_args=dev)
     P = P_PER_GPU
+    # one global noise stream for the whole job: rank r owns particles [r*P, (r+1)*P) of world*P
     planner = StochGPMP(robot=robot, n_dof=DOF, n_support_points=H, num_particles_per_goal=P, opt_iters=1, dt=cfg['dt'],
                         start_state=torch.tensor(cfg['start']).to(**dev),
                         multi_goal_states=torch.tensor(cfg['goal']).to(**dev).unsqueeze(0),
-                        collision_fields=[field], tensor_args=dev, num_samples=S, **cfg['params'])
-    n_buf = 8
-    eps_bufs = [torch.randn(S, P, M, **dev) for _ in range(n_buf)]
+                        collision_fields=[field], tensor_args=dev, num_samples=S, seed=1000,
+                        noise_particle_offset=rank * P, noise_particles_global=world * P, **sig)
+    assert planner._sample_dist.kron_tc_kind == 1, 'the C4 factor must take the default structured sampler'
     means0 = planner._particle_means.clone()
 
     def barrier():
@@ -255,41 +307,89 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up ---------------------------------------------------------------------------
-    for i in range(W):
-        planner.step_staged(eps_bufs[i % n_buf])
-    planner._particle_means.copy_(means0)
+    def allmax(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev['device'], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
 
-    # ---- timed region: exactly K steps, per-stage events inside ---------------------------------
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    def timed(step_fn, n):
+        """n steps bracketed by barrier + synchronize, per-stage events inside -> (ms total max over ranks, stage ms)."""
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(n)]
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(n):
+            step_fn(i, ev[i])
+        t1.record()
+        barrier()
+        stage = np.array([[ev[i][j].elapsed_time(ev[i][j + 1]) for j in range(4)] for i in range(n)]).mean(0)
+        return allmax(t0.elapsed_time(t1)), stage
+
+    # ---- headline: K steps, noise drawn inside K1 (the way the reference's optimize() is called) -----------------------
+    for i in range(W):
+        planner.step_staged(None)
+    planner._particle_means.copy_(means0)
     sampler = ClockSampler(physical_gpu_index(local_rank))
-    barrier()
     sampler.start()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for i in range(K):
-        planner.step_staged(eps_bufs[i % n_buf], events=ev[i])
-    t_end.record()
-    barrier()
+    ms_total, stage_ms = timed(lambda i, ev: planner.step_staged(None, events=ev), K)
     clocks = sampler.stop()
-    ms_total = t_start.elapsed_time(t_end)
-    stage_ms = np.array([[ev[i][j].elapsed_time(ev[i][j + 1]) for j in range(4)] for i in range(K)]).mean(0)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev['device'], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     value = world * P * S * K / (ms_total * 1e-3)
     free_frac = float(planner.free_flags.float().mean())
+    # K3 reads only the sample rows whose weight is non-zero: count them (roofline on bytes actually needed)
+    rows_nonzero = int((planner._w_buf != 0).sum())
 
-    # ---- e2e through the public API with HOST buffers ------------------------------------------
-    # per step: pinned-host eps -> device (H2D), planner.optimize(opt_iters=1, eps=...), trajectory -> pinned host (D2H)
+    # ---- parity of what was just timed (rank 0; the checker runs after / outside the timed region) ----------------------
+    check = None
+    if rank == 0 and not args.no_parity_check:
+        planner._particle_means.copy_(means0)
+        desc = planner._noise.desc()
+        planner.step_staged(None)
+        torch.cuda.synchronize()
+        eps_last = _lib.philox_normal(desc, _lib.NOISE_SPM, (S, P, M), dev['device'])
+        check = parity_check(planner, cfg, sig, means0, eps_last)
+        del eps_last
+
+    # ---- the same step on INJECTED noise resident in HBM (the parity configuration; K1 reads 117 MB more) --------------
+    n_buf = 8
+    eps_bufs = [torch.randn(S, P, M, **dev) for _ in range(n_buf)]
     planner._particle_means.copy_(means0)
+    for i in range(3):
+        planner.step_staged(eps_bufs[i % n_buf])
+    planner._particle_means.copy_(means0)
+    Ki = max(3, min(K, 20))
+    ms_inj, stage_inj = timed(lambda i, ev: planner.step_staged(eps_bufs[i % n_buf], events=ev), Ki)
+    del eps_bufs
+
+    # ---- e2e through the public API with HOST buffers: planner.optimize(opt_iters=1) -----------------------------------
+    # per step: the problem (initial particle trajectories) comes from pinned host memory, the optimised trajectories go
+    # back to pinned host memory; the noise is drawn by the planner on the device, as in the reference
+    h_means = means0.cpu().pin_memory()
+    h_traj = torch.empty(P, H, D).pin_memory()
+    Ke = max(3, min(K, 20))
+
+    def e2e_steps(n):
+        for _ in range(n):
+            planner._particle_means.copy_(h_means, non_blocking=True)
+            traj = planner.optimize(opt_iters=1)
+            h_traj.copy_(traj, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_steps(3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_steps(Ke)
+    e1.record()
+    barrier()
+    ms_e2e = allmax(e0.elapsed_time(e1))
+    e2e_value = world * P * S * Ke / (ms_e2e * 1e-3)
+
+    # e2e with INJECTED host noise (parity-style call: 117 MB of eps uploaded per step; PCIe bound) -- secondary
     h_eps = [torch.randn(S, P, M).pin_memory() for _ in range(2)]
     d_eps = [torch.empty(S, P, M, **dev) for _ in range(2)]
-    h_traj = torch.empty(P, H, D).pin_memory()
     copy_stream = torch.cuda.Stream()
     main_stream = torch.cuda.current_stream()
-    Ke = max(3, min(K, 20))
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
@@ -300,7 +400,7 @@ def main():
             d_eps[b].copy_(h_eps[b], non_blocking=True)
             ready[b].record(copy_stream)
 
-    def e2e_steps(n):
+    def e2e_injected(n):
         for b in range(2):
             consumed[b].record(main_stream)
         upload(0)
@@ -313,41 +413,15 @@ def main():
             consumed[b].record(main_stream)
             h_traj.copy_(traj, non_blocking=True)
         torch.cuda.synchronize()
-    e2e_steps(2)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_steps(Ke)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev['device'], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    e2e_value = world * P * S * Ke / (ms_e2e * 1e-3)
-
-    # e2e the way the reference's API is normally called (informational): the planner draws its own noise on the device
-    # (optimize() takes no noise argument in the reference); per step the problem -- the initial particle trajectories --
-    # comes from pinned host memory and the optimised trajectories go back to it
-    h_means = means0.cpu().pin_memory()
-
-    def dev_noise_steps(n):
-        for _ in range(n):
-            planner._particle_means.copy_(h_means, non_blocking=True)
-            traj = planner.optimize(opt_iters=1)
-            h_traj.copy_(traj, non_blocking=True)
-    dev_noise_steps(3)
+    Kj = max(3, min(K, 10))
+    e2e_injected(2)
     barrier()
     e0.record()
-    dev_noise_steps(Ke)
+    e2e_injected(Kj)
     e1.record()
     barrier()
-    ms_e2e_dev = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e_dev], device=dev['device'], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e_dev = float(t.item())
+    ms_e2e_inj = allmax(e0.elapsed_time(e1))
+    del h_eps, d_eps
 
     if rank != 0:
         if world > 1:
@@ -356,70 +430,72 @@ def main():
 
     pk = peaks()
     n_samp = P * S
+    fp32_measured = measure_fp32_peak(dev)
     sm_mhz_peak = clocks.get('sm_max_mhz') or pk['sm_max_mhz']
-    fp32_peak = 148 * 128 * 2 * sm_mhz_peak * 1e6 / 1e12            # TFLOP/s, nominal FMA rate at clocks.max.sm
-    kernels = []
-    flops = [FLOP_SAMPLING, None, FLOP_FK + FLOP_SDF + FLOP_GP + FLOP_IS, None]
-    sd = planner._sample_dist
-    k1_name = ('sample_gp_kron_umma_kernel (K1, structured, tcgen05 3xTF32)' if sd.kron_tc_kind == 2 else
-               'sample_gp_kron_mma_kernel (K1, structured, warp MMA fp16x2 split)' if sd.kron_tc_kind == 1 else
-               'sample_gp_kron_kernel (K1, structured FP32)' if sd.scale_tril_kron is not None else
-               'sample_gp_tc_kernel (K1, tcgen05 3xTF32)' if sd.scale_tril_split is not None else 'sample_gp_simt_kernel (K1)')
-    if sd.scale_tril_kron is not None:
-        flops[0] = DOF * (2 * H) * (2 * H + 1)          # 7 independent [128,128] triangular mat-vecs = 115,584 flop / sample
-    names = [k1_name, 'prior_matvec_kernel', 'cost_eval_kernel (K2)', 'softmax_update_kernel (K3)']
-    for j, nm in enumerate(names):
-        k = dict(kernel=nm, ms=float(stage_ms[j]), share=float(stage_ms[j] / stage_ms.sum()))
-        if flops[j] and j == 0 and 'tcgen05' in nm:
-            a = flops[j] * n_samp / (stage_ms[j] * 1e-3) / 1e12
-            tf32_peak = pk['bf16'] / 2.0
-            k.update(bound='tensor', achieved=a, peak=tf32_peak, unit='TFLOP/s', frac=a / tf32_peak,
-                     note='algorithmic flops M(M+1) per sample; peak = TF32 dense = measured bf16 peak / 2 (' + pk['source'] +
-                          '); fp32 parity needs the 3xTF32 split, i.e. 3 tensor-core flops per algorithmic flop, so the '
-                          'ceiling for this ratio is 1/3 (times the triangular-tile granularity)')
-        elif flops[j]:
-            a = flops[j] * n_samp / (stage_ms[j] * 1e-3) / 1e12
-            k.update(bound='fp32', achieved=a, peak=fp32_peak, unit='TFLOP/s', frac=a / fp32_peak)
-            if j == 2:      # the same kernel against the HBM roofline (it reads every sample row once): far from memory bound
-                gbs = M * 4 * n_samp / (stage_ms[j] * 1e-3) / 1e9
-                k.update(hbm_gbs=gbs, hbm_frac=gbs / pk['hbm'], hbm_peak=pk['hbm'], hbm_peak_source=pk['source'])
-            if j == 0 and 'kron' in nm:
-                gbs = 2 * M * 4 * n_samp / (stage_ms[j] * 1e-3) / 1e9
-                k.update(hbm_gbs=gbs, hbm_frac=gbs / pk['hbm'],
-                         note='the factor decouples over the 7 dofs (exact zeros, verified bit-exactly at setup): '
-                              'dof*2H*(2H+1) = 115,584 flop / sample instead of the dense M(M+1) = 803,712; '
-                              'HBM floor = eps read + x written = 7,168 B / sample')
-        elif j == 3:
-            a = BYTES_UPDATE * n_samp / (stage_ms[j] * 1e-3) / 1e9
-            k.update(bound='hbm', achieved=a, peak=pk['hbm'], unit='GB/s', frac=a / pk['hbm'],
-                     note='algorithmic bytes = one read of every sample row; rows with zero weight are skipped, so achieved can exceed peak')
-        kernels.append(k)
-    dom = max((k for k in kernels if 'achieved' in k), key=lambda k: k['ms'])
+    fp32_nominal = 148 * 128 * 2 * sm_mhz_peak * 1e6 / 1e12
+
+    def kernel_table(stage, k1_reads_eps):
+        flop_k1 = DOF * (2 * H) * (2 * H + 1)       # 7 independent [128,128] triangular mat-vecs = 115,584 flop / sample
+        bytes_k1 = M * 4 * (2 if k1_reads_eps else 1)
+        k1 = dict(kernel='sample_gp_kron_mma_kernel<7,64,%s> (K1: structured GP sampler, warp MMA fp16x2 split%s)'
+                         % ('false' if k1_reads_eps else 'true', '' if k1_reads_eps else ', Philox noise in-kernel'),
+                  ms=float(stage[0]), bound='hbm', achieved=bytes_k1 * n_samp / (stage[0] * 1e-3) / 1e9, peak=pk['hbm'], unit='GB/s',
+                  algorithmic_bytes_per_sample=bytes_k1, algorithmic_flop_per_sample=flop_k1,
+                  note='HBM floor = x written' + (' + eps read' if k1_reads_eps else '') + '; the factor decouples over the 7 dofs '
+                       '(exact zeros, verified bit-exactly at setup): 115,584 flop / sample instead of the dense 803,712')
+        k1['frac'] = k1['achieved'] / k1['peak']
+        mv = dict(kernel='prior_matvec_dof_kernel (Sigma^-1 mu)', ms=float(stage[1]), bound='latency')
+        flop_k2 = FLOP_FK + FLOP_SDF + FLOP_GP + FLOP_IS
+        a2 = flop_k2 * n_samp / (stage[2] * 1e-3) / 1e12
+        k2 = dict(kernel='cost_eval_kernel<1,4,0> (K2: FK + collision + GP cost + IS dot)', ms=float(stage[2]), bound='fp32',
+                  achieved=a2, peak=fp32_measured, unit='TFLOP/s', frac=a2 / fp32_measured,
+                  peak_nominal=fp32_nominal, frac_of_nominal=a2 / fp32_nominal, algorithmic_flop_per_sample=flop_k2,
+                  hbm_gbs=M * 4 * n_samp / (stage[2] * 1e-3) / 1e9, hbm_frac=M * 4 * n_samp / (stage[2] * 1e-3) / 1e9 / pk['hbm'],
+                  note='algorithmic flops count ALL 50 x 16 sphere pairs per waypoint; the broad phase skips provably-zero pairs, '
+                       'so executed instructions are fewer (see profiles/): the kernel is FP32-issue bound')
+        bytes_k3 = (rows_nonzero * M * 4 + 3 * P * M * 4 + 2 * n_samp * 4)
+        a3 = bytes_k3 / (stage[3] * 1e-3) / 1e9
+        k3 = dict(kernel='softmax_update_kernel (K3)', ms=float(stage[3]), bound='latency', achieved=a3, peak=pk['hbm'], unit='GB/s',
+                  frac=a3 / pk['hbm'], bytes_needed=bytes_k3, rows_with_nonzero_weight=rows_nonzero, rows_total=n_samp,
+                  note='bytes actually needed: rows whose softmax weight is non-zero (nearly one-hot at T = 1) + means + costs / '
+                       'weights; a 12 us launch + DRAM-latency chain, not a throughput kernel')
+        tot = float(np.sum(stage))
+        for k in (k1, mv, k2, k3):
+            k['share'] = k['ms'] / tot
+        return [k1, mv, k2, k3]
+
+    kernels = kernel_table(stage_ms, k1_reads_eps=False)
+    dom = max(kernels, key=lambda k: k['ms'])
     roofline = dict(bound=dom['bound'], achieved=dom['achieved'], peak=dom['peak'], unit=dom['unit'], frac=dom['frac'],
                     traffic=ncu_traffic(dom['kernel']), kernel=dom['kernel'], ms_per_launch=dom['ms'],
-                    peak_source=('nominal FP32 FMA rate 148 SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json holds only '
-                                 'HBM and bf16 tensor peaks; this kernel is FP32-issue bound)') if dom['bound'] == 'fp32' else dom.get('note', pk['source']),
-                    algorithmic_flop_per_sample=flops[2] if 'K2' in dom['kernel'] else flops[0],
-                    hbm_view=dict(achieved=dom.get('hbm_gbs'), peak=pk['hbm'], unit='GB/s', frac=dom.get('hbm_frac'), peak_source=pk['source'],
-                                  algorithmic_bytes_per_sample=M * 4), kernels=kernels)
+                    peak_source='FP32 FFMA rate MEASURED in this run (mpb_bench_fp32_peak: 8 independent FMA chains per thread, '
+                                'best of 6 launches); nominal 148 SMs x 128 lanes x 2 x clocks.max.sm = %.1f TFLOP/s' % fp32_nominal,
+                    peak_nominal=fp32_nominal, frac_of_nominal=dom.get('frac_of_nominal'),
+                    algorithmic_flop_per_sample=dom.get('algorithmic_flop_per_sample'),
+                    hbm_view=dict(achieved=dom.get('hbm_gbs'), peak=pk['hbm'], unit='GB/s', frac=dom.get('hbm_frac'),
+                                  peak_source=pk['source'], algorithmic_bytes_per_sample=M * 4),
+                    kernels=kernels)
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                 config=workload_config(world), clocks=clocks, gpu_launches=4 * K,
-                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=S * P * M * 4, d2h_bytes_per_step=P * H * D * 4,
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=P * H * D * 4, d2h_bytes_per_step=P * H * D * 4,
                          steps=Ke, ms_per_step=ms_e2e / Ke,
-                         note='planner.optimize(opt_iters=1, eps=<pinned host noise>) + trajectory read-back; the next '
-                              "step's noise upload overlaps this step's kernels; bound by the 117 MB noise upload over PCIe (h2d_gb_per_s)",
-                         h2d_gb_per_s=S * P * M * 4 / (ms_e2e / Ke * 1e-3) / 1e9,
-                         device_noise=dict(value=world * P * S * Ke / (ms_e2e_dev * 1e-3), unit=UNIT, ms_per_step=ms_e2e_dev / Ke,
-                                           h2d_bytes_per_step=P * H * D * 4, d2h_bytes_per_step=P * H * D * 4,
-                                           note='planner.optimize(opt_iters=1) as the reference is called: noise drawn on the '
-                                                'device by the planner; initial particle trajectories uploaded from pinned host '
-                                                'memory and optimised trajectories read back every step')),
-                roofline=roofline, collision_free_fraction_last_step=free_frac)
+                         note='planner.optimize(opt_iters=1) exactly as the reference is called (no noise argument: drawn in K1); '
+                              'per step the initial particle trajectories come from pinned host memory and the optimised '
+                              'trajectories go back to pinned host memory',
+                         injected_noise=dict(value=world * P * S * Kj / (ms_e2e_inj * 1e-3), unit=UNIT, ms_per_step=ms_e2e_inj / Kj,
+                                             h2d_bytes_per_step=S * P * M * 4, d2h_bytes_per_step=P * H * D * 4,
+                                             h2d_gb_per_s=S * P * M * 4 / (ms_e2e_inj / Kj * 1e-3) / 1e9,
+                                             note='parity-style call planner.optimize(opt_iters=1, eps=<pinned host noise>): '
+                                                  '117 MB of noise uploaded per step, PCIe bound')),
+                injected_noise=dict(value=world * P * S * Ki / (ms_inj * 1e-3), unit=UNIT, ms_per_step=ms_inj / Ki, steps=Ki,
+                                    note='the same step on injected noise resident in HBM (8 rotating 117 MB buffers): K1 reads eps '
+                                         'instead of drawing it', kernels=kernel_table(stage_inj, k1_reads_eps=True)),
+                roofline=roofline, collision_free_fraction_last_step=free_frac, parity_check=check)
     if world == 1 and not args.no_other_configs:
         # the other BASELINE.json configs ("ms per planner iter"), informational: see bench_configs.py
-        del planner, eps_bufs, d_eps
+        del planner
         torch.cuda.empty_cache()
         try:
             import bench_configs

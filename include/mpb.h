@@ -114,13 +114,41 @@ typedef struct mpb_extra_cost_desc {
     const float* q_max;         /* [d] */
 } mpb_extra_cost_desc;
 
+/* In-kernel Gaussian noise (csrc/philox.cuh).  Replaces the draws the reference makes inside
+ * torch.distributions.MultivariateNormal.rsample (mp_priors_multi.py:253-256, stomp.py:102, priors/gaussian.py:295):
+ * element e (flat index) of the VIRTUAL GLOBAL noise tensor of the whole job is output e % 4 of
+ * Philox4x32-10(counter = (e / 4, offset), key = seed) pushed through Box-Muller -- independent of how particles or
+ * samples are sharded over GPUs.  Global tensor per layout (local extents n0..n3 of the call in brackets):
+ *   MPB_NOISE_SPM    [S_glob, P_glob, M]      (Stoch-GPMP / MultiMPPrior.sample;  local [S,P,M])
+ *   MPB_NOISE_STOMP  [S_glob, D, P_glob, H]   (STOMP.sample;                       local [S,D,P,H])
+ *   MPB_NOISE_MPPI   [C, N_glob, T]           (ControlTrajectoryGaussian.sample;   local [C,N,T], N_glob = P_global,
+ *                                              first local sample = s_offset)
+ * The caller advances `offset` by one per draw (per optimize() iteration). */
+#define MPB_NOISE_SPM 0
+#define MPB_NOISE_STOMP 1
+#define MPB_NOISE_MPPI 2
+typedef struct mpb_noise_desc {
+    uint64_t seed;          /* Philox key */
+    uint64_t offset;        /* draw counter */
+    int64_t s_offset;       /* global index of this call's first sample   (sample split over ranks; else 0) */
+    int64_t p_offset;       /* global index of this call's first particle (particle sharding over ranks; else 0) */
+    int64_t P_global;       /* particles (MPPI: control samples) of the whole job, >= offset + local count */
+} mpb_noise_desc;
+/* out[local layout] = the normals a kernel called with this descriptor consumes (debug / replay entry, and the
+ * generator in front of the samplers that have no fused variant).  n3 is ignored for 3-D layouts. */
+int mpb_philox_normal(const mpb_noise_desc* noise, int layout, float* out, int n0, int n1, int n2, int n3, void* stream);
+
+/* FP32 FFMA micro-benchmark (csrc/microbench.cu): launches 2*64*iters flop per thread on *threads_out threads; the
+ * caller times it with CUDA events.  bench.py uses it as the measured FP32 roofline denominator. */
+int mpb_bench_fp32_peak(float* scratch, int iters, long long* threads_out, void* stream);
+
 const char* mpb_last_error(void);
 int mpb_version(void);
 /* Allocates and zeroes the work-scheduler slots of the CURRENT device (see "Conventions"; no counterpart in the
  * reference, which has no native state).  Idempotent, synchronous, not capturable.  Also the recovery call after a
  * failed launch: it re-arms every slot. */
 int mpb_init(void);
-/* sizeof(mpb_robot_desc | mpb_field_desc | mpb_gp_desc | mpb_extra_cost_desc) for which = 0 | 1 | 2 | 3: lets a foreign-language binding
+/* sizeof(mpb_robot_desc | mpb_field_desc | mpb_gp_desc | mpb_extra_cost_desc | mpb_noise_desc) for which = 0 | 1 | 2 | 3 | 4: lets a foreign-language binding
  * verify its struct layout before the first call. */
 int mpb_sizeof_desc(int which);
 
@@ -161,6 +189,10 @@ int mpb_sample_gp_kron(const float* LkT, const float* mu, const float* eps, floa
  *                                   bytes, 16-byte aligned.  One-off setup, stream-ordered. */
 long long mpb_sample_gp_kron_tc_bytes(int H, int dof);
 int mpb_sample_gp_kron_tc_prepare(const float* LkT, void* LkF, int H, int dof, void* stream);
+/* mpb_sample_gp_kron_tc_rng: the same sampler drawing its own noise (layout MPB_NOISE_SPM) slot by slot while it fills
+ * its shared-memory tile -- no eps tensor, no generator launch; bit-identical to mpb_philox_normal + mpb_sample_gp_kron_tc. */
+int mpb_sample_gp_kron_tc_rng(const void* LkF, const float* mu, const mpb_noise_desc* noise, float* x,
+                              int P, int S, int H, int dof, void* stream);
 int mpb_sample_gp_kron_tc(const void* LkF, const float* mu, const float* eps, float* x,
                           int P, int S, int H, int dof, void* stream);
 
@@ -180,6 +212,9 @@ int mpb_sample_gp_kron_umma(const float* Lp, const float* mu, const float* eps, 
  * Replaces STOMP.sample (mp_baselines/planners/stomp.py:97-108); eps is [S,D,P,H]. */
 int mpb_sample_stomp(const float* L_R, const float* mu, const float* eps, float* x,
                      int P, int S, int H, int D, void* stream);
+/* Same with the noise drawn in the kernel (layout MPB_NOISE_STOMP): bit-identical to mpb_philox_normal + mpb_sample_stomp. */
+int mpb_sample_stomp_rng(const float* L_R, const float* mu, const mpb_noise_desc* noise, float* x,
+                         int P, int S, int H, int D, void* stream);
 
 /* y[p,:] = Sigma_inv @ mu[p,:] for a banded (block-tridiagonal) Sigma_inv [M,M] with
  * half bandwidth half_bw (= 2D-1).  Accumulated in fp64.  First half of the
@@ -249,6 +284,13 @@ int mpb_stoch_gpmp_iter_kron(const float* L_kron, const void* L_kron_tc, int tc_
                              const mpb_field_desc* fields, int n_fields,
                              const mpb_gp_desc* gp,
                              float temp, float step, void* stream);
+/* mpb_stoch_gpmp_iter_kron_rng: the iteration as the reference runs it -- optimize() takes no noise (stoch_gpmp.py:281-309),
+ * the draw happens inside the sampler: K1 = mpb_sample_gp_kron_tc_rng (tc_kind 1 operand LkF). */
+int mpb_stoch_gpmp_iter_kron_rng(const void* L_kron_tc, const float* Sigma_inv, int sigma_inv_structured,
+                                 const mpb_noise_desc* noise, float* mu, float* x, float* cost, float* weights,
+                                 float* is_vec, uint8_t* free_flag, int P, int S, int H, const mpb_robot_desc* robot,
+                                 const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp, float temp, float step,
+                                 void* stream);
 int mpb_stoch_gpmp_iter(const float* L, const float* L_split, const float* Sigma_inv, const float* eps,
                         float* mu, float* x, float* cost, float* weights, float* is_vec,
                         uint8_t* free_flag,
@@ -341,6 +383,16 @@ int mpb_mppi_rollout(const float* L_ctrl, const float* Cov_inv, const float* mea
                      const float* state0, const float* goal, const float* ctrl_min, const float* ctrl_max,
                      float* xu, float* quad, float* isv, int N, int T, int C, int sd,
                      float dt, float discount, float w_pos, float w_ctrl, float w_posT, void* stream);
+/* mpb_mppi_rollout_ex: `mean_sample` [T,C]|NULL = the mean the controls are SAMPLED around when it differs from the
+ * mean of the IS term: the reference samples from ctrl_dist, whose loc is refreshed only by update_ctrl_dist()
+ * (mppi.py:68-70,86), so after pop()/shift() (mppi.py:171-178) it still holds the unshifted mean while the IS term and
+ * the update use the shifted self._mean.  eps == NULL: the noise is drawn in the kernel (`noise`, layout MPB_NOISE_MPPI;
+ * bit-identical to mpb_philox_normal + eps). */
+int mpb_mppi_rollout_ex(const float* L_ctrl, const float* Cov_inv, const float* mean, const float* mean_sample,
+                        const float* eps, const mpb_noise_desc* noise, const float* state0, const float* goal,
+                        const float* ctrl_min, const float* ctrl_max, float* xu, float* quad, float* isv,
+                        int N, int T, int C, int sd, float dt, float discount, float w_pos, float w_ctrl, float w_posT,
+                        void* stream);
 /* cost[n] = (quad[n] + energy[0]) + temp*isv[n,0] + temp*isv[n,1] + ...; energy (device fp64 scalar | NULL) is the
  * obstacle cost SUMMED OVER THE BATCH, which the reference adds to every sample (point.py:196, quirk B2). */
 int mpb_mppi_finalize(const float* quad, const float* isv, const double* energy, float temp, float* cost,

@@ -47,6 +47,13 @@ class ExtraCostDesc(C.Structure):
                 ('q_min', C.c_void_p), ('q_max', C.c_void_p)]
 
 
+class NoiseDesc(C.Structure):
+    """mpb_noise_desc: in-kernel Philox noise keyed on the global element index (include/mpb.h)."""
+    _fields_ = [('seed', C.c_uint64), ('offset', C.c_uint64), ('s_offset', C.c_int64), ('p_offset', C.c_int64),
+                ('P_global', C.c_int64)]
+
+
+NOISE_SPM, NOISE_STOMP, NOISE_MPPI = 0, 1, 2
 MPB_MAX_INTERP = 32
 _lib = None
 
@@ -55,6 +62,7 @@ _SIGNATURES = {
     'mpb_last_error': (C.c_char_p, []),
     'mpb_version': (C.c_int, []),
     'mpb_init': (C.c_int, []),
+    'mpb_bench_fp32_peak': (C.c_int, [_vp, _i, C.POINTER(C.c_longlong), _vp]),
     'mpb_sizeof_desc': (C.c_int, [_i]),
     'mpb_sample_gp': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'mpb_split_tf32': (C.c_int, [_vp, _vp, _vp, C.c_longlong, _vp]),
@@ -67,6 +75,12 @@ _SIGNATURES = {
     'mpb_sample_gp_kron_tc_prepare': (C.c_int, [_vp, _vp, _i, _i, _vp]),
     'mpb_sample_gp_kron_tc': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'mpb_sample_stomp': (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'mpb_sample_stomp_rng': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _i, _i, _i, _i, _vp]),
+    'mpb_philox_normal': (C.c_int, [C.POINTER(NoiseDesc), _i, _vp, _i, _i, _i, _i, _vp]),
+    'mpb_sample_gp_kron_tc_rng': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _i, _i, _i, _i, _vp]),
+    'mpb_stoch_gpmp_iter_kron_rng': (C.c_int, [_vp, _vp, _i, C.POINTER(NoiseDesc), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                               C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc), _f, _f, _vp]),
+    'mpb_mppi_rollout_ex': (C.c_int, [_vp] * 5 + [C.POINTER(NoiseDesc)] + [_vp] * 7 + [_i, _i, _i, _i, _f, _f, _f, _f, _f, _vp]),
     'mpb_prior_matvec': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'mpb_cost_eval': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
                                 _vp, _i, _f, _vp, _vp, _vp, _vp]),
@@ -183,7 +197,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        for which, struct in enumerate((RobotDesc, FieldDesc, GPDesc, ExtraCostDesc)):
+        for which, struct in enumerate((RobotDesc, FieldDesc, GPDesc, ExtraCostDesc, NoiseDesc)):
             if handle.mpb_sizeof_desc(which) != C.sizeof(struct):
                 raise MpbError(f'{struct.__name__}: ctypes layout ({C.sizeof(struct)} B) differs from the library '
                                f'({handle.mpb_sizeof_desc(which)} B); rebuild with ./build.sh')
@@ -227,6 +241,36 @@ def ptr(t):
 def stream_ptr():
     """The stream argument of a C-ABI call: the current stream of the device the call's tensors live on."""
     return _STREAM
+
+
+class NoiseStream:
+    """Host-side state of the in-kernel noise: a seed and a draw counter, plus where this process sits in the job
+    (first global particle / sample it owns, global count).  ``next()`` returns the descriptor of one draw and
+    advances the counter, so successive optimize() iterations see fresh noise; two processes built with the same seed
+    and the job's global extents draw exactly the slices of ONE global stream they own."""
+
+    def __init__(self, seed=None, p_offset=0, P_global=1, s_offset=0, offset=0):
+        self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        self.offset = int(offset)
+        self.p_offset, self.P_global, self.s_offset = int(p_offset), int(P_global), int(s_offset)
+
+    def desc(self, offset=None):
+        return NoiseDesc(seed=self.seed, offset=self.offset if offset is None else int(offset), s_offset=self.s_offset,
+                         p_offset=self.p_offset, P_global=self.P_global)
+
+    def next(self):
+        d = self.desc()
+        self.offset += 1
+        return d
+
+
+def philox_normal(noise_desc, layout, shape, device):
+    """The normals a kernel called with ``noise_desc`` consumes, in the call's local layout (replay / debug; also the
+    generator in front of the samplers without a fused variant)."""
+    out = torch.empty(*shape, device=device, dtype=torch.float32)
+    n = list(shape) + [1] * (4 - len(shape))
+    check(lib().mpb_philox_normal(C.byref(noise_desc), layout, ptr(out), n[0], n[1], n[2], n[3], stream_ptr()))
+    return out
 
 
 def require_f32(*tensors):

@@ -88,6 +88,7 @@ extern "C" int mpb_sizeof_desc(int which) {
         case 1: return (int)sizeof(mpb_field_desc);
         case 2: return (int)sizeof(mpb_gp_desc);
         case 3: return (int)sizeof(mpb_extra_cost_desc);
+        case 4: return (int)sizeof(mpb_noise_desc);
         default: return -1;
     }
 }
@@ -121,6 +122,25 @@ extern "C" int mpb_stoch_gpmp_iter_kron(const float* L_kron, const void* L_kron_
     int rc = (tc_kind == 2 && L_kron_tc) ? mpb_sample_gp_kron_umma(static_cast<const float*>(L_kron_tc), mu, eps, x, P, S, H, robot->q_dim, stream)
              : (tc_kind == 1 && L_kron_tc) ? mpb_sample_gp_kron_tc(L_kron_tc, mu, eps, x, P, S, H, robot->q_dim, stream)
                                            : mpb_sample_gp_kron(L_kron, mu, eps, x, P, S, H, robot->q_dim, stream);
+    if (rc) return rc;
+    rc = sigma_inv_structured ? mpb_prior_matvec_dof(Sigma_inv, mu, is_vec, P, H, robot->q_dim, stream)
+                              : mpb_prior_matvec(Sigma_inv, mu, is_vec, P, M, 2 * D - 1, stream);
+    if (rc) return rc;
+    rc = mpb_cost_eval(x, P * S, H, robot, fields, n_fields, gp, is_vec, S, temp, cost, nullptr, free_flag, stream);
+    if (rc) return rc;
+    return mpb_softmax_update(cost, x, mu, weights, nullptr, temp, step, nullptr, P, S, H, D, stream);
+}
+
+// The same iteration drawing its own noise inside K1 (mpb_sample_gp_kron_tc_rng): the way the reference is called --
+// optimize() takes no noise argument (stoch_gpmp.py:281-309), the draw happens inside MultiMPPrior.sample.
+extern "C" int mpb_stoch_gpmp_iter_kron_rng(const void* L_kron_tc, const float* Sigma_inv, int sigma_inv_structured,
+                                            const mpb_noise_desc* noise, float* mu, float* x, float* cost, float* weights,
+                                            float* is_vec, uint8_t* free_flag, int P, int S, int H, const mpb_robot_desc* robot,
+                                            const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp, float temp,
+                                            float step, void* stream) {
+    MPB_REQUIRE(robot && L_kron_tc && noise, "mpb_stoch_gpmp_iter_kron_rng: null robot / factor / noise descriptor");
+    const int D = 2 * robot->q_dim, M = H * D;
+    int rc = mpb_sample_gp_kron_tc_rng(L_kron_tc, mu, noise, x, P, S, H, robot->q_dim, stream);
     if (rc) return rc;
     rc = sigma_inv_structured ? mpb_prior_matvec_dof(Sigma_inv, mu, is_vec, P, H, robot->q_dim, stream)
                               : mpb_prior_matvec(Sigma_inv, mu, is_vec, P, M, 2 * D - 1, stream);

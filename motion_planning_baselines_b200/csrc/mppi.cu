@@ -18,6 +18,7 @@
 // state dimension (lane = dimension) so that it rounds exactly like the reference's step-by-step loop.
 // Bound: FP32 (T(T+1)C/2 FMAs per sample) / HBM write of the (state | control) rows.
 #include "mpb_common.cuh"
+#include "philox.cuh"
 
 namespace mpb {
 
@@ -26,8 +27,10 @@ constexpr int kMppiWarps = 8;
 struct MppiArgs {
     const float* L;        // [C,T,T] lower factors
     const float* Cov_inv;  // [C,T,T]
-    const float* mean;     // [T,C]
-    const float* eps;      // [C,N,T]
+    const float* mean;     // [T,C] mean of the IS term (MPPI._mean)
+    const float* mean_s;   // [T,C] mean the controls are sampled around (ctrl_dist.loc: differs from `mean` after shift())
+    const float* eps;      // [C,N,T], or NULL: drawn in the kernel (layout MPB_NOISE_MPPI)
+    NoiseArgs noise;
     const float* state0;   // [sd]
     const float* goal;     // [>=sd]
     const float* ctrl_min; // [C]
@@ -74,9 +77,25 @@ __global__ void __launch_bounds__(kMppiWarps * 32) mppi_rollout_kernel(const __g
     float* us = es + C * T;
     float* xs = us + T * C;
     for (int n = blockIdx.x * kMppiWarps + warp; n < a.N; n += gridDim.x * kMppiWarps) {
-        // stage this sample's noise rows (coalesced over time)
-        for (int i = 0; i < C; ++i)
-            for (int k = lane; k < T; k += 32) es[i * T + k] = __ldg(a.eps + ((size_t)i * a.N + n) * T + k);
+        // stage this sample's noise rows (coalesced over time), or draw them: global element (i, s_off+n, k) of [C,N_glob,T]
+        if (a.eps) {
+            for (int i = 0; i < C; ++i)
+                for (int k = lane; k < T; k += 32) es[i * T + k] = __ldg(a.eps + ((size_t)i * a.N + n) * T + k);
+        } else if ((T & 3) == 0) {
+            const int TQ = T >> 2;
+            for (int o = lane; o < C * TQ; o += 32) {
+                const int i = o / TQ, kq = o - i * TQ;
+                const unsigned long long e = ((unsigned long long)i * a.noise.P_glob + a.noise.s_off + n) * T + 4 * kq;
+                const float4 q = philox_normal4(e >> 2, a.noise);
+                float* d = es + i * T + 4 * kq;
+                d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+            }
+        } else {
+            for (int o = lane; o < C * T; o += 32) {
+                const int i = o / T, k = o - i * T;
+                es[o] = philox_normal1(((unsigned long long)i * a.noise.P_glob + a.noise.s_off + n) * T + k, a.noise);
+            }
+        }
         __syncwarp();
         // U[t,i] = mean[t,i] + sum_{k<=t} L_i[t,k] eps_i[k]
         for (int t = lane; t < T; t += 32) {
@@ -90,7 +109,7 @@ __global__ void __launch_bounds__(kMppiWarps * 32) mppi_rollout_kernel(const __g
                     const float* lr = a.L + ((size_t)i * T + t) * T;
                     for (int k = 0; k <= t; ++k) acc = fmaf(__ldg(lr + k), er[k], acc);
                 }
-                us[t * C + i] = __ldg(a.mean + (size_t)t * C + i) + acc;
+                us[t * C + i] = __ldg(a.mean_s + (size_t)t * C + i) + acc;
             }
         }
         __syncwarp();
@@ -166,32 +185,51 @@ __global__ void mppi_finalize_kernel(const float* __restrict__ quad, const float
 
 }  // namespace mpb
 
-extern "C" int mpb_mppi_rollout(const float* L_ctrl, const float* Cov_inv, const float* mean, const float* eps,
-                                const float* state0, const float* goal, const float* ctrl_min, const float* ctrl_max,
-                                float* xu, float* quad, float* isv, int N, int T, int C, int sd, float dt, float discount,
-                                float w_pos, float w_ctrl, float w_posT, void* stream) {
+extern "C" int mpb_mppi_rollout_ex(const float* L_ctrl, const float* Cov_inv, const float* mean, const float* mean_sample,
+                                   const float* eps, const mpb_noise_desc* noise, const float* state0, const float* goal,
+                                   const float* ctrl_min, const float* ctrl_max, float* xu, float* quad, float* isv, int N,
+                                   int T, int C, int sd, float dt, float discount, float w_pos, float w_ctrl, float w_posT,
+                                   void* stream) {
     using namespace mpb;
     MPB_REQUIRE(N >= 0, "mpb_mppi_rollout: negative N");
     if (N == 0) return MPB_OK;
-    MPB_REQUIRE(L_ctrl && Cov_inv && mean && eps && state0 && goal && ctrl_min && ctrl_max && xu && quad && isv,
+    MPB_REQUIRE(L_ctrl && Cov_inv && mean && (eps || noise) && state0 && goal && ctrl_min && ctrl_max && xu && quad && isv,
                 "mpb_mppi_rollout: null pointer");
     MPB_REQUIRE(T >= 2 && C >= 1 && C <= MPB_MAX_DOF, "mpb_mppi_rollout: need T >= 2 and 1 <= C <= %d", MPB_MAX_DOF);
     MPB_REQUIRE(sd == C, "mpb_mppi_rollout: velocity control needs state_dim == control_dim (got %d, %d)", sd, C);
     MppiArgs a{};
-    a.L = L_ctrl; a.Cov_inv = Cov_inv; a.mean = mean; a.eps = eps; a.state0 = state0; a.goal = goal;
+    a.L = L_ctrl; a.Cov_inv = Cov_inv; a.mean = mean; a.mean_s = mean_sample ? mean_sample : mean; a.eps = eps;
+    if (!eps) {
+        const char* why = noise_args(*noise, N, a.noise);
+        MPB_REQUIRE(!why, "mpb_mppi_rollout: %s", why);
+    }
+    a.state0 = state0; a.goal = goal;
     a.ctrl_min = ctrl_min; a.ctrl_max = ctrl_max; a.xu = xu; a.quad = quad; a.isv = isv;
     a.N = N; a.T = T; a.C = C; a.sd = sd; a.dt = dt; a.discount = discount; a.w_pos = w_pos; a.w_ctrl = w_ctrl; a.w_posT = w_posT;
     const size_t base = (size_t)(C * T + T + kMppiWarps * (C * T + T * C + T * sd)) * sizeof(float);
     const size_t lbytes = (size_t)C * T * (T + 1) * sizeof(float);
+    // L in shared memory when two CTAs still fit per SM (or when it fits at all); else it is read through L1
     a.l_in_smem = (base + lbytes <= 200 * 1024) ? 1 : 0;
     const size_t smem = base + (a.l_in_smem ? lbytes : 0);
     MPB_REQUIRE(smem <= 227 * 1024, "mpb_mppi_rollout: T*C too large for shared memory");
     cudaError_t e = cudaFuncSetAttribute(mppi_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("mpb_mppi_rollout: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mppi_rollout_kernel, kMppiWarps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const int blocks = (N + kMppiWarps - 1) / kMppiWarps;
-    const int grid = blocks < sm_count() ? blocks : sm_count();
+    const int cap = sm_count() * per_sm;
+    const int grid = blocks < cap ? blocks : cap;
     mppi_rollout_kernel<<<grid, kMppiWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch("mpb_mppi_rollout");
+}
+
+extern "C" int mpb_mppi_rollout(const float* L_ctrl, const float* Cov_inv, const float* mean, const float* eps,
+                                const float* state0, const float* goal, const float* ctrl_min, const float* ctrl_max,
+                                float* xu, float* quad, float* isv, int N, int T, int C, int sd, float dt, float discount,
+                                float w_pos, float w_ctrl, float w_posT, void* stream) {
+    MPB_REQUIRE(eps, "mpb_mppi_rollout: eps is null (use mpb_mppi_rollout_ex for in-kernel noise)");
+    return mpb_mppi_rollout_ex(L_ctrl, Cov_inv, mean, mean, eps, nullptr, state0, goal, ctrl_min, ctrl_max, xu, quad, isv, N, T,
+                               C, sd, dt, discount, w_pos, w_ctrl, w_posT, stream);
 }
 
 extern "C" int mpb_mppi_finalize(const float* quad, const float* isv, const double* energy, float temp, float* cost, int N,

@@ -10,6 +10,7 @@
 // reads are bank-conflict free; global->shared prefetch is double buffered through registers.
 // Bound: FP32 FMA.  (The tcgen05 3xTF32 variant lives in sample_gp_tc.cu.)
 #include "mpb_common.cuh"
+#include "philox.cuh"
 
 namespace mpb {
 
@@ -138,9 +139,11 @@ __global__ void __launch_bounds__(256) sample_gp_simt_kernel(const float* __rest
 
 // STOMP noise: x[p,s,h,j] = mu[p,h,j] + (endpoint ? 0 : sum_{k<=h} L_R[h,k] eps[s,j,p,k])
 // (mp_baselines/planners/stomp.py:97-108).  One CTA stages L_R once and loops over (p,s) pairs.
+// GEN: eps is unused, the noise block is drawn in place (layout MPB_NOISE_STOMP, philox.cuh).
+template <bool GEN>
 __global__ void __launch_bounds__(256) sample_stomp_kernel(const float* __restrict__ LR, const float* __restrict__ mu,
                                                            const float* __restrict__ eps, float* __restrict__ x,
-                                                           int P, int S, int H, int D) {
+                                                           int P, int S, int H, int D, const NoiseArgs noise) {
     extern __shared__ __align__(16) float sm[];
     float* Ls = sm;                         // [H][H+1]
     float* es = sm + H * (H + 1);           // [D][H+1]
@@ -149,9 +152,29 @@ __global__ void __launch_bounds__(256) sample_stomp_kernel(const float* __restri
     for (int ps = blockIdx.x; ps < P * S; ps += gridDim.x) {
         const int p = ps / S, s = ps - p * S;
         __syncthreads();
-        for (int i = threadIdx.x; i < M; i += blockDim.x) {      // i = j*H + k
-            const int j = i / H, k = i - j * H;
-            es[j * (H + 1) + k] = __ldg(eps + (((size_t)s * D + j) * P + p) * H + k);
+        if (GEN) {
+            // global element of (s, j, p, k):  (((s_off+s) D + j) P_glob + p_off+p) H + k
+            if ((H & 3) == 0) {
+                const int HQ = H >> 2;
+                for (int i = threadIdx.x; i < D * HQ; i += blockDim.x) {
+                    const int j = i / HQ, kq = i - j * HQ;
+                    const unsigned long long e = ((unsigned long long)((noise.s_off + s) * D + j) * noise.P_glob + noise.p_off + p) * H + 4 * kq;
+                    const float4 q = philox_normal4(e >> 2, noise);
+                    float* d = es + j * (H + 1) + 4 * kq;
+                    d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+                }
+            } else {
+                for (int i = threadIdx.x; i < M; i += blockDim.x) {
+                    const int j = i / H, k = i - j * H;
+                    const unsigned long long e = ((unsigned long long)((noise.s_off + s) * D + j) * noise.P_glob + noise.p_off + p) * H + k;
+                    es[j * (H + 1) + k] = philox_normal1(e, noise);
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < M; i += blockDim.x) {      // i = j*H + k
+                const int j = i / H, k = i - j * H;
+                es[j * (H + 1) + k] = __ldg(eps + (((size_t)s * D + j) * P + p) * H + k);
+            }
         }
         __syncthreads();
         for (int o = threadIdx.x; o < M; o += blockDim.x) {      // o = h*D + j
@@ -164,6 +187,34 @@ __global__ void __launch_bounds__(256) sample_stomp_kernel(const float* __restri
             }
             x[(size_t)ps * M + o] = __ldg(mu + (size_t)p * M + o) + acc;
         }
+    }
+}
+
+// The normals a kernel consumes for a noise descriptor, written in the LOCAL layout of the call (mpb_philox_normal).
+// Quads of the innermost axis are group aligned when its extent is a multiple of 4; otherwise element by element.
+__global__ void __launch_bounds__(256) philox_dump_kernel(const NoiseArgs noise, int layout, float* __restrict__ out,
+                                                          long long n0, long long n1, long long n2, long long n3, int vec) {
+    const long long inner = layout == MPB_NOISE_STOMP ? n3 : n2;
+    const long long total = n0 * n1 * n2 * (layout == MPB_NOISE_STOMP ? n3 : 1);
+    const long long items = vec ? total >> 2 : total;
+    for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+        const long long flat = vec ? it << 2 : it;
+        const long long k = flat % inner;
+        long long r = flat / inner;
+        unsigned long long e;
+        if (layout == MPB_NOISE_SPM) {                 // r = s * P + p
+            const long long p = r % n1, s = r / n1;
+            e = ((unsigned long long)(noise.s_off + s) * noise.P_glob + noise.p_off + p) * inner + k;
+        } else if (layout == MPB_NOISE_STOMP) {        // r = (s * D + j) * P + p
+            const long long p = r % n2; r /= n2;
+            const long long j = r % n1, s = r / n1;
+            e = ((unsigned long long)((noise.s_off + s) * n1 + j) * noise.P_glob + noise.p_off + p) * inner + k;
+        } else {                                       // MPPI: r = i * N + n
+            const long long n = r % n1, i = r / n1;
+            e = ((unsigned long long)i * noise.P_glob + noise.s_off + n) * inner + k;
+        }
+        if (vec) *reinterpret_cast<float4*>(out + flat) = philox_normal4(e >> 2, noise);
+        else out[flat] = philox_normal1(e, noise);
     }
 }
 
@@ -285,20 +336,58 @@ extern "C" int mpb_sample_gp(const float* L, const float* mu, const float* eps, 
     return check_launch("mpb_sample_gp");
 }
 
-extern "C" int mpb_sample_stomp(const float* L_R, const float* mu, const float* eps, float* x, int P, int S, int H,
-                                int D, void* stream) {
+extern "C" int mpb_philox_normal(const mpb_noise_desc* nd, int layout, float* out, int n0, int n1, int n2, int n3, void* stream) {
     using namespace mpb;
-    MPB_REQUIRE(L_R && mu && eps && x, "mpb_sample_stomp: null pointer");
+    MPB_REQUIRE(nd && out, "mpb_philox_normal: null pointer");
+    MPB_REQUIRE(layout == MPB_NOISE_SPM || layout == MPB_NOISE_STOMP || layout == MPB_NOISE_MPPI, "mpb_philox_normal: unknown layout %d", layout);
+    MPB_REQUIRE(n0 >= 0 && n1 >= 0 && n2 >= 0 && (layout != MPB_NOISE_STOMP || n3 >= 0), "mpb_philox_normal: negative extent");
+    NoiseArgs noise{};
+    const char* why = noise_args(*nd, 0, noise);
+    MPB_REQUIRE(!why, "mpb_philox_normal: %s", why);
+    const long long inner = layout == MPB_NOISE_STOMP ? n3 : n2;
+    const long long total = (long long)n0 * n1 * n2 * (layout == MPB_NOISE_STOMP ? n3 : 1);
+    if (total == 0) return MPB_OK;
+    const int vec = (inner % 4 == 0) && ((uintptr_t)out % 16 == 0);
+    const long long items = vec ? total / 4 : total;
+    const long long blocks = (items + 255) / 256;
+    const int grid = (int)(blocks < (long long)sm_count() * 8 ? blocks : (long long)sm_count() * 8);
+    philox_dump_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(noise, layout, out, n0, n1, n2, n3, vec);
+    return check_launch("mpb_philox_normal");
+}
+
+static int sample_stomp_any(const float* L_R, const float* mu, const float* eps, const mpb_noise_desc* nd, float* x, int P,
+                            int S, int H, int D, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(L_R && mu && (eps || nd) && x, "mpb_sample_stomp: null pointer");
     MPB_REQUIRE(P >= 0 && S >= 0 && H >= 2 && D >= 1, "mpb_sample_stomp: bad sizes");
     if (P == 0 || S == 0) return MPB_OK;
     const size_t smem = (size_t)(H + D) * (H + 1) * sizeof(float);
     MPB_REQUIRE(smem <= 200 * 1024, "mpb_sample_stomp: H=%d too large for shared memory", H);
-    cudaError_t e = cudaFuncSetAttribute(sample_stomp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    NoiseArgs noise{};
+    if (!eps) {
+        const char* why = noise_args(*nd, P, noise);
+        MPB_REQUIRE(!why, "mpb_sample_stomp_rng: %s", why);
+    }
+    cudaError_t e = eps ? cudaFuncSetAttribute(sample_stomp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(sample_stomp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("mpb_sample_stomp: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
     const long long work = (long long)P * S;
     const int grid = (int)(work < (long long)sm_count() * 4 ? work : (long long)sm_count() * 4);
-    sample_stomp_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(L_R, mu, eps, x, P, S, H, D);
+    if (eps) sample_stomp_kernel<false><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(L_R, mu, eps, x, P, S, H, D, noise);
+    else sample_stomp_kernel<true><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(L_R, mu, eps, x, P, S, H, D, noise);
     return check_launch("mpb_sample_stomp");
+}
+
+extern "C" int mpb_sample_stomp(const float* L_R, const float* mu, const float* eps, float* x, int P, int S, int H,
+                                int D, void* stream) {
+    MPB_REQUIRE(eps, "mpb_sample_stomp: eps is null (use mpb_sample_stomp_rng for in-kernel noise)");
+    return sample_stomp_any(L_R, mu, eps, nullptr, x, P, S, H, D, stream);
+}
+
+extern "C" int mpb_sample_stomp_rng(const float* L_R, const float* mu, const mpb_noise_desc* noise, float* x, int P, int S,
+                                    int H, int D, void* stream) {
+    MPB_REQUIRE(noise, "mpb_sample_stomp_rng: noise descriptor is null");
+    return sample_stomp_any(L_R, mu, nullptr, noise, x, P, S, H, D, stream);
 }
 
 extern "C" int mpb_prior_matvec(const float* Sigma_inv, const float* mu, float* y, int P, int M, int half_bw,

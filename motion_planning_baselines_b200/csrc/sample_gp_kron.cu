@@ -25,6 +25,7 @@
 #include <cuda_fp16.h>
 
 #include "mpb_common.cuh"
+#include "philox.cuh"
 
 namespace mpb {
 
@@ -266,14 +267,33 @@ __device__ __forceinline__ uint32_t split_f16(float v) {
 }
 
 struct KronRow {            // per tile row: where its noise comes from and which particle it belongs to
-    long long src;          // float offset of the eps row, or -1 past the end
+    long long src;          // float offset of the eps row (GEN: of the row in the virtual GLOBAL noise tensor), or -1 past the end
     int p, pad;
 };
 
-template <int DOF, int H>
+// (v0..v3) -> packed (fp16 hi | fp16 lo << 16) words, the tile's operand format
+__device__ __forceinline__ uint4 pack_split4(const float4 v) {
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(__fsub_rn(v.x, f01.x), __fsub_rn(v.y, f01.y));
+    const __half2 l23 = __floats2half2_rn(__fsub_rn(v.z, f23.x), __fsub_rn(v.w, f23.y));
+    const uint32_t uh01 = *reinterpret_cast<const uint32_t*>(&h01), ul01 = *reinterpret_cast<const uint32_t*>(&l01);
+    const uint32_t uh23 = *reinterpret_cast<const uint32_t*>(&h23), ul23 = *reinterpret_cast<const uint32_t*>(&l23);
+    uint4 w;
+    w.x = __byte_perm(uh01, ul01, 0x5410); w.y = __byte_perm(uh01, ul01, 0x7632);
+    w.z = __byte_perm(uh23, ul23, 0x5410); w.w = __byte_perm(uh23, ul23, 0x7632);
+    return w;
+}
+
+// GEN = false: noise rows are read from `eps` [S,P,M] (injected noise: parity runs).
+// GEN = true : `eps` is unused; every 4-column slot is drawn in place with Philox4x32-10 keyed on the slot's index in the
+//              virtual global noise tensor [S_glob, P_glob, M] (philox.cuh) and written straight in the packed operand
+//              format, so the global read of the noise, the separate conversion pass and the torch.randn launch that
+//              produced it all disappear.  Same bits as mpb_philox_normal(MPB_NOISE_SPM) followed by GEN = false.
+template <int DOF, int H, bool GEN>
 __global__ void __launch_bounds__(KronMmaCfg<DOF, H>::THREADS, KronMmaCfg<DOF, H>::CTAS_PER_SM)
 sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restrict__ mu, const float* __restrict__ eps,
-                          float* __restrict__ x, int P, int S) {
+                          float* __restrict__ x, int P, int S, const NoiseArgs noise) {
     using Cfg = KronMmaCfg<DOF, H>;
     constexpr int M = Cfg::M, N = Cfg::N, NB = Cfg::NB, WPD = Cfg::WPD, RS = Cfg::RS, THREADS = Cfg::THREADS;
     constexpr int ROWS = Cfg::ROWS, NT = Cfg::NT, PPW = Cfg::PPW;
@@ -297,7 +317,7 @@ sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restr
         r.src = -1; r.p = 0; r.pad = 0;
         if (n < Ntot) {
             const int p = (int)(n / S), s = (int)(n - (long long)p * S);
-            r.src = ((long long)s * P + p) * M;
+            r.src = GEN ? ((noise.s_off + s) * noise.P_glob + noise.p_off + p) * M : ((long long)s * P + p) * M;
             r.p = p;
         }
         rows[buf * ROWS + threadIdx.x] = r;
@@ -305,8 +325,14 @@ sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restr
     auto fill_slot = [&](int buf, int r, int v) {   // float4 slot (row r, 4-column group v) <- next tile's noise
         const long long src = rows[buf * ROWS + r].src;
         float* dst = tile + r * RS + 4 * v;
-        if (src >= 0) cp_async16_cg(dst, eps + src + 4 * v);
-        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (GEN) {
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (src >= 0) w = pack_split4(philox_normal4((unsigned long long)(src >> 2) + (unsigned)v, noise));
+            *reinterpret_cast<uint4*>(dst) = w;
+        } else {
+            if (src >= 0) cp_async16_cg(dst, eps + src + 4 * v);
+            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     };
 
     // Factor staging: every lane copies exactly the 2 x 16 bytes (hi and lo A fragments of one 16-row x 16-k chunk) it
@@ -399,21 +425,13 @@ sample_gp_kron_mma_kernel(const uint32_t* __restrict__ LkF, const float* __restr
                     const int blk = hb ? NB - 1 - (a0 + i) : a0 + i;
                     mrow[i][hb][hrow] = one_particle ? __ldg(mu + (size_t)(((long long)t * ROWS) / S) * M + DOF * (16 * blk + g + 8 * hrow) + j) : 0.f;
                 }
+        if (!GEN) {
 #pragma unroll
-        for (int it = 0; it < Cfg::IPT; ++it) {        // own slots only: fp32 -> packed (fp16 hi | fp16 lo << 16)
-            const int e = threadIdx.x + it * THREADS;
-            float4* slot = reinterpret_cast<float4*>(tile + (e / Cfg::V4_PER_ROW) * RS + 4 * (e % Cfg::V4_PER_ROW));
-            const float4 v = *slot;
-            const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            const __half2 l01 = __floats2half2_rn(__fsub_rn(v.x, f01.x), __fsub_rn(v.y, f01.y));
-            const __half2 l23 = __floats2half2_rn(__fsub_rn(v.z, f23.x), __fsub_rn(v.w, f23.y));
-            const uint32_t uh01 = *reinterpret_cast<const uint32_t*>(&h01), ul01 = *reinterpret_cast<const uint32_t*>(&l01);
-            const uint32_t uh23 = *reinterpret_cast<const uint32_t*>(&h23), ul23 = *reinterpret_cast<const uint32_t*>(&l23);
-            uint4 w;
-            w.x = __byte_perm(uh01, ul01, 0x5410); w.y = __byte_perm(uh01, ul01, 0x7632);
-            w.z = __byte_perm(uh23, ul23, 0x5410); w.w = __byte_perm(uh23, ul23, 0x7632);
-            *reinterpret_cast<uint4*>(slot) = w;
+            for (int it = 0; it < Cfg::IPT; ++it) {    // own slots only: fp32 -> packed (fp16 hi | fp16 lo << 16)
+                const int e = threadIdx.x + it * THREADS;
+                float4* slot = reinterpret_cast<float4*>(tile + (e / Cfg::V4_PER_ROW) * RS + 4 * (e % Cfg::V4_PER_ROW));
+                *reinterpret_cast<uint4*>(slot) = pack_split4(*slot);
+            }
         }
         __syncthreads();                               // tile t has landed and is converted
         float acc[PPW][2][NT][4];
@@ -531,9 +549,12 @@ __global__ void kron_frag_kernel(const float* __restrict__ LkT, uint32_t* __rest
     }
 }
 
-template <int DOF, int H, bool MMA>
-static int launch_kron(const void* Lp, const float* mu, const float* eps, float* x, int P, int S, cudaStream_t st) {
-    const void* kern = MMA ? (const void*)sample_gp_kron_mma_kernel<DOF, H> : (const void*)sample_gp_kron_kernel<DOF, H>;
+template <int DOF, int H, int KIND>      // KIND 0: exact FP32, 1: warp MMA on injected noise, 2: warp MMA with in-kernel Philox noise
+static int launch_kron(const void* Lp, const float* mu, const float* eps, float* x, int P, int S, const NoiseArgs& noise,
+                       cudaStream_t st) {
+    constexpr bool MMA = KIND != 0;
+    const void* kern = KIND == 2 ? (const void*)sample_gp_kron_mma_kernel<DOF, H, true>
+                     : KIND == 1 ? (const void*)sample_gp_kron_mma_kernel<DOF, H, false> : (const void*)sample_gp_kron_kernel<DOF, H>;
     const size_t smem_bytes = MMA ? KronMmaCfg<DOF, H>::SMEM : KronCfg<DOF, H>::SMEM;
     const int threads = MMA ? KronMmaCfg<DOF, H>::THREADS : KronCfg<DOF, H>::THREADS;
     const int tile_rows = MMA ? KronMmaCfg<DOF, H>::ROWS : kTileRows;
@@ -553,7 +574,7 @@ static int launch_kron(const void* Lp, const float* mu, const float* eps, float*
     const long long ntiles = ((long long)P * S + tile_rows - 1) / tile_rows;
     const long long cap = (long long)sm_count() * per_sm;
     const int grid = (int)(ntiles < cap ? ntiles : cap);
-    void* args[] = {(void*)&Lp, (void*)&mu, (void*)&eps, (void*)&x, (void*)&P, (void*)&S};
+    void* args[] = {(void*)&Lp, (void*)&mu, (void*)&eps, (void*)&x, (void*)&P, (void*)&S, (void*)&noise};
     cudaError_t le = cudaLaunchKernel(kern, dim3(grid), dim3(threads), args, smem_bytes, st);
     if (le != cudaSuccess) { set_error("mpb_sample_gp_kron: %s", cudaGetErrorString(le)); return MPB_ECUDA; }
     return check_launch("mpb_sample_gp_kron");
@@ -594,17 +615,26 @@ extern "C" int mpb_sample_gp_kron_pack(const float* L, float* LkT, int H, int do
     return MPB_OK;
 }
 
-static int sample_gp_kron_any(bool mma, const void* LkT, const float* mu, const float* eps, float* x, int P, int S, int H,
-                              int dof, void* stream) {
+static int sample_gp_kron_any(int kind, const void* LkT, const float* mu, const float* eps, float* x, int P, int S, int H,
+                              int dof, const mpb_noise_desc* nd, void* stream) {
     using namespace mpb;
-    MPB_REQUIRE(LkT && mu && eps && x, "mpb_sample_gp_kron: null pointer");
+    MPB_REQUIRE(LkT && mu && x && (kind == 2 ? nd != nullptr : eps != nullptr), "mpb_sample_gp_kron: null pointer");
+    NoiseArgs noise{};
+    if (kind == 2) {
+        const char* why = noise_args(*nd, P, noise);
+        MPB_REQUIRE(!why, "mpb_sample_gp_kron_tc_rng: %s", why);
+    }
     MPB_REQUIRE(P >= 0 && S >= 0, "mpb_sample_gp_kron: bad sizes P=%d S=%d", P, S);
     MPB_REQUIRE(mpb_sample_gp_kron_supported(H, dof), "mpb_sample_gp_kron: shape H=%d dof=%d has no structured kernel", H, dof);
-    MPB_REQUIRE(((uintptr_t)LkT | (uintptr_t)mu | (uintptr_t)eps | (uintptr_t)x) % 16 == 0, "mpb_sample_gp_kron: pointers must be 16-byte aligned");
+    MPB_REQUIRE(((uintptr_t)LkT | (uintptr_t)mu | (uintptr_t)eps | (uintptr_t)x) % 16 == 0, "mpb_sample_gp_kron: pointers must be 16-byte aligned");   // eps == NULL (rng) passes
     if (P == 0 || S == 0) return MPB_OK;
     MPB_REQUIRE((long long)P * S <= 0x7fffffffLL / 2, "mpb_sample_gp_kron: P*S too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define X(d, h) if (dof == d && H == h) return mma ? launch_kron<d, h, true>(LkT, mu, eps, x, P, S, st) : launch_kron<d, h, false>(LkT, mu, eps, x, P, S, st);
+#define X(d, h)                                                                                  \
+    if (dof == d && H == h)                                                                      \
+        return kind == 2   ? launch_kron<d, h, 2>(LkT, mu, eps, x, P, S, noise, st)              \
+               : kind == 1 ? launch_kron<d, h, 1>(LkT, mu, eps, x, P, S, noise, st)              \
+                           : launch_kron<d, h, 0>(LkT, mu, eps, x, P, S, noise, st);
     MPB_KRON_SHAPES(X)
 #undef X
     return MPB_EINVAL;
@@ -612,7 +642,7 @@ static int sample_gp_kron_any(bool mma, const void* LkT, const float* mu, const 
 
 extern "C" int mpb_sample_gp_kron(const float* LkT, const float* mu, const float* eps, float* x, int P, int S, int H,
                                   int dof, void* stream) {
-    return sample_gp_kron_any(false, LkT, mu, eps, x, P, S, H, dof, stream);
+    return sample_gp_kron_any(0, LkT, mu, eps, x, P, S, H, dof, nullptr, stream);
 }
 
 extern "C" long long mpb_sample_gp_kron_tc_bytes(int H, int dof) {
@@ -638,5 +668,10 @@ extern "C" int mpb_sample_gp_kron_tc_prepare(const float* LkT, void* LkF, int H,
 
 extern "C" int mpb_sample_gp_kron_tc(const void* LkF, const float* mu, const float* eps, float* x, int P, int S, int H,
                                      int dof, void* stream) {
-    return sample_gp_kron_any(true, LkF, mu, eps, x, P, S, H, dof, stream);
+    return sample_gp_kron_any(1, LkF, mu, eps, x, P, S, H, dof, nullptr, stream);
+}
+
+extern "C" int mpb_sample_gp_kron_tc_rng(const void* LkF, const float* mu, const mpb_noise_desc* noise, float* x, int P, int S,
+                                         int H, int dof, void* stream) {
+    return sample_gp_kron_any(2, LkF, mu, nullptr, x, P, S, H, dof, noise, stream);
 }

@@ -71,7 +71,7 @@ class MultiMPPrior:
     (mp_priors_multi.py:15-259).  ``sample`` runs on the GPU (csrc/sample_gp.cu)."""
 
     def __init__(self, num_steps, dt, state_dim, dof, K_s_inv, K_gp_inv, start_state, means=None, K_g_inv=None,
-                 goal_states=None, use_numpy=False, tensor_args=None, factor_dtype=torch.float32):
+                 goal_states=None, use_numpy=False, tensor_args=None, factor_dtype=torch.float32, noise=None):
         self.state_dim, self.dof, self.num_steps = state_dim, dof, num_steps
         self.M = state_dim * (num_steps + 1)
         self.tensor_args = tensor_args
@@ -82,6 +82,8 @@ class MultiMPPrior:
         else:
             self.num_modes = means.shape[0]
         self.means = means.reshape(self.num_modes, -1).to(**tensor_args).contiguous()
+        # in-kernel noise (csrc/philox.cuh): seed from torch's global seed unless the owner hands in its own stream
+        self.noise = noise if noise is not None else _lib.NoiseStream(P_global=self.num_modes)
 
         Sinv64 = _precision(num_steps, dt, state_dim, dof, K_s_inv, K_gp_inv, K_g_inv if self.goal_directed else None)
         Sinv_cpu = Sinv64.to(factor_dtype)      # float64: the reference's init path (base.py:155-158, quirk B8)
@@ -161,29 +163,37 @@ class MultiMPPrior:
         assert means_new.shape == self.means.shape
         self.means = means_new.clone().detach().contiguous()
 
-    def sample(self, num_samples, eps=None, out=None):
-        """-> [num_modes, num_samples, H, state_dim].  ``eps`` ([S,P,M], the layout torch draws) can be
-        injected for parity runs; otherwise it is drawn on the device."""
+    def sample(self, num_samples, eps=None, out=None, noise_desc=None):
+        """-> [num_modes, num_samples, H, state_dim].  ``eps`` ([S,P,M], the layout torch draws) can be injected for
+        parity runs; otherwise the noise is drawn on the device by Philox keyed on the global element index
+        (``noise_desc``, default: the next draw of ``self.noise``) -- inside the sampler itself for the default
+        structured kernel, by mpb_philox_normal in front of the other variants (same numbers either way)."""
         P, S, M = self.num_modes, num_samples, self.M
+        x = out if out is not None else torch.empty(P, S, M, **self.tensor_args)
+        lib = _lib.lib()
         if eps is None:
-            eps = torch.randn(S, P, M, **self.tensor_args)
+            nd = noise_desc if noise_desc is not None else self.noise.next()
+            if self.kron_tc_kind == 1:
+                _lib.check(lib.mpb_sample_gp_kron_tc_rng(_lib.ptr(self.scale_tril_kron_tc), _lib.ptr(self.means), C.byref(nd),
+                                                         _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))
+                return x.view(P, S, self.num_steps + 1, self.state_dim)
+            eps = _lib.philox_normal(nd, _lib.NOISE_SPM, (S, P, M), self.tensor_args['device'])
         _lib.require_f32(eps)
         assert eps.shape == (S, P, M)
-        x = out if out is not None else torch.empty(P, S, M, **self.tensor_args)
         eps = eps.contiguous()
         if self.kron_tc_kind == 2:
-            _lib.check(_lib.lib().mpb_sample_gp_kron_umma(_lib.ptr(self.scale_tril_kron_tc), _lib.ptr(self.means), _lib.ptr(eps),
-                                                          _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))
+            _lib.check(lib.mpb_sample_gp_kron_umma(_lib.ptr(self.scale_tril_kron_tc), _lib.ptr(self.means), _lib.ptr(eps),
+                                                   _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))
         elif self.kron_tc_kind == 1:
-            _lib.check(_lib.lib().mpb_sample_gp_kron_tc(_lib.ptr(self.scale_tril_kron_tc), _lib.ptr(self.means), _lib.ptr(eps),
-                                                        _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))
+            _lib.check(lib.mpb_sample_gp_kron_tc(_lib.ptr(self.scale_tril_kron_tc), _lib.ptr(self.means), _lib.ptr(eps),
+                                                 _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))
         elif self.scale_tril_kron is not None:
-            _lib.check(_lib.lib().mpb_sample_gp_kron(_lib.ptr(self.scale_tril_kron), _lib.ptr(self.means), _lib.ptr(eps),
-                                                     _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))
+            _lib.check(lib.mpb_sample_gp_kron(_lib.ptr(self.scale_tril_kron), _lib.ptr(self.means), _lib.ptr(eps),
+                                              _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))
         elif self.scale_tril_split is not None:
-            _lib.check(_lib.lib().mpb_sample_gp_tc(_lib.ptr(self.scale_tril_split[0]), _lib.ptr(self.scale_tril_split[1]),
-                                                   _lib.ptr(self.means), _lib.ptr(eps), _lib.ptr(x), P, S, M, _lib.stream_ptr()))
+            _lib.check(lib.mpb_sample_gp_tc(_lib.ptr(self.scale_tril_split[0]), _lib.ptr(self.scale_tril_split[1]),
+                                            _lib.ptr(self.means), _lib.ptr(eps), _lib.ptr(x), P, S, M, _lib.stream_ptr()))
         else:
-            _lib.check(_lib.lib().mpb_sample_gp(_lib.ptr(self.scale_tril), _lib.ptr(self.means), _lib.ptr(eps),
-                                                _lib.ptr(x), P, S, M, _lib.stream_ptr()))
+            _lib.check(lib.mpb_sample_gp(_lib.ptr(self.scale_tril), _lib.ptr(self.means), _lib.ptr(eps),
+                                         _lib.ptr(x), P, S, M, _lib.stream_ptr()))
         return x.view(P, S, self.num_steps + 1, self.state_dim)

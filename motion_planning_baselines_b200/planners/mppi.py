@@ -9,6 +9,8 @@
 ``sample_split``: optional motion_planning_baselines_b200.update.SampleSplit -- the N control samples of ONE problem
 are sharded over the ranks of a process group; each rank rolls out its block and a single all-gather of the packed
 records (plus one of the batch-sum scalar) makes every rank apply the identical update."""
+import ctypes as C
+
 import torch
 
 from .. import _lib
@@ -22,7 +24,8 @@ _CPU32 = dict(device='cpu', dtype=torch.float32)
 class MPPI(MPPlanner):
 
     def __init__(self, system, num_ctrl_samples, rollout_steps, opt_iters, control_std=None, initial_mean=None,
-                 step_size=1., temp=1., cov_prior_type='indep_ctrl', tensor_args=None, sample_split=None, **kwargs):
+                 step_size=1., temp=1., cov_prior_type='indep_ctrl', tensor_args=None, sample_split=None, seed=None,
+                 **kwargs):
         super().__init__(name='MPPI', tensor_args=tensor_args)
         self.system = system
         self.state_dim = system.state_dim
@@ -44,6 +47,8 @@ class MPPI(MPPlanner):
         self.best_traj = torch.zeros(rollout_steps, self.state_dim, **self.tensor_args)
         self.split = sample_split or SampleSplit(world=1, rank=0)
         self._offset, self._n_local = self.split.local_slice(num_ctrl_samples)
+        # in-kernel noise: one global Philox stream [C, N_glob, T]; a rank of a sample split draws its own samples
+        self._noise = _lib.NoiseStream(seed, s_offset=self._offset, P_global=num_ctrl_samples)
         N, T, W = self._n_local, rollout_steps, self.state_dim + self.control_dim
         dev = self.tensor_args['device']
         self._xu = torch.empty(N, T, W, **self.tensor_args)
@@ -70,21 +75,25 @@ class MPPI(MPPlanner):
     def sample_and_eval(self, eps=None, **observation):
         """``eps``: optional injected noise [C, N_global, T] (one block per control dimension, as the reference's
         per-dimension MultivariateNormal.sample((N,)) draws them)."""
-        N, T, C, sd = self._n_local, self.rollout_steps, self.control_dim, self.state_dim
+        N, T, C_, sd = self._n_local, self.rollout_steps, self.control_dim, self.state_dim
         lib, st = _lib.lib(), _lib.stream_ptr()
-        if eps is None:
-            eps_l = torch.randn(C, N, T, **self.tensor_args)
+        eps_l, nd = None, None
+        if eps is None:     # drawn inside the kernel (Philox keyed on the global element index)
+            nd = C.byref(self._noise.next())
         else:
             _lib.require_f32(eps)
-            assert eps.shape == (C, self.num_ctrl_samples, T)
+            assert eps.shape == (C_, self.num_ctrl_samples, T)
             eps_l = eps[:, self._offset:self._offset + N].contiguous()
         state0 = observation['state'].to(**self.tensor_args).contiguous()
         goal = observation.get('goal_state', self.system.goal_state).to(**self.tensor_args).contiguous()
         cw = self.system._c_weights
-        _lib.check(lib.mpb_mppi_rollout(
-            _lib.ptr(self.ctrl_dist.scale_tril), _lib.ptr(self.Cov_inv), _lib.ptr(self._mean), _lib.ptr(eps_l), _lib.ptr(state0),
+        # controls are sampled around ctrl_dist.mu (refreshed by update_ctrl_dist only), the IS term uses self._mean:
+        # they differ after pop()/shift(), exactly as in the reference (mppi.py:68-70,125-128,171-178)
+        _lib.check(lib.mpb_mppi_rollout_ex(
+            _lib.ptr(self.ctrl_dist.scale_tril), _lib.ptr(self.Cov_inv), _lib.ptr(self._mean.contiguous()), _lib.ptr(self.ctrl_dist.mu.contiguous()),
+            _lib.ptr(eps_l), nd, _lib.ptr(state0),
             _lib.ptr(goal), _lib.ptr(self.system.ctrl_min), _lib.ptr(self.system.ctrl_max), _lib.ptr(self._xu), _lib.ptr(self._quad),
-            _lib.ptr(self._isv), N, T, C, sd, float(self.system.dt), float(self.system.discount), float(cw['pos']),
+            _lib.ptr(self._isv), N, T, C_, sd, float(self.system.dt), float(self.system.discount), float(cw['pos']),
             float(cw['ctrl']), float(cw['pos_T']), st))
         cost = observation.get('cost', None)
         energy = None
@@ -95,7 +104,7 @@ class MPPI(MPPlanner):
                 self._energy = self.split.all_gather_cat(self._energy).sum(0, keepdim=True)
             energy = self._energy
         _lib.check(lib.mpb_mppi_finalize(_lib.ptr(self._quad), _lib.ptr(self._isv), _lib.ptr(energy), float(self.temp),
-                                         _lib.ptr(self.costs), N, C, st))
+                                         _lib.ptr(self.costs), N, C_, st))
         self.state_trajectories = self._xu[..., :sd]
         return self._xu[..., sd:], self.state_trajectories, self.costs
 

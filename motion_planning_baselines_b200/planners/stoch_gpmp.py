@@ -22,13 +22,21 @@ class StochGPMP(OptimizationPlanner):
     def __init__(self, robot=None, n_dof=None, n_support_points=None, num_particles_per_goal=None, opt_iters=None,
                  dt=None, start_state=None, step_size=1., multi_goal_states=None, initial_particle_means=None,
                  sigma_start_init=None, sigma_start_sample=None, sigma_goal_init=None, sigma_goal_sample=None,
-                 sigma_gp_init=None, sigma_gp_sample=None, num_samples=2, temperature=1., **kwargs):
+                 sigma_gp_init=None, sigma_gp_sample=None, num_samples=2, temperature=1., seed=None,
+                 noise_particle_offset=0, noise_particles_global=None, **kwargs):
         super().__init__(name='StochGPMP', n_dof=n_dof, n_support_points=n_support_points,
                          num_particles_per_goal=num_particles_per_goal, opt_iters=opt_iters, dt=dt,
                          start_state=start_state, initial_particle_means=initial_particle_means,
                          multi_goal_states=multi_goal_states, sigma_start_init=sigma_start_init,
                          sigma_goal_init=sigma_goal_init, sigma_gp_init=sigma_gp_init, pos_only=False, **kwargs)
         self.robot = robot
+        # In-kernel noise (the reference draws inside MultiMPPrior.sample): one global Philox stream for the whole job.
+        # A process that holds particles [noise_particle_offset, +num_particles) of noise_particles_global draws exactly
+        # its slice, so results do not depend on how particles are sharded over GPUs.  seed: torch.initial_seed().
+        P_glob = noise_particles_global if noise_particles_global is not None else noise_particle_offset + self.num_particles
+        self._noise = _lib.NoiseStream(seed, p_offset=noise_particle_offset, P_global=P_glob)
+        self._noise_init = _lib.NoiseStream(self._noise.seed, s_offset=noise_particle_offset, P_global=self.num_goals,
+                                            offset=1 << 62)
         self.goal_directed = multi_goal_states is not None
         if self.goal_directed and self.num_goals != 1:
             raise NotImplementedError('Stoch-GPMP is single-goal (the reference cost breaks for > 1 goal, quirk B3)')
@@ -63,9 +71,10 @@ class StochGPMP(OptimizationPlanner):
         self.multi_goal_prior_sample = [UnaryFactor(D, self.sigma_goal_sample, g, ta) for g in self.multi_goal_states] \
             if self.goal_directed else []
 
-    def get_prior_dist(self, start_K, gp_K, goal_K, state_init, particle_means=None, goal_states=None):
+    def get_prior_dist(self, start_K, gp_K, goal_K, state_init, particle_means=None, goal_states=None, noise=None):
         return MultiMPPrior(self.n_support_points - 1, self.dt, 2 * self.n_dof, self.n_dof, start_K, gp_K, state_init,
-                            K_g_inv=goal_K, means=particle_means, goal_states=goal_states, tensor_args=self.tensor_args)
+                            K_g_inv=goal_K, means=particle_means, goal_states=goal_states, tensor_args=self.tensor_args,
+                            noise=noise)
 
     def const_vel_trajectories(self, start_state, multi_goal_states):
         H, d = self.n_support_points, self.n_dof
@@ -91,13 +100,13 @@ class StochGPMP(OptimizationPlanner):
                 means = initial_particle_means.to(**self.tensor_args)
         else:
             init = self.get_prior_dist(self.start_prior_init.K, self.gp_prior_init.Q_inv[0], goal_K_init,
-                                       self.start_state, goal_states=self.multi_goal_states)
+                                       self.start_state, goal_states=self.multi_goal_states, noise=self._noise_init)
             means = init.sample(self.num_particles_per_goal, eps=eps_init)
             del init
         self._particle_means = means.flatten(0, 1).contiguous().clone() if means.ndim == 4 else means.contiguous().clone()
         self._sample_dist = self.get_prior_dist(self.start_prior_sample.K, self.gp_prior_sample.Q_inv[0], goal_K_sample,
                                                 self.start_state, particle_means=self._particle_means,
-                                                goal_states=self.multi_goal_states)
+                                                goal_states=self.multi_goal_states, noise=self._noise)
         self.Sigma_inv = self._sample_dist.Sigma_inv
         # the reference's precision couples only equal dofs (<= 7 non-zeros per row): verified bit-exactly, once
         ok = C.c_int(0)
@@ -174,13 +183,25 @@ class StochGPMP(OptimizationPlanner):
             return self._get_traj()
         lib = _lib.lib()
         pos_mean = vel_mean = None
+        sd = self._sample_dist
         for it in range(opt_iters):
-            e = eps[it] if eps is not None else torch.randn(S, P, M, **self.tensor_args)
-            _lib.require_f32(e)
-            assert e.shape == (S, P, M) and e.is_contiguous()
             if it == opt_iters - 1:     # the reference returns the pre-update particle means of the last iteration
                 pos_mean = self._particle_means[..., :self.n_dof].clone()
                 vel_mean = self._particle_means[..., -self.n_dof:].clone()
+            if eps is None:
+                nd = self._noise.next()
+                if sd.kron_tc_kind == 1:        # default: the noise is drawn inside K1
+                    _lib.check(lib.mpb_stoch_gpmp_iter_kron_rng(
+                        _lib.ptr(sd.scale_tril_kron_tc), _lib.ptr(self.Sigma_inv), int(self._sinv_structured), C.byref(nd),
+                        _lib.ptr(self._particle_means), _lib.ptr(self.state_samples), _lib.ptr(self.costs), _lib.ptr(self._w_buf),
+                        _lib.ptr(self._is_vec), _lib.ptr(self.free_flags), P, S, H,
+                        C.byref(self.robot.desc), fields, nf, C.byref(gp), self.temperature, self.step_size, _lib.stream_ptr()))
+                    continue
+                e = _lib.philox_normal(nd, _lib.NOISE_SPM, (S, P, M), self.tensor_args['device'])
+            else:
+                e = eps[it]
+            _lib.require_f32(e)
+            assert e.shape == (S, P, M) and e.is_contiguous()
             if self._sample_dist.scale_tril_kron is not None:
                 _lib.check(lib.mpb_stoch_gpmp_iter_kron(
                     _lib.ptr(self._sample_dist.scale_tril_kron), _lib.ptr(self._sample_dist.scale_tril_kron_tc),
@@ -210,16 +231,17 @@ class StochGPMP(OptimizationPlanner):
         if opt_iters <= 0:
             return self._get_traj()
         for it in range(opt_iters):
-            e = eps[it] if eps is not None else torch.randn(S, P, M, **self.tensor_args)
+            e = eps[it] if eps is not None else None        # None: drawn on the device (Philox, self._noise)
             (self._recent_control_samples, self._recent_state_trajectories, self._recent_control_particles,
              self._recent_state_particles, costs) = self.sample_and_eval(eps=e, **observation)
             self._update_distribution(costs, self.state_samples)
         self._recent_weights = self._weights
         return self._get_traj()
 
-    def step_staged(self, eps, events=None):
-        """One iteration as four separate C-ABI calls (same kernels as mpb_stoch_gpmp_iter); ``events`` is an
-        optional list of 5 torch.cuda.Event recorded around the stages (bench.py per-kernel timing)."""
+    def step_staged(self, eps=None, events=None):
+        """One iteration as four separate C-ABI calls (same kernels as mpb_stoch_gpmp_iter*); ``events`` is an
+        optional list of 5 torch.cuda.Event recorded around the stages (bench.py per-kernel timing).  ``eps`` None:
+        the noise is drawn inside K1 (default structured sampler) -- the way optimize() runs without injected noise."""
         P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
         M = H * D
         lib, st = _lib.lib(), _lib.stream_ptr()
@@ -227,7 +249,10 @@ class StochGPMP(OptimizationPlanner):
         rec = (lambda i: events[i].record()) if events is not None else (lambda i: None)
         rec(0)
         split = self._sample_dist.scale_tril_split
-        if self._sample_dist.kron_tc_kind == 2:
+        if eps is None:
+            self._sample_dist.means = self._particle_means.view(P, -1)
+            self._sample_dist.sample(S, out=self.state_samples.view(P, S, M))
+        elif self._sample_dist.kron_tc_kind == 2:
             _lib.check(lib.mpb_sample_gp_kron_umma(_lib.ptr(self._sample_dist.scale_tril_kron_tc), _lib.ptr(self._particle_means),
                                                    _lib.ptr(eps), _lib.ptr(self.state_samples), P, S, H, self.n_dof, st))
         elif self._sample_dist.kron_tc_kind == 1:

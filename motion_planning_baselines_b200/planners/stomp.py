@@ -5,6 +5,8 @@
     _sample_and_eval       stomp.py:162-197   ->  mpb_sample_stomp + cost.eval (mpb_cost_eval)
     _update_distribution   stomp.py:199-220   ->  mpb_softmax_update with SigmaR = inverse(R)
 """
+import ctypes as C
+
 import torch
 import torch.distributions as dist
 
@@ -20,7 +22,8 @@ class STOMP(OptimizationPlanner):
                  opt_iters=None, dt=None, start_state=None, cost=None, initial_particle_means=None,
                  multi_goal_states=None, sigma_start_init=0.001, sigma_goal_init=0.001, sigma_gp_init=10.,
                  temperature=1., step_size=1., sigma_spectral=0.1, goal_state=None, pos_only=False,
-                 tensor_args=None, sample_split=None, **kwargs):
+                 tensor_args=None, sample_split=None, seed=None, noise_particle_offset=0, noise_particles_global=None,
+                 **kwargs):
         super().__init__(name='STOMP', n_dof=n_dof, n_support_points=n_support_points,
                          num_particles_per_goal=num_particles_per_goal, opt_iters=opt_iters, dt=dt,
                          start_state=start_state, cost=cost, initial_particle_means=initial_particle_means,
@@ -47,6 +50,9 @@ class STOMP(OptimizationPlanner):
         # sample-split mode: the S samples of every particle are sharded over the ranks of a process group
         self.split = sample_split or SampleSplit(world=1, rank=0)
         self._offset, self._s_local = self.split.local_slice(num_samples)
+        # in-kernel noise: one global Philox stream [S_glob, D, P_glob, H]; a rank of a sample split draws its own samples
+        P_glob = noise_particles_global if noise_particles_global is not None else noise_particle_offset + self.num_particles
+        self._noise = _lib.NoiseStream(seed, p_offset=noise_particle_offset, P_global=P_glob, s_offset=self._offset)
         P, S, H, D = self.num_particles, self._s_local, n_support_points, self.d_state_opt
         self.state_particles = torch.empty(P, S, H, D, **self.tensor_args)
         self._w_buf = torch.empty(P, S, **self.tensor_args)
@@ -74,13 +80,14 @@ class STOMP(OptimizationPlanner):
         """-> [P,S_local,H,D]; ``eps`` [S,D,P,H] is the block torch would draw (stomp.py:102); with a sample split
         every rank consumes its own slice of the sample axis."""
         P, S, H, D = self.num_particles, self._s_local, self.n_support_points, self.d_state_opt
-        if eps is None:
-            eps = torch.randn(S, D, P, H, **self.tensor_args)
-        else:
-            _lib.require_f32(eps)
-            assert eps.shape == (self.num_samples, D, P, H)
-            eps = eps[self._offset:self._offset + S]
-        eps = eps.contiguous()
+        if eps is None:     # drawn inside the kernel (Philox keyed on the global element index)
+            nd = self._noise.next()
+            _lib.check(_lib.lib().mpb_sample_stomp_rng(_lib.ptr(self._L_R), _lib.ptr(self._particle_means), C.byref(nd),
+                                                       _lib.ptr(self.state_particles), P, S, H, D, _lib.stream_ptr()))
+            return self.state_particles
+        _lib.require_f32(eps)
+        assert eps.shape == (self.num_samples, D, P, H)
+        eps = eps[self._offset:self._offset + S].contiguous()
         _lib.check(_lib.lib().mpb_sample_stomp(_lib.ptr(self._L_R), _lib.ptr(self._particle_means), _lib.ptr(eps),
                                                _lib.ptr(self.state_particles), P, S, H, D, _lib.stream_ptr()))
         return self.state_particles

@@ -110,12 +110,16 @@ def mppi_rollout(U, state0, dt, ctrl_min, ctrl_max):
 
 
 def mppi_iteration(mean, L_ctrl, Cov_inv, eps, state0, goal, dt, ctrl_min, ctrl_max, c_weights,
-                   temp, step_size, discount=1.0, ext_cost=None):
+                   temp, step_size, discount=1.0, ext_cost=None, mean_sample=None):
     """One MPPI iteration.  mean [T,C]; L_ctrl [C,T,T] (cholesky of Cov[:,:,i]); Cov_inv [C,T,T];
-    eps [C,N,T].  Returns controls, states, costs [N,1], weights, new mean, argmin, min cost."""
+    eps [C,N,T].  Returns controls, states, costs [N,1], weights, new mean, argmin, min cost.
+    mean_sample: the loc of ctrl_dist when it differs from `mean` -- the reference refreshes it only in
+    update_ctrl_dist() (mppi.py:68-70,86), so after pop()/shift() (mppi.py:171-178) controls are still sampled around
+    the UNSHIFTED mean while the IS term and the update use the shifted one."""
     T, C = mean.shape
     N = eps.shape[1]
-    U = torch.stack([mean[:, i] + eps[i] @ L_ctrl[i].t() for i in range(C)], dim=-1)    # [N,T,C]
+    ms = mean if mean_sample is None else mean_sample
+    U = torch.stack([ms[:, i] + eps[i] @ L_ctrl[i].t() for i in range(C)], dim=-1)    # [N,T,C]
     X = mppi_rollout(U, state0, dt, ctrl_min, ctrl_max)
     sd = X.shape[-1]
     disc = torch.cumprod(torch.ones(T, dtype=U.dtype) * discount, dim=0) / discount

@@ -62,6 +62,7 @@ def main():
                   f'max|dmean| {float((p_split._mean - p_full._mean).abs().max()):.3e}', flush=True)
         ok &= all(checks.values())
         p_full._mean.copy_(p_split._mean)
+        p_full.update_ctrl_dist()      # controls are sampled around ctrl_dist.mu (as in the reference)
     print(f'[rank {rank}] MPPI sample-split x{world}: {"ok" if ok else "MISMATCH"}', flush=True)
 
     # ---- STOMP, 2-D point mass, one particle with 4 099 samples ------------------------------------------------------

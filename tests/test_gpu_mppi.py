@@ -54,6 +54,7 @@ def test_mppi_vs_reference_golden(dev):
     best = float('inf')
     for it in range(m['iters']):
         planner._mean.copy_(T(g['mean0'] if it == 0 else g[f'mean{it}']).to(**dev))
+        planner.update_ctrl_dist()      # controls are sampled around ctrl_dist.mu (as in the reference)
         U, X, c = planner.optimize(opt_iters=1, eps=[T(g[f'eps{it}']).to(**dev).contiguous()], **obs)
         assert_close(U, g[f'controls{it}'], rtol=1e-5, atol=1e-6, what='controls')
         assert_close(X, g[f'states{it}'], rtol=1e-5, atol=1e-6, what='states')
@@ -69,6 +70,7 @@ def test_mppi_vs_reference_golden(dev):
         assert_close(planner.best_traj, g[f'best_traj{it}'], rtol=1e-5, atol=1e-6, what='best trajectory')
         # update kernels on the reference's own costs: weights / mean to 1e-5
         planner._mean.copy_(T(g['mean0'] if it == 0 else g[f'mean{it}']).to(**dev))
+        planner.update_ctrl_dist()      # controls are sampled around ctrl_dist.mu (as in the reference)
         planner._xu[..., 2:] = T(g[f'controls{it}']).to(**dev)
         planner.update_controller(T(g[f'costs{it}']).to(**dev).contiguous())
         assert_close(planner.weights.reshape(-1), g[f'weights{it}'].reshape(-1), rtol=1e-5, atol=1e-30, what='weights (reference costs)')
@@ -102,6 +104,7 @@ def test_mppi_iteration_vs_oracle(cfg_name, N, Tn, dev):
         ref = op.mppi_iteration(mean, planner.ctrl_dist.scale_tril.cpu(), planner.Cov_inv.cpu(), eps, start, goal, cfg['dt'], lo, hi,
                                 cw, 1.0, 1.0, ext_cost=Ext())
         planner._mean.copy_(mean.to(**dev))
+        planner.update_ctrl_dist()      # controls are sampled around ctrl_dist.mu (as in the reference)
         U, X, c = planner.optimize(opt_iters=1, eps=[eps.to(**dev)], **obs)
         assert_close(U, ref['controls'], rtol=1e-5, atol=1e-6, what='controls')
         assert_close(X, ref['states'], rtol=1e-5, atol=1e-6, what='states')
@@ -109,6 +112,7 @@ def test_mppi_iteration_vs_oracle(cfg_name, N, Tn, dev):
         assert int(c.argmin()) == int(ref['argmin'])
         # update on the oracle's costs
         planner._mean.copy_(mean.to(**dev))
+        planner.update_ctrl_dist()      # controls are sampled around ctrl_dist.mu (as in the reference)
         planner.update_controller(ref['costs'].to(**dev).contiguous())
         assert_close(planner.weights.reshape(-1), ref['weights'].reshape(-1), rtol=1e-5, atol=1e-30, what='weights')
         assert_close(planner._mean, ref['mean'], rtol=1e-5, atol=1e-6, what='mean')
@@ -200,8 +204,10 @@ def test_mppi_large_batch_properties(dev):
     # the obstacle cost enters as a constant shift (quirk B2): weights must not depend on it
     planner2, _ = _mppi(cfg, N, Tn, dev, 1e-1, cw, cfg['params']['control_std'])
     planner2._mean.copy_(mean0)
+    planner2.update_ctrl_dist()      # controls are sampled around ctrl_dist.mu (as in the reference)
     eps = torch.randn(d, N, Tn, **dev)
     planner._mean.copy_(mean0)
+    planner.update_ctrl_dist()      # controls are sampled around ctrl_dist.mu (as in the reference)
     planner.optimize(opt_iters=1, eps=[eps], **obs)
     planner2.optimize(opt_iters=1, eps=[eps], state=obs['state'], goal_state=obs['goal_state'])
     assert_close(planner2.costs + float(planner._energy), planner.costs, rtol=1e-5, what='constant shift')
