@@ -186,8 +186,8 @@ class StochGPMP(OptimizationPlanner):
         sd = self._sample_dist
         for it in range(opt_iters):
             if it == opt_iters - 1:     # the reference returns the pre-update particle means of the last iteration
-                pos_mean = self._particle_means[..., :self.n_dof].clone()
-                vel_mean = self._particle_means[..., -self.n_dof:].clone()
+                pre = self._particle_means.clone()          # one private copy; the two halves are views of it
+                pos_mean, vel_mean = pre[..., :self.n_dof], pre[..., -self.n_dof:]
             if eps is None:
                 nd = self._noise.next()
                 if sd.kron_tc_kind == 1:        # default: the noise is drawn inside K1

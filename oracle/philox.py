@@ -11,6 +11,10 @@ the float64 value of every normal for a tolerance check of the device's fast-int
     group   = global element index // 4;  the four outputs of one call serve elements 4*group .. 4*group+3
     (u0,u1) -> n0 = r cos(t), n1 = r sin(t),  r = sqrt(-2 ln a), a = u0 * 2^-32 + 2^-33, t = 2 pi (u1 * 2^-32 + 2^-33) - pi
     (u2,u3) -> n2, n3 likewise.
+The device forms a and t in fp32 (uint -> float conversion, then ONE fused multiply-add with fp32 constants); that
+rounding is part of the specification and is reproduced here exactly, so the only device-vs-oracle difference left is
+the accuracy of the MUFU lg2 / sin / cos approximations: |dn| <~ 4e-7 r + 2e-7 / r (the second term matters only
+for |n| < 1e-2, where a is within 5e-5 of 1 and lg2's absolute error of 2^-22 is amplified by 1 / r).
 """
 import numpy as np
 
@@ -51,9 +55,11 @@ def philox_normal(seed, offset, first, count):
     _, quad = philox_u32(seed, offset, first, count)
     e = np.arange(first, first + count, dtype=np.uint64)
     lane = (e & np.uint64(3)).astype(np.int64)
-    u = quad.astype(np.float64) * 2.0 ** -32 + 2.0 ** -33
+    uf = quad.astype(np.float32).astype(np.float64)                     # __uint2float_rn
     pair = lane >> 1
-    a = u[np.arange(count), 2 * pair]
-    t = 2.0 * np.pi * u[np.arange(count), 2 * pair + 1] - np.pi
+    ua, ut = uf[np.arange(count), 2 * pair], uf[np.arange(count), 2 * pair + 1]
+    # fmaf(uf, c1, c0) with fp32 constants: exact in float64, then ONE rounding to fp32
+    a = (ua * float(np.float32(2.3283064365386963e-10)) + float(np.float32(1.1641532182693481e-10))).astype(np.float32).astype(np.float64)
+    t = (ut * float(np.float32(1.4629180792671596e-09)) + float(np.float32(-3.1415925803542134))).astype(np.float32).astype(np.float64)
     r = np.sqrt(-2.0 * np.log(a))
     return np.where((lane & 1) == 0, r * np.cos(t), r * np.sin(t))

@@ -60,7 +60,7 @@ def test_get_random_trajs_vs_reference(name, dev):
 def test_const_vel_trajectories_vs_reference(name, dev):
     g = load_golden(name)
     m = g['meta']
-    planner = make_planner(g, dev)                                  # any means: only the constructor is needed here
+    planner = make_planner(g, dev, S=2)                             # any means: only the constructor is needed here
     got = planner.const_vel_trajectories(planner.start_state, planner.multi_goal_states)
     assert_close(got.flatten(0, 1), g['means0'], rtol=1e-6, atol=1e-7, what='const-velocity trajectories')
     from motion_planning_baselines_b200.fields import CollisionField

@@ -31,19 +31,31 @@ def nd(seed=1, offset=0, s_off=0, p_off=0, P_glob=1):
     return _lib.NoiseDesc(seed=seed, offset=offset, s_offset=s_off, p_offset=p_off, P_global=P_glob)
 
 
+def assert_normals_close(got, ref):
+    """Device (MUFU lg2 / sin / cos) vs the float64 evaluation of the same fp32 inputs (oracle/philox.py): the radius
+    r = sqrt(-2 ln a) carries lg2's absolute error 2^-22 amplified by 1 / r, the angle sin/cos's 2^-21.4 times r."""
+    n = ref.size - ref.size % 2
+    r = np.sqrt(ref[0:n:2] ** 2 + ref[1:n:2] ** 2).repeat(2)       # pairs (cos, sin) share their radius
+    err = np.abs(got[:n] - ref[:n])
+    bound = 2e-6 + 1e-6 * r + 4e-7 / np.maximum(r, 1e-4)
+    assert (err <= bound).all(), f'max err {err.max():.3e} at r = {r[err.argmax()]:.3e}'
+
+
 def test_generator_vs_numpy_oracle(dev):
     from oracle.philox import philox_normal
     # SPM layout with P_glob = P, no offsets: local [S,P,M] flat index == global element index
     for seed, offset, (S, P, M) in [(1, 0, (3, 2, 8)), (0xDEADBEEFCAFEF00D, (1 << 40) + 5, (5, 3, 28)), (77, 2, (2, 2, 7))]:
         got = _lib.philox_normal(nd(seed, offset, P_glob=P), _lib.NOISE_SPM, (S, P, M), dev['device']).cpu().double().numpy().ravel()
         ref = philox_normal(seed, offset, 0, S * P * M)
-        # fast-intrinsic Box-Muller on the device (lg2 / sin / cos approximations): absolute error ~1e-6, a few 1e-6 in the tails
-        assert np.abs(got - ref).max() < 2e-5, np.abs(got - ref).max()
+        assert_normals_close(got, ref)
     # far into the stream (group index beyond 2^32)
     big = nd(5, 9, s_off=(1 << 36), P_glob=3)
     got = _lib.philox_normal(big, _lib.NOISE_SPM, (2, 3, 8), dev['device']).cpu().double().numpy().ravel()
     ref = philox_normal(5, 9, (1 << 36) * 3 * 8, 2 * 3 * 8)
-    assert np.abs(got - ref).max() < 2e-5
+    assert_normals_close(got, ref)
+    # a large block: the bound holds over 2M draws (incl. the tails and the near-zero radii)
+    got = _lib.philox_normal(nd(9, 1, P_glob=64), _lib.NOISE_SPM, (128, 64, 256), dev['device']).cpu().double().numpy().ravel()
+    assert_normals_close(got, philox_normal(9, 1, 0, got.size))
 
 
 @pytest.mark.parametrize('layout,shape', [(0, (6, 8, 12)), (1, (6, 3, 8, 16)), (2, (3, 8, 12)), (1, (4, 2, 4, 7))])
