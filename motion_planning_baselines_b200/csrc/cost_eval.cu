@@ -13,6 +13,9 @@
 // per-warp queue and evaluated exactly 32 at a time.  Per-trajectory sums are reduced with warp
 // shuffles; nothing but the [B] cost (and optional terms / flags) is written.
 // Bound: FP32 issue rate.
+#include <cstdlib>
+#include <cstring>
+
 #include "collision.cuh"
 
 namespace mpb {
@@ -544,6 +547,35 @@ static cudaError_t launch(const CostArgs& a, int blocks_needed, size_t smem, cud
 
 }  // namespace mpb
 
+#include "cost_eval_packed.cuh"
+
+namespace mpb {
+
+template <int DOF>
+static cudaError_t launch_chain2(const CostArgs& a, int blocks_needed, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(cost_eval_chain2_kernel<DOF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(cost_eval_chain2_kernel<DOF>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cost_eval_chain2_kernel<DOF>, kWarps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int resident = sm_count() * per_sm;
+    const int grid = blocks_needed < resident ? blocks_needed : resident;
+    cost_eval_chain2_kernel<DOF><<<grid, kWarps * 32, smem, st>>>(a);
+    return cudaSuccess;
+}
+
+// MPB_COST_EVAL=generic forces the one-waypoint-per-lane kernel (A/B timing and the cross-check in the tests).
+static bool packed_allowed() {
+    const char* v = getenv("MPB_COST_EVAL");
+    return !(v && strcmp(v, "generic") == 0);
+}
+
+}  // namespace mpb
+
 extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc* robot,
                              const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp,
                              const float* is_vec, int samples_per_particle, float is_scale,
@@ -615,7 +647,11 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
         if (m > a.list_cap) a.list_cap = (m + 7) & ~7;
     }
     a.list_off = off;
-    off += (unsigned)(kWarps * 2 * a.list_cap * sizeof(unsigned short));
+    // serial chains against primitive fields: the packed two-waypoints-per-lane kernel (cost_eval_packed.cuh) when the
+    // per-warp primitive lists (52 bytes per entry) fit next to the staged rows
+    const bool packed = robot->kind == MPB_ROBOT_CHAIN && !a.fields.has_extra && !has_extra_terms && robot->q_dim >= 2 &&
+                        robot->q_dim <= 8 && off + (size_t)kWarps * a.list_cap * 52 <= 100 * 1024 && packed_allowed();
+    off += packed ? (unsigned)(kWarps * a.list_cap * 52) : (unsigned)(kWarps * 2 * a.list_cap * sizeof(unsigned short));
     const size_t smem = off;
     MPB_REQUIRE(smem <= 227 * 1024, "mpb_cost_eval: %zu bytes of shared memory needed (H*D too large or too many primitives)", smem);
 
@@ -625,7 +661,17 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
     const int blocks_needed = (B + kWarps - 1) / kWarps;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    if (a.fields.has_extra || has_extra_terms)   // self-collision / workspace fields or extra terms: the variant that carries them
+    if (packed) {
+        switch (robot->q_dim) {
+            case 2: e = launch_chain2<2>(a, blocks_needed, smem, st); break;
+            case 3: e = launch_chain2<3>(a, blocks_needed, smem, st); break;
+            case 4: e = launch_chain2<4>(a, blocks_needed, smem, st); break;
+            case 5: e = launch_chain2<5>(a, blocks_needed, smem, st); break;
+            case 6: e = launch_chain2<6>(a, blocks_needed, smem, st); break;
+            case 7: e = launch_chain2<7>(a, blocks_needed, smem, st); break;
+            default: e = launch_chain2<8>(a, blocks_needed, smem, st); break;
+        }
+    } else if (a.fields.has_extra || has_extra_terms)   // self-collision / workspace fields or extra terms: the variant that carries them
         e = (robot->kind == MPB_ROBOT_POINT) ? launch<MPB_ROBOT_POINT, 1, true>(a, blocks_needed, smem, st)
                                              : launch<MPB_ROBOT_CHAIN, 4, true>(a, blocks_needed, smem, st);
     else
