@@ -551,20 +551,20 @@ static cudaError_t launch(const CostArgs& a, int blocks_needed, size_t smem, cud
 
 namespace mpb {
 
-template <int DOF>
+template <int DOF, int MINB>
 static cudaError_t launch_chain2(const CostArgs& a, int blocks_needed, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(cost_eval_chain2_kernel<DOF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(cost_eval_chain2_kernel<DOF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(cost_eval_chain2_kernel<DOF>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(cost_eval_chain2_kernel<DOF, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cost_eval_chain2_kernel<DOF>, kWarps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cost_eval_chain2_kernel<DOF, MINB>, kWarps * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const int resident = sm_count() * per_sm;
     const int grid = blocks_needed < resident ? blocks_needed : resident;
-    cost_eval_chain2_kernel<DOF><<<grid, kWarps * 32, smem, st>>>(a);
+    cost_eval_chain2_kernel<DOF, MINB><<<grid, kWarps * 32, smem, st>>>(a);
     return cudaSuccess;
 }
 
@@ -572,6 +572,12 @@ static cudaError_t launch_chain2(const CostArgs& a, int blocks_needed, size_t sm
 static bool packed_allowed() {
     const char* v = getenv("MPB_COST_EVAL");
     return !(v && strcmp(v, "generic") == 0);
+}
+
+// Resident CTAs per SM the packed kernel is compiled for: 2 (<= 128 registers) or 3 (<= 80); MPB_K2_CTAS overrides.
+static int k2_ctas() {
+    const char* v = getenv("MPB_K2_CTAS");
+    return (v && atoi(v) == 3) ? 3 : 2;
 }
 
 }  // namespace mpb
@@ -639,7 +645,7 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
     a.rows_off = off;
     off += (unsigned)(kWarps * 2 * a.row_stride * sizeof(float));       // current + prefetched row per warp
     a.queue_off = off;
-    off += (unsigned)(kWarps * kQCap * 5 * sizeof(float));
+    off += (unsigned)(kWarps * kQCap * 7 * sizeof(float));      // 5 words per entry (generic) / 7 (packed: + primitive masks)
     a.list_cap = 8;
     for (int i = 0; i < n_fields; ++i) {
         if (fields[i].kind != MPB_FIELD_PRIMITIVES) continue;
@@ -663,13 +669,13 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
     cudaError_t e;
     if (packed) {
         switch (robot->q_dim) {
-            case 2: e = launch_chain2<2>(a, blocks_needed, smem, st); break;
-            case 3: e = launch_chain2<3>(a, blocks_needed, smem, st); break;
-            case 4: e = launch_chain2<4>(a, blocks_needed, smem, st); break;
-            case 5: e = launch_chain2<5>(a, blocks_needed, smem, st); break;
-            case 6: e = launch_chain2<6>(a, blocks_needed, smem, st); break;
-            case 7: e = launch_chain2<7>(a, blocks_needed, smem, st); break;
-            default: e = launch_chain2<8>(a, blocks_needed, smem, st); break;
+            case 2: e = (k2_ctas() == 3 ? launch_chain2<2, 3>(a, blocks_needed, smem, st) : launch_chain2<2, 2>(a, blocks_needed, smem, st)); break;
+            case 3: e = (k2_ctas() == 3 ? launch_chain2<3, 3>(a, blocks_needed, smem, st) : launch_chain2<3, 2>(a, blocks_needed, smem, st)); break;
+            case 4: e = (k2_ctas() == 3 ? launch_chain2<4, 3>(a, blocks_needed, smem, st) : launch_chain2<4, 2>(a, blocks_needed, smem, st)); break;
+            case 5: e = (k2_ctas() == 3 ? launch_chain2<5, 3>(a, blocks_needed, smem, st) : launch_chain2<5, 2>(a, blocks_needed, smem, st)); break;
+            case 6: e = (k2_ctas() == 3 ? launch_chain2<6, 3>(a, blocks_needed, smem, st) : launch_chain2<6, 2>(a, blocks_needed, smem, st)); break;
+            case 7: e = (k2_ctas() == 3 ? launch_chain2<7, 3>(a, blocks_needed, smem, st) : launch_chain2<7, 2>(a, blocks_needed, smem, st)); break;
+            default: e = (k2_ctas() == 3 ? launch_chain2<8, 3>(a, blocks_needed, smem, st) : launch_chain2<8, 2>(a, blocks_needed, smem, st)); break;
         }
     } else if (a.fields.has_extra || has_extra_terms)   // self-collision / workspace fields or extra terms: the variant that carries them
         e = (robot->kind == MPB_ROBOT_POINT) ? launch<MPB_ROBOT_POINT, 1, true>(a, blocks_needed, smem, st)
