@@ -17,6 +17,8 @@ for f in $SRC/*.cu; do
     pids+=($!)
   fi
 done
-for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+fail=0
+for p in "${pids[@]:-}"; do [ -n "$p" ] && { wait "$p" || fail=1; }; done
+if [ "$fail" -ne 0 ]; then grep -h -B2 -A2 "error" build/*.ptxas.log >&2 || true; echo "build failed" >&2; exit 1; fi
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "${objs[@]}" -lcudart
 echo "built $OUT"

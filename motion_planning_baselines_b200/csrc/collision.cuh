@@ -395,18 +395,24 @@ struct RobotLayout {
     unsigned link;        // int[n]     ascending joint index
     unsigned bound;       // float4[dof] bounding sphere of each link's collision spheres (link frame): mx,my,mz,R
     unsigned link_end;    // int[dof]   one past the last sphere of each link
+    unsigned pat;         // int[dof]   rotation pattern of the fixed transform (MPB_TF_*), see frame2_advance
     int n_spheres, dof;
 };
 
+// Rotation part of a joint's fixed transform: general, identity, or a quarter turn about x (URDF rpy = (+-pi/2, 0, 0),
+// six of the Panda's seven joints).  For the special patterns R * Fr is a signed column permutation: no arithmetic.
+enum { MPB_TF_GENERAL = 0, MPB_TF_IDENTITY = 1, MPB_TF_RX_PLUS = 2, MPB_TF_RX_MINUS = 3 };
+
 inline unsigned layout_robot(const mpb_robot_desc& r, RobotLayout& l, unsigned base) {
     l.n_spheres = r.n_spheres; l.dof = r.q_dim;
-    if (r.kind != MPB_ROBOT_CHAIN) { l.sphere = l.tf = l.link = l.bound = l.link_end = base; return base; }
+    if (r.kind != MPB_ROBOT_CHAIN) { l.sphere = l.tf = l.link = l.bound = l.link_end = l.pat = base; return base; }
     unsigned p = base;
     l.sphere = p; p += (unsigned)r.n_spheres * 16;
     l.tf = p;     p += (unsigned)r.q_dim * 48;
     l.bound = p;  p += (unsigned)r.q_dim * 16;
     l.link = p;   p += (unsigned)r.n_spheres * 4;
     l.link_end = p; p += (unsigned)r.q_dim * 4;
+    l.pat = p;    p += (unsigned)r.q_dim * 4;
     return (p + 15u) & ~15u;
 }
 
@@ -419,6 +425,16 @@ __device__ __forceinline__ void stage_robot(const mpb_robot_desc& r, const Robot
         lk[s] = r.sphere_link[s];
     }
     for (int i = threadIdx.x; i < r.q_dim * 12; i += blockDim.x) tf[i] = r.fixed_tf[i];
+    for (int j = threadIdx.x; j < r.q_dim; j += blockDim.x) {
+        const float* F = r.fixed_tf + j * 12;       // row-major 3x4
+        int pat = MPB_TF_GENERAL;
+        if (F[0] == 1.f && F[1] == 0.f && F[2] == 0.f && F[4] == 0.f && F[8] == 0.f) {
+            if (F[5] == 1.f && F[6] == 0.f && F[9] == 0.f && F[10] == 1.f) pat = MPB_TF_IDENTITY;
+            else if (F[5] == 0.f && F[6] == -1.f && F[9] == 1.f && F[10] == 0.f) pat = MPB_TF_RX_PLUS;
+            else if (F[5] == 0.f && F[6] == 1.f && F[9] == -1.f && F[10] == 0.f) pat = MPB_TF_RX_MINUS;
+        }
+        reinterpret_cast<int*>(smem + l.pat)[j] = pat;
+    }
     // per-link bounding spheres: warp w handles links w, w+nwarps, ... with lanes over the sphere table, so the
     // global-memory round trips overlap instead of forming one long dependent chain per link
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;

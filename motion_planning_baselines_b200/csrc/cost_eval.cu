@@ -13,6 +13,7 @@
 // per-warp queue and evaluated exactly 32 at a time.  Per-trajectory sums are reduced with warp
 // shuffles; nothing but the [B] cost (and optional terms / flags) is written.
 // Bound: FP32 issue rate.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -551,20 +552,20 @@ static cudaError_t launch(const CostArgs& a, int blocks_needed, size_t smem, cud
 
 namespace mpb {
 
-template <int DOF, int MINB>
-static cudaError_t launch_chain2(const CostArgs& a, int blocks_needed, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(cost_eval_chain2_kernel<DOF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int DOF, int NW, int MINB>
+static cudaError_t launch_chain2(const CostArgs& a, size_t smem, cudaStream_t st) {
+    auto kern = cost_eval_chain2_kernel<DOF, NW, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(cost_eval_chain2_kernel<DOF, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cost_eval_chain2_kernel<DOF, MINB>, kWarps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    const int resident = sm_count() * per_sm;
+    const int resident = sm_count() * per_sm, blocks_needed = (a.B + NW - 1) / NW;
     const int grid = blocks_needed < resident ? blocks_needed : resident;
-    cost_eval_chain2_kernel<DOF, MINB><<<grid, kWarps * 32, smem, st>>>(a);
+    kern<<<grid, NW * 32, smem, st>>>(a);
     return cudaSuccess;
 }
 
@@ -574,10 +575,14 @@ static bool packed_allowed() {
     return !(v && strcmp(v, "generic") == 0);
 }
 
-// Resident CTAs per SM the packed kernel is compiled for: 2 (<= 128 registers) or 3 (<= 80); MPB_K2_CTAS overrides.
-static int k2_ctas() {
-    const char* v = getenv("MPB_K2_CTAS");
-    return (v && atoi(v) == 3) ? 3 : 2;
+// Launch shape of the packed kernel: warps per CTA x resident CTAs per SM (register cap = 65536 / threads per SM).
+// MPB_K2_CFG=<warps>x<ctas> selects one of the compiled experiment shapes (7-dof chains only).
+static int k2_cfg() {
+    const char* v = getenv("MPB_K2_CFG");
+    if (!v) return 82;
+    int w = 0, c = 0;
+    if (sscanf(v, "%dx%d", &w, &c) != 2) return 82;
+    return w * 10 + c;
 }
 
 }  // namespace mpb
@@ -641,11 +646,17 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
 
     unsigned off = layout_fields(a.fields, 0);
     off = layout_robot(*robot, a.rl, off);
+    // serial chains against primitive fields take the packed two-waypoints-per-lane kernel (cost_eval_packed.cuh)
+    bool packed = robot->kind == MPB_ROBOT_CHAIN && !a.fields.has_extra && !has_extra_terms && robot->q_dim >= 2 &&
+                  robot->q_dim <= 8 && packed_allowed();
+    const int cfg = (packed && robot->q_dim == 7) ? k2_cfg() : 82;
+    int nw = packed ? cfg / 10 : kWarps;
+    if (nw != 4 && nw != 6 && nw != 8) nw = 8;
     a.row_stride = (a.M + 3) & ~3;
     a.rows_off = off;
-    off += (unsigned)(kWarps * 2 * a.row_stride * sizeof(float));       // current + prefetched row per warp
+    off += (unsigned)(nw * 2 * a.row_stride * sizeof(float));       // current + prefetched row per warp
     a.queue_off = off;
-    off += (unsigned)(kWarps * kQCap * 7 * sizeof(float));      // 5 words per entry (generic) / 7 (packed: + primitive masks)
+    off += (unsigned)(nw * kQCap * (packed ? 7 : 5) * sizeof(float));   // generic: 5 words per entry; packed: + primitive masks
     a.list_cap = 8;
     for (int i = 0; i < n_fields; ++i) {
         if (fields[i].kind != MPB_FIELD_PRIMITIVES) continue;
@@ -653,11 +664,8 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
         if (m > a.list_cap) a.list_cap = (m + 7) & ~7;
     }
     a.list_off = off;
-    // serial chains against primitive fields: the packed two-waypoints-per-lane kernel (cost_eval_packed.cuh) when the
-    // per-warp primitive lists (52 bytes per entry) fit next to the staged rows
-    const bool packed = robot->kind == MPB_ROBOT_CHAIN && !a.fields.has_extra && !has_extra_terms && robot->q_dim >= 2 &&
-                        robot->q_dim <= 8 && off + (size_t)kWarps * a.list_cap * 52 <= 100 * 1024 && packed_allowed();
-    off += packed ? (unsigned)(kWarps * a.list_cap * 52) : (unsigned)(kWarps * 2 * a.list_cap * sizeof(unsigned short));
+    // packed: per-warp primitive DATA lists (52 bytes per entry); generic: index lists
+    off += packed ? (unsigned)(nw * a.list_cap * 52) : (unsigned)(nw * 2 * a.list_cap * sizeof(unsigned short));
     const size_t smem = off;
     MPB_REQUIRE(smem <= 227 * 1024, "mpb_cost_eval: %zu bytes of shared memory needed (H*D too large or too many primitives)", smem);
 
@@ -669,13 +677,20 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
     cudaError_t e;
     if (packed) {
         switch (robot->q_dim) {
-            case 2: e = (k2_ctas() == 3 ? launch_chain2<2, 3>(a, blocks_needed, smem, st) : launch_chain2<2, 2>(a, blocks_needed, smem, st)); break;
-            case 3: e = (k2_ctas() == 3 ? launch_chain2<3, 3>(a, blocks_needed, smem, st) : launch_chain2<3, 2>(a, blocks_needed, smem, st)); break;
-            case 4: e = (k2_ctas() == 3 ? launch_chain2<4, 3>(a, blocks_needed, smem, st) : launch_chain2<4, 2>(a, blocks_needed, smem, st)); break;
-            case 5: e = (k2_ctas() == 3 ? launch_chain2<5, 3>(a, blocks_needed, smem, st) : launch_chain2<5, 2>(a, blocks_needed, smem, st)); break;
-            case 6: e = (k2_ctas() == 3 ? launch_chain2<6, 3>(a, blocks_needed, smem, st) : launch_chain2<6, 2>(a, blocks_needed, smem, st)); break;
-            case 7: e = (k2_ctas() == 3 ? launch_chain2<7, 3>(a, blocks_needed, smem, st) : launch_chain2<7, 2>(a, blocks_needed, smem, st)); break;
-            default: e = (k2_ctas() == 3 ? launch_chain2<8, 3>(a, blocks_needed, smem, st) : launch_chain2<8, 2>(a, blocks_needed, smem, st)); break;
+            case 2: e = launch_chain2<2, 8, 2>(a, smem, st); break;
+            case 3: e = launch_chain2<3, 8, 2>(a, smem, st); break;
+            case 4: e = launch_chain2<4, 8, 2>(a, smem, st); break;
+            case 5: e = launch_chain2<5, 8, 2>(a, smem, st); break;
+            case 6: e = launch_chain2<6, 8, 2>(a, smem, st); break;
+            case 8: e = launch_chain2<8, 8, 2>(a, smem, st); break;
+            default:
+                switch (cfg) {
+                    case 83: e = launch_chain2<7, 8, 3>(a, smem, st); break;
+                    case 45: e = launch_chain2<7, 4, 5>(a, smem, st); break;
+                    case 46: e = launch_chain2<7, 4, 6>(a, smem, st); break;
+                    case 63: e = launch_chain2<7, 6, 3>(a, smem, st); break;
+                    default: e = launch_chain2<7, 8, 2>(a, smem, st); break;
+                }
         }
     } else if (a.fields.has_extra || has_extra_terms)   // self-collision / workspace fields or extra terms: the variant that carries them
         e = (robot->kind == MPB_ROBOT_POINT) ? launch<MPB_ROBOT_POINT, 1, true>(a, blocks_needed, smem, st)
