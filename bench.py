@@ -449,6 +449,24 @@ def main():
     ms_e2e_inj = allmax(e0.elapsed_time(e1))
     del h_eps, d_eps
 
+    # N > 1: the sample-split variant (BASELINE.json configs[4]): ONE problem's samples sharded over the ranks, one
+    # exchange step per iteration (all-gather of packed softmax records over NCCL/NVLink).  Strong scaling: total samples fixed.
+    split_block = None
+    if world > 1:
+        del planner
+        torch.cuda.empty_cache()
+        try:
+            import bench_configs
+            res = bench_configs.bench_c5(dev, Ns=(100000, 1000000), split=bench_configs.TimedSplit(), iters=10,
+                                         stomp_Ns=(100000,), reduce_max=allmax)
+            split_block = dict(scaling='strong (total samples fixed; efficiency = t(1 GPU) / (N x t(N GPUs)), the 1-GPU times '
+                                       'are the C5 rows of other_configs in the N=1 line)',
+                               exchange='per iteration: all_gather_into_tensor of the packed (m, Z, cmin, argmin, sum e(x-mu)) '
+                                        'records + fixed-order combine on every rank; MPPI adds a scalar all-gather (batch-summed '
+                                        'obstacle cost, quirk B2) and a [T,sd] gather of the best rollout',
+                               results=res)
+        except Exception as exc:
+            split_block = dict(error=repr(exc))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -520,6 +538,8 @@ def main():
                                     note='the same step on injected noise resident in HBM (8 rotating 117 MB buffers): K1 reads eps '
                                          'instead of drawing it', kernels=kernel_table(stage_inj, k1_reads_eps=True)),
                 roofline=roofline, collision_free_fraction_last_step=free_frac, parity_check=check)
+    if split_block is not None:
+        line['sample_split'] = split_block
     if world == 1 and not args.no_other_configs:
         # the other BASELINE.json configs ("ms per planner iter"), informational: see bench_configs.py
         del planner

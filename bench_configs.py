@@ -35,6 +35,25 @@ def _time(fn, iters, warmup=3, sync=None):
     return e0.elapsed_time(e1) / iters
 
 
+def _timed_split(fn, iters, sync, split, reduce_max):
+    """_time + (for a TimedSplit) the stream time of the collectives per iteration, both as max over ranks."""
+    for _ in range(3):
+        fn()
+    if hasattr(split, 'reset'):
+        split.reset()
+    ms = _time(fn, iters, warmup=0, sync=sync)
+    coll = {}
+    if hasattr(split, 'collective_ms') and split.world > 1:
+        c_ms = split.collective_ms() / iters
+        if reduce_max is not None:
+            c_ms = reduce_max(c_ms)
+        coll = dict(collective_ms_per_iter=c_ms, collectives_per_iter=split.calls // iters,
+                    collective_bytes_per_iter=split.bytes // iters)
+    if reduce_max is not None:
+        ms = reduce_max(ms)
+    return dict(ms=ms, collectives=dict(collectives=coll) if coll else {})
+
+
 def _straight(cfg, P, H, d, dev, jitter=0.0):
     w = torch.linspace(0, 1, H, device=dev['device']).view(1, H, 1)
     x = torch.zeros(P, H, 2 * d, **dev)
@@ -126,7 +145,42 @@ def bench_stoch(dev, name, iters=30):
                 samples_per_s=P * S / (ms * 1e-3))
 
 
-def bench_c5(dev, Ns=(1000, 10000, 100000, 1000000), split=None, iters=10):
+class TimedSplit:
+    """SampleSplit whose collectives are bracketed by CUDA events on the launching stream, so that a sample-split run
+    reports how long its exchange step occupies the stream per iteration (waiting for the slowest peer included)."""
+
+    def __new__(cls, *a, **kw):
+        from motion_planning_baselines_b200.update import SampleSplit
+
+        class _Timed(SampleSplit):
+            def __init__(self, *a, **kw):
+                super().__init__(*a, **kw)
+                self.events, self.calls, self.bytes = [], 0, 0
+
+            def all_gather_cat(self, t):
+                if self.world == 1:
+                    return t
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = super().all_gather_cat(t)
+                e1.record()
+                self.events.append((e0, e1))
+                self.calls += 1
+                self.bytes += out.numel() * out.element_size()
+                return out
+
+            def reset(self):
+                self.events, self.calls, self.bytes = [], 0, 0
+
+            def collective_ms(self):
+                torch.cuda.synchronize()
+                return sum(a.elapsed_time(b) for a, b in self.events)
+        return _Timed(*a, **kw)
+
+
+def bench_c5(dev, Ns=(1000, 10000, 100000, 1000000), split=None, iters=10, stomp_Ns=None, reduce_max=None):
+    """MPPI at every N of ``Ns`` and STOMP at ``stomp_Ns`` (default: the first three).  With a (Timed)SampleSplit the N
+    samples of the ONE problem are sharded over the ranks; ``reduce_max`` turns a rank-local time into the max over ranks."""
     from motion_planning_baselines_b200 import configs
     from motion_planning_baselines_b200.costs import CostCollision, CostComposite
     from motion_planning_baselines_b200.dynamics import PointParticleDynamics
@@ -148,22 +202,24 @@ def bench_c5(dev, Ns=(1000, 10000, 100000, 1000000), split=None, iters=10):
                                        ctrl_max=[prm['ctrl_max']] * d, c_weights=prm['c_weights'], tensor_args=dev)
         planner = MPPI(system, num_ctrl_samples=N, rollout_steps=Tn, opt_iters=1, control_std=prm['control_std'], temp=prm['temp'],
                        step_size=prm['step_size'], cov_prior_type=prm['cov_prior_type'], tensor_args=dev, sample_split=split)
-        ms = _time(lambda: planner.optimize(opt_iters=1, **obs), iters if N <= 100000 else 5, sync=sync)
+        n_it = iters if N <= 100000 else 5
+        ms = _timed_split(lambda: planner.optimize(opt_iters=1, **obs), n_it, sync, split, reduce_max)
         out.append(dict(config='C5 panda_table_shelf MPPI', shape=f'{N} control samples x 64 steps x 7 dof', n_gpus=world,
-                        ms_per_iter=ms, samples_per_s=N / (ms * 1e-3),
-                        sharding='samples split over ranks; all-gather of packed records + fixed-order combine' if world > 1 else 'single GPU'))
+                        ms_per_iter=ms['ms'], samples_per_s=N / (ms['ms'] * 1e-3),
+                        sharding='samples split over ranks; all-gather of packed records + fixed-order combine' if world > 1 else 'single GPU',
+                        **ms['collectives']))
         del planner
         torch.cuda.empty_cache()
     c1 = configs.config('C1')['params']
-    for S in Ns[:3]:
+    for S in (Ns[:3] if stomp_Ns is None else stomp_Ns):
         planner = STOMP(n_dof=d, n_support_points=Tn, num_particles_per_goal=1, num_samples=S, opt_iters=1, dt=cfg['dt'],
                         start_state=torch.tensor(cfg['start']).to(**dev), cost=cost,
                         multi_goal_states=torch.tensor(cfg['goal']).to(**dev).unsqueeze(0), temperature=c1['temperature'],
                         step_size=c1['step_size'], sigma_spectral=c1['sigma_spectral'],
                         initial_particle_means=_straight(cfg, 1, Tn, d, dev), pos_only=False, tensor_args=dev, sample_split=split)
-        ms = _time(lambda: planner.optimize(opt_iters=1), iters, sync=sync)
+        ms = _timed_split(lambda: planner.optimize(opt_iters=1), iters, sync, split, reduce_max)
         out.append(dict(config='C5 panda_table_shelf STOMP', shape=f'1 particle x {S} samples x 64 waypoints', n_gpus=world,
-                        ms_per_iter=ms, samples_per_s=S / (ms * 1e-3)))
+                        ms_per_iter=ms['ms'], samples_per_s=S / (ms['ms'] * 1e-3), **ms['collectives']))
         del planner
         torch.cuda.empty_cache()
     return out
@@ -174,7 +230,7 @@ def run_other_configs(dev, quick=False):
     res = [bench_c1_stomp(dev, iters=50 if quick else 200)]
     res += bench_c2(dev, iters=5 if quick else 20)
     res.append(bench_stoch(dev, 'C3', iters=10 if quick else 30))
-    res += bench_c5(dev, Ns=(1000, 10000, 100000) if quick else (1000, 10000, 100000, 1000000))
+    res += bench_c5(dev, Ns=(1000, 10000, 100000, 1000000), stomp_Ns=(1000, 10000, 100000), iters=5 if quick else 10)
     return res
 
 
@@ -190,8 +246,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     if args.sample_split:
-        from motion_planning_baselines_b200.update import SampleSplit
-        res = bench_c5(dev, split=SampleSplit())
+        res = bench_c5(dev, split=TimedSplit())
     else:
         res = run_other_configs(dev, quick=args.quick)
     if rank == 0:
