@@ -347,7 +347,7 @@ def main():
         desc = planner._noise.desc()
         planner.step_staged(None)
         torch.cuda.synchronize()
-        eps_last = _lib.philox_normal(desc, _lib.NOISE_SPM, (S, P, M), dev['device'])
+        eps_last = planner._sample_dist.replay_noise(desc, S)
         check = parity_check(planner, cfg, sig, means0, eps_last)
         del eps_last
 

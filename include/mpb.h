@@ -123,8 +123,12 @@ typedef struct mpb_extra_cost_desc {
  *   MPB_NOISE_STOMP  [S_glob, D, P_glob, H]   (STOMP.sample;                       local [S,D,P,H])
  *   MPB_NOISE_MPPI   [C, N_glob, T]           (ControlTrajectoryGaussian.sample;   local [C,N,T], N_glob = P_global,
  *                                              first local sample = s_offset)
+ *   MPB_NOISE_SPMD   [S_glob, P_glob, dof, 2H] (the tcgen05 structured sampler mpb_sample_gp_kron_gen: dof-major inside a
+ *                                              row, so one Philox call yields four consecutive k of one dof; the dump is
+ *                                              written in the local [S,P,M] order, m = n * dof + j, with n3 = dof)
  * The caller advances `offset` by one per draw (per optimize() iteration). */
 #define MPB_NOISE_SPM 0
+#define MPB_NOISE_SPMD 3
 #define MPB_NOISE_STOMP 1
 #define MPB_NOISE_MPPI 2
 typedef struct mpb_noise_desc {
@@ -195,6 +199,20 @@ int mpb_sample_gp_kron_tc_rng(const void* LkF, const float* mu, const mpb_noise_
                               int P, int S, int H, int dof, void* stream);
 int mpb_sample_gp_kron_tc(const void* LkF, const float* mu, const float* eps, float* x,
                           int P, int S, int H, int dof, void* stream);
+
+/* Blackwell path of the structured sampler with the noise drawn in the kernel (csrc/sample_gp_kron_gen.cu): the factor is
+ * the M = 128 operand of tcgen05.mma.kind::f16 (two-term fp16 split, fp32 accumulation in tensor memory), a tile is 64
+ * samples, warp-specialised producers write Philox / Box-Muller noise (layout MPB_NOISE_SPMD) straight into the operand
+ * tiles, the factor streams through shared memory by bulk-async (TMA) copies and finished rows leave by bulk-async
+ * stores.  Replaces MultiMPPrior.sample (mp_priors_multi.py:253-256) INCLUDING torch's noise draw.
+ *   mpb_sample_gp_kron_gen_prepare : LkT (from mpb_sample_gp_kron_pack) -> Limg, mpb_sample_gp_kron_gen_bytes(H, dof) bytes,
+ *                                    16-byte aligned; one-off setup, stream-ordered.
+ * Same numbers as mpb_philox_normal(MPB_NOISE_SPMD) + mpb_sample_gp_kron_tc up to the fp32 accumulation order. */
+int mpb_sample_gp_kron_gen_supported(int H, int dof);
+long long mpb_sample_gp_kron_gen_bytes(int H, int dof);
+int mpb_sample_gp_kron_gen_prepare(const float* LkT, void* Limg, int H, int dof, void* stream);
+int mpb_sample_gp_kron_gen(const void* Limg, const float* mu, const mpb_noise_desc* noise, float* x, int P, int S, int H,
+                           int dof, void* stream);
 
 /* tcgen05 variant of the structured sampler (csrc/sample_gp_tc.cu, sample_gp_kron_umma_kernel): TMA -> per-dof
  * gather + 3xTF32 split into tensor memory -> one M128 x N32 tcgen05.mma chain per dof with TMEM accumulators -> dofs
@@ -287,6 +305,13 @@ int mpb_stoch_gpmp_iter_kron(const float* L_kron, const void* L_kron_tc, int tc_
 /* mpb_stoch_gpmp_iter_kron_rng: the iteration as the reference runs it -- optimize() takes no noise (stoch_gpmp.py:281-309),
  * the draw happens inside the sampler: K1 = mpb_sample_gp_kron_tc_rng (tc_kind 1 operand LkF). */
 int mpb_stoch_gpmp_iter_kron_rng(const void* L_kron_tc, const float* Sigma_inv, int sigma_inv_structured,
+                                 const mpb_noise_desc* noise, float* mu, float* x, float* cost, float* weights,
+                                 float* is_vec, uint8_t* free_flag, int P, int S, int H, const mpb_robot_desc* robot,
+                                 const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp, float temp, float step,
+                                 void* stream);
+/* ... and on the Blackwell sampler mpb_sample_gp_kron_gen (operand from mpb_sample_gp_kron_gen_prepare, noise layout
+ * MPB_NOISE_SPMD): the default iteration for the shapes that sampler supports. */
+int mpb_stoch_gpmp_iter_kron_gen(const void* L_kron_gen, const float* Sigma_inv, int sigma_inv_structured,
                                  const mpb_noise_desc* noise, float* mu, float* x, float* cost, float* weights,
                                  float* is_vec, uint8_t* free_flag, int P, int S, int H, const mpb_robot_desc* robot,
                                  const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp, float temp, float step,

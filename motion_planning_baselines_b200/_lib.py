@@ -53,7 +53,7 @@ class NoiseDesc(C.Structure):
                 ('P_global', C.c_int64)]
 
 
-NOISE_SPM, NOISE_STOMP, NOISE_MPPI = 0, 1, 2
+NOISE_SPM, NOISE_STOMP, NOISE_MPPI, NOISE_SPMD = 0, 1, 2, 3
 MPB_MAX_INTERP = 32
 _lib = None
 
@@ -80,6 +80,12 @@ _SIGNATURES = {
     'mpb_sample_gp_kron_tc_rng': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _i, _i, _i, _i, _vp]),
     'mpb_stoch_gpmp_iter_kron_rng': (C.c_int, [_vp, _vp, _i, C.POINTER(NoiseDesc), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                                C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc), _f, _f, _vp]),
+    'mpb_stoch_gpmp_iter_kron_gen': (C.c_int, [_vp, _vp, _i, C.POINTER(NoiseDesc), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                               C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc), _f, _f, _vp]),
+    'mpb_sample_gp_kron_gen_supported': (C.c_int, [_i, _i]),
+    'mpb_sample_gp_kron_gen_bytes': (C.c_longlong, [_i, _i]),
+    'mpb_sample_gp_kron_gen_prepare': (C.c_int, [_vp, _vp, _i, _i, _vp]),
+    'mpb_sample_gp_kron_gen': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _i, _i, _i, _i, _vp]),
     'mpb_mppi_rollout_ex': (C.c_int, [_vp] * 5 + [C.POINTER(NoiseDesc)] + [_vp] * 7 + [_i, _i, _i, _i, _f, _f, _f, _f, _f, _vp]),
     'mpb_prior_matvec': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'mpb_cost_eval': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
@@ -264,11 +270,13 @@ class NoiseStream:
         return d
 
 
-def philox_normal(noise_desc, layout, shape, device):
+def philox_normal(noise_desc, layout, shape, device, dof=None):
     """The normals a kernel called with ``noise_desc`` consumes, in the call's local layout (replay / debug; also the
-    generator in front of the samplers without a fused variant)."""
+    generator in front of the samplers without a fused variant).  NOISE_SPMD takes the dof count (``dof``)."""
     out = torch.empty(*shape, device=device, dtype=torch.float32)
     n = list(shape) + [1] * (4 - len(shape))
+    if layout == NOISE_SPMD:
+        n[3] = int(dof)
     check(lib().mpb_philox_normal(C.byref(noise_desc), layout, ptr(out), n[0], n[1], n[2], n[3], stream_ptr()))
     return out
 

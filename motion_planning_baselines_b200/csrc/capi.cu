@@ -149,3 +149,22 @@ extern "C" int mpb_stoch_gpmp_iter_kron_rng(const void* L_kron_tc, const float* 
     if (rc) return rc;
     return mpb_softmax_update(cost, x, mu, weights, nullptr, temp, step, nullptr, P, S, H, D, stream);
 }
+
+// The same iteration on the Blackwell sampler (mpb_sample_gp_kron_gen: tcgen05 + bulk-async copies, noise layout
+// MPB_NOISE_SPMD drawn in the kernel) -- the default for the shapes it supports.
+extern "C" int mpb_stoch_gpmp_iter_kron_gen(const void* L_kron_gen, const float* Sigma_inv, int sigma_inv_structured,
+                                            const mpb_noise_desc* noise, float* mu, float* x, float* cost, float* weights,
+                                            float* is_vec, uint8_t* free_flag, int P, int S, int H, const mpb_robot_desc* robot,
+                                            const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp, float temp,
+                                            float step, void* stream) {
+    MPB_REQUIRE(robot && L_kron_gen && noise, "mpb_stoch_gpmp_iter_kron_gen: null robot / factor / noise descriptor");
+    const int D = 2 * robot->q_dim, M = H * D;
+    int rc = mpb_sample_gp_kron_gen(L_kron_gen, mu, noise, x, P, S, H, robot->q_dim, stream);
+    if (rc) return rc;
+    rc = sigma_inv_structured ? mpb_prior_matvec_dof(Sigma_inv, mu, is_vec, P, H, robot->q_dim, stream)
+                              : mpb_prior_matvec(Sigma_inv, mu, is_vec, P, M, 2 * D - 1, stream);
+    if (rc) return rc;
+    rc = mpb_cost_eval(x, P * S, H, robot, fields, n_fields, gp, is_vec, S, temp, cost, nullptr, free_flag, stream);
+    if (rc) return rc;
+    return mpb_softmax_update(cost, x, mu, weights, nullptr, temp, step, nullptr, P, S, H, D, stream);
+}

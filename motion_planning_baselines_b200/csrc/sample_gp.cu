@@ -205,6 +205,9 @@ __global__ void __launch_bounds__(256) philox_dump_kernel(const NoiseArgs noise,
         if (layout == MPB_NOISE_SPM) {                 // r = s * P + p
             const long long p = r % n1, s = r / n1;
             e = ((unsigned long long)(noise.s_off + s) * noise.P_glob + noise.p_off + p) * inner + k;
+        } else if (layout == MPB_NOISE_SPMD) {         // local [S,P,M] with m = n * dof + j; virtual [S_glob,P_glob,dof,M/dof]
+            const long long p = r % n1, s = r / n1, dof = n3, j = k % dof, n = k / dof;
+            e = (((unsigned long long)(noise.s_off + s) * noise.P_glob + noise.p_off + p) * dof + j) * (inner / dof) + n;
         } else if (layout == MPB_NOISE_STOMP) {        // r = (s * D + j) * P + p
             const long long p = r % n2; r /= n2;
             const long long j = r % n1, s = r / n1;
@@ -339,7 +342,9 @@ extern "C" int mpb_sample_gp(const float* L, const float* mu, const float* eps, 
 extern "C" int mpb_philox_normal(const mpb_noise_desc* nd, int layout, float* out, int n0, int n1, int n2, int n3, void* stream) {
     using namespace mpb;
     MPB_REQUIRE(nd && out, "mpb_philox_normal: null pointer");
-    MPB_REQUIRE(layout == MPB_NOISE_SPM || layout == MPB_NOISE_STOMP || layout == MPB_NOISE_MPPI, "mpb_philox_normal: unknown layout %d", layout);
+    MPB_REQUIRE(layout == MPB_NOISE_SPM || layout == MPB_NOISE_STOMP || layout == MPB_NOISE_MPPI || layout == MPB_NOISE_SPMD,
+                "mpb_philox_normal: unknown layout %d", layout);
+    MPB_REQUIRE(layout != MPB_NOISE_SPMD || (n3 >= 1 && n2 % n3 == 0), "mpb_philox_normal: MPB_NOISE_SPMD takes the dof count in n3 (M %% dof == 0)");
     MPB_REQUIRE(n0 >= 0 && n1 >= 0 && n2 >= 0 && (layout != MPB_NOISE_STOMP || n3 >= 0), "mpb_philox_normal: negative extent");
     NoiseArgs noise{};
     const char* why = noise_args(*nd, 0, noise);
@@ -347,7 +352,7 @@ extern "C" int mpb_philox_normal(const mpb_noise_desc* nd, int layout, float* ou
     const long long inner = layout == MPB_NOISE_STOMP ? n3 : n2;
     const long long total = (long long)n0 * n1 * n2 * (layout == MPB_NOISE_STOMP ? n3 : 1);
     if (total == 0) return MPB_OK;
-    const int vec = (inner % 4 == 0) && ((uintptr_t)out % 16 == 0);
+    const int vec = (inner % 4 == 0) && ((uintptr_t)out % 16 == 0) && layout != MPB_NOISE_SPMD;
     const long long items = vec ? total / 4 : total;
     const long long blocks = (items + 255) / 256;
     const int grid = (int)(blocks < (long long)sm_count() * 8 ? blocks : (long long)sm_count() * 8);

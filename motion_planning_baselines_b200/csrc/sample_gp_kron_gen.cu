@@ -1,0 +1,353 @@
+// K1 (Blackwell path of the structured sampler, noise drawn in the kernel):
+//     x[p,s,:] = mu[p,:] + L @ eps[s,p,:],   eps ~ N(0, I) generated on the fly
+//
+// Replaces MultiMPPrior.sample (mp_baselines/planners/costs/factors/mp_priors_multi.py:253-256) including the noise draw
+// torch does inside MultivariateNormal.rsample.  The factor decouples over the dofs (sample_gp_kron.cu), so per dof j
+//     X_j^T [2H x samples] = L_j [2H x 2H] * E_j^T [2H x samples]
+// which this kernel runs on tcgen05 with the FACTOR as the M = 128 operand and a tile of 64 samples as N: the seven
+// accumulators of a tile (7 x 64 fp32 columns) fit tensor memory at once, so every noise value is generated exactly once
+// and every factor chunk is streamed once per tile.  FP32 accuracy comes from a two-term fp16 split of both operands
+// (kind::f16, three MMAs per k-step: hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; the factor is scaled per dof by a
+// power of two so that its fp16 parts stay normal) -- the same arithmetic as the warp-MMA kernel it supersedes.
+//
+// One persistent CTA per SM, warp-specialised (704 threads for the 7-dof arm):
+//   warp 0       factor loader: one elected lane streams the 56 KiB factor chunk of each k-step (16 k x 7 dofs x hi/lo,
+//                pre-arranged on the host side of the C ABI in the exact shared-memory image) with ONE bulk-async copy
+//                (TMA engine, mbarrier complete_tx) into a 2-stage ring
+//   warp 1       MMA issuer: one elected lane, 21 tcgen05.mma.kind::f16 (M128 x N64 x K16) per k-step
+//   warps 4-7    epilogue: tcgen05.ld the accumulators (thread = output row n of every dof), x = mu + acc / scale, dofs
+//                re-interleaved into full trajectory rows in shared memory (conflict-free: lane stride 7 words), rows
+//                leave through bulk-async stores (14 KiB each), double buffered
+//   warps 8-21   noise producers: Philox4x32-10 + Box-Muller, split into fp16 hi / lo and written with 8-byte stores
+//                straight into the canonical K-major (no swizzle) operand tiles of a 3-stage ring; the lane mapping makes
+//                every store bank-conflict free
+// Noise layout MPB_NOISE_SPMD: the virtual global tensor is [S_glob, P_glob, dof, 2H] (dof-major inside a row), so the
+// four normals of one Philox call are four consecutive k of ONE dof -- one 8-byte store per operand part.  As with the
+// other layouts a value depends only on (seed, offset, global sample, global particle, element): results do not depend
+// on the sharding.  mpb_philox_normal(MPB_NOISE_SPMD) dumps the same numbers in the [S,P,M] order the injected-noise
+// kernels read, which is how the tests replay a run through the oracle.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
+#include "mpb_common.cuh"
+#include "philox.cuh"
+#include "tcgen05.cuh"
+
+namespace mpb {
+
+template <int DOF>
+struct GenCfg {
+    static constexpr int NOUT = 128;                         // 2H = rows of a per-dof block (UMMA M); H = 64
+    static constexpr int TS = 64;                            // samples per tile (UMMA N)
+    static constexpr int KC = 16;                            // k per stage = one kind::f16 MMA
+    static constexpr int NKC = NOUT / KC;
+    static constexpr int M = NOUT * DOF;                     // floats per trajectory row
+    static constexpr uint32_t B_TILE = TS * KC * 2;          // noise tile of one (dof, part): 2 KiB
+    static constexpr uint32_t A_TILE = NOUT * KC * 2;        // factor tile of one (dof, part): 4 KiB
+    static constexpr uint32_t B_STAGE = DOF * 2 * B_TILE;
+    static constexpr uint32_t A_STAGE = DOF * 2 * A_TILE;
+    static constexpr int B_STAGES = 3, A_STAGES = 2;
+    static constexpr int OUT_ROWS = 4;                       // samples per staged output batch
+    static constexpr uint32_t OUT_BUF = OUT_ROWS * M * 4;
+    static constexpr int PROD_WARPS = 2 * DOF;
+    static constexpr int FIRST_EPI_WARP = 4, FIRST_PROD_WARP = 8;
+    static constexpr int THREADS = (FIRST_PROD_WARP + PROD_WARPS) * 32;
+    static constexpr uint32_t OFF_A = 0;
+    static constexpr uint32_t OFF_B = OFF_A + A_STAGES * A_STAGE;
+    static constexpr uint32_t OFF_OUT = OFF_B + B_STAGES * B_STAGE;
+    static constexpr uint32_t OFF_BAR = OFF_OUT + 2 * OUT_BUF;
+    static constexpr uint32_t SMEM = OFF_BAR + 256 + 128 /*alignment slack*/;
+    static constexpr uint32_t TMEM_COLS = DOF * TS <= 256 ? 256 : 512;
+    static_assert(DOF * TS <= 512, "accumulators must fit tensor memory");
+    static_assert(SMEM <= 227 * 1024, "shared-memory budget");
+};
+
+struct GenArgs {
+    const unsigned char* Limg;      // [NKC][DOF][hi|lo][A_TILE bytes] + inverse scales (DOF floats) behind it
+    const float* mu;                // [P, M]
+    float* x;                       // [P, S, M]
+    int P, S;
+    long long Ntot;                 // P * S rows
+    int ntiles;
+    int swap_strides;               // debug: exchange the two descriptor strides (MPB_KRON_GEN_DBG=1)
+};
+
+// fp16 hi / lo parts of four floats -> two 8-byte words
+__device__ __forceinline__ void split4_f16(const float4 v, uint2& hi, uint2& lo) {
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(__fsub_rn(v.x, f01.x), __fsub_rn(v.y, f01.y));
+    const __half2 l23 = __floats2half2_rn(__fsub_rn(v.z, f23.x), __fsub_rn(v.w, f23.y));
+    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
+
+template <int DOF>
+__global__ void __launch_bounds__(GenCfg<DOF>::THREADS, 1)
+sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
+    using C = GenCfg<DOF>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+    uint64_t* a_full = bars;                           // [A_STAGES] factor chunk landed
+    uint64_t* a_empty = a_full + C::A_STAGES;          // [A_STAGES] MMAs that read it completed
+    uint64_t* b_full = a_empty + C::A_STAGES;          // [B_STAGES] noise chunk written (PROD_WARPS arrivals)
+    uint64_t* b_empty = b_full + C::B_STAGES;          // [B_STAGES]
+    uint64_t* acc_full = b_empty + C::B_STAGES;        // accumulators of the tile complete
+    uint64_t* acc_empty = acc_full + 1;                // accumulators drained (4 epilogue warps)
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], C::PROD_WARPS); mbar_init(&b_empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_base_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ================================ factor loader ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+                for (int kc = 0; kc < C::NKC; ++kc) {
+                    mbar_wait(&a_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&a_full[stage], C::A_STAGE);
+                    bulk_load(sm + C::OFF_A + stage * C::A_STAGE, a.Limg + (size_t)kc * C::A_STAGE, C::A_STAGE, &a_full[stage]);
+                    if (++stage == C::A_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ===================================
+        if (lane == 0) {
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0, acc_ph = 0;
+            const uint32_t idesc = make_idesc_f16(C::NOUT, C::TS);
+            const uint32_t lbo = a.swap_strides ? 256u : 128u, sbo = a.swap_strides ? 128u : 256u;
+            for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+                mbar_wait(acc_empty, acc_ph ^ 1);
+                tc_fence_after();
+                for (int kc = 0; kc < C::NKC; ++kc) {
+                    mbar_wait(&a_full[as], aph);
+                    mbar_wait(&b_full[bs], bph);
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(sm + C::OFF_A + as * C::A_STAGE);
+                    const uint32_t bbase = smem_u32(sm + C::OFF_B + bs * C::B_STAGE);
+#pragma unroll
+                    for (int j = 0; j < DOF; ++j) {
+                        const uint64_t ahi = make_nosw_desc(abase + (2 * j) * C::A_TILE, lbo, sbo);
+                        const uint64_t alo = make_nosw_desc(abase + (2 * j + 1) * C::A_TILE, lbo, sbo);
+                        const uint64_t bhi = make_nosw_desc(bbase + (2 * j) * C::B_TILE, lbo, sbo);
+                        const uint64_t blo = make_nosw_desc(bbase + (2 * j + 1) * C::B_TILE, lbo, sbo);
+                        const uint32_t d = tmem_base + (uint32_t)(j * C::TS);
+                        umma_f16(d, alo, bhi, idesc, kc ? 1u : 0u);          // small terms first
+                        umma_f16(d, ahi, blo, idesc, 1u);
+                        umma_f16(d, ahi, bhi, idesc, 1u);
+                    }
+                    umma_commit(&a_empty[as]);
+                    umma_commit(&b_empty[bs]);
+                    if (++as == C::A_STAGES) { as = 0; aph ^= 1; }
+                    if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
+                }
+                umma_commit(acc_full);
+                acc_ph ^= 1;
+            }
+        }
+    } else if (warp >= C::FIRST_EPI_WARP && warp < C::FIRST_EPI_WARP + 4) {
+        // ================================ epilogue =====================================
+        const int q4 = warp & 3;
+        const int n_out = 32 * q4 + lane;                       // TMEM lane = output row of every dof
+        const int et = threadIdx.x - C::FIRST_EPI_WARP * 32;    // 0..127
+        const float* inv_scale_g = reinterpret_cast<const float*>(a.Limg + (size_t)C::NKC * C::A_STAGE);
+        float inv_scale[DOF];
+#pragma unroll
+        for (int j = 0; j < DOF; ++j) inv_scale[j] = __ldg(inv_scale_g + j);
+        const bool one_particle = (a.S % C::TS) == 0;
+        uint32_t acc_ph = 0;
+        int buf = 0;
+        for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+            const long long row0 = (long long)t * C::TS;
+            float mrow[DOF];
+            if (one_particle) {
+                const float* mp = a.mu + (size_t)(row0 / a.S) * C::M + DOF * n_out;
+#pragma unroll
+                for (int j = 0; j < DOF; ++j) mrow[j] = __ldg(mp + j);
+            }
+            mbar_wait(acc_full, acc_ph);
+            tc_fence_after();
+            for (int b = 0; b < C::TS / C::OUT_ROWS; ++b, buf ^= 1) {
+                if (et == 0) bulk_wait_read<1>();               // the store that last read this buffer has drained it
+                named_bar_sync(1, 128);
+                uint32_t r[DOF][4];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * C::OUT_ROWS);
+#pragma unroll
+                for (int j = 0; j < DOF; ++j) tmem_ld4_nowait(taddr + (uint32_t)(j * C::TS), r[j]);
+                tmem_wait_ld();
+                float* ob = reinterpret_cast<float*>(sm + C::OFF_OUT + buf * C::OUT_BUF) + DOF * n_out;
+#pragma unroll
+                for (int sl = 0; sl < C::OUT_ROWS; ++sl) {
+                    if (!one_particle) {
+                        const long long row = row0 + b * C::OUT_ROWS + sl;
+                        const long long p = (row < a.Ntot ? row : a.Ntot - 1) / a.S;
+                        const float* mp = a.mu + (size_t)p * C::M + DOF * n_out;
+#pragma unroll
+                        for (int j = 0; j < DOF; ++j) mrow[j] = __ldg(mp + j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < DOF; ++j) ob[sl * C::M + j] = fmaf(__uint_as_float(r[j][sl]), inv_scale[j], mrow[j]);
+                }
+                fence_async_proxy();
+                named_bar_sync(1, 128);
+                if (et == 0) {
+                    const long long first = row0 + b * C::OUT_ROWS;
+                    long long rows = a.Ntot - first;
+                    if (rows > C::OUT_ROWS) rows = C::OUT_ROWS;
+                    if (rows > 0)
+                        bulk_store(a.x + (size_t)first * C::M, sm + C::OFF_OUT + buf * C::OUT_BUF, (uint32_t)(rows * C::M * 4));
+                    bulk_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+            acc_ph ^= 1;
+        }
+        if (et == 0) bulk_wait<0>();
+    } else if (warp >= C::FIRST_PROD_WARP) {
+        // ================================ noise producers ==============================
+        const int pw = warp - C::FIRST_PROD_WARP;
+        const int j = pw % DOF, g2 = pw / DOF;                  // dof, one bit of the 8-sample group
+        const int r8 = lane & 7, par = (lane >> 3) & 1, g1 = lane >> 4;
+        int bs = 0;
+        uint32_t bph = 0;
+        for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+            // the two samples of this thread in the tile and their rows in the virtual global noise tensor
+            long long grow[2];
+            int sgrp[2];
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                sgrp[it] = g1 + 2 * g2 + 4 * it;
+                const long long n = (long long)t * C::TS + sgrp[it] * 8 + r8;
+                if (n < a.Ntot) {
+                    const long long p = n / a.S, s = n - p * a.S;
+                    grow[it] = (((noise.s_off + s) * noise.P_glob + noise.p_off + p) * DOF + j) * (C::NOUT / 4);
+                } else {
+                    grow[it] = -1;
+                }
+            }
+            for (int kc = 0; kc < C::NKC; ++kc) {
+                mbar_wait(&b_empty[bs], bph ^ 1);
+                unsigned char* tile = sm + C::OFF_B + bs * C::B_STAGE + (2 * j) * C::B_TILE;
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        const int q = 2 * qq + par;                            // 4-k group inside the chunk
+                        uint2 hi = make_uint2(0u, 0u), lo = hi;
+                        if (grow[it] >= 0) split4_f16(philox_normal4((unsigned long long)grow[it] + (unsigned)(kc * 4 + q), noise), hi, lo);
+                        // (sample row, k) -> core matrix (row / 8, k / 8): 16-byte rows, K groups 128 B apart, row groups 256 B
+                        const uint32_t off = (uint32_t)(sgrp[it] * 256 + (q >> 1) * 128 + r8 * 16 + (q & 1) * 8);
+                        *reinterpret_cast<uint2*>(tile + off) = hi;
+                        *reinterpret_cast<uint2*>(tile + C::B_TILE + off) = lo;
+                    }
+                }
+                fence_async_proxy();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_full[bs]);
+                if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// Factor image: per k-chunk kc, dof j, part (hi | lo): the [128 x 16] fp16 tile  A[n][k] = L_j[n][16 kc + k] * scale_j
+// in the canonical K-major no-swizzle layout (8-row x 16-byte core matrices, K groups 128 B apart, row groups 256 B apart).
+__global__ void kron_gen_image_kernel(const float* __restrict__ LkT, unsigned char* __restrict__ img, const unsigned* __restrict__ maxbits,
+                                      int dof) {
+    constexpr int N = 128, KC = 16, NKC = 8;
+    const long long total = (long long)dof * N * N;
+    float* inv_scale = reinterpret_cast<float*>(img + (size_t)NKC * dof * 2 * N * KC * 2);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(idx % N);
+        const int k = (int)((idx / N) % N);
+        const int j = (int)(idx / ((long long)N * N));
+        const float mx = __uint_as_float(maxbits[j]);
+        const float scale = mx > 0.f ? exp2f((float)(13 - ilogbf(mx))) : 1.f;
+        if (n == 0 && k == 0) inv_scale[j] = 1.f / scale;
+        const float v = LkT[((size_t)j * N + k) * N + n] * scale;               // LkT[j][k][n] = L_j[n][k]
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(__fsub_rn(v, __half2float(hi)));
+        const int kc = k / KC, kk = k % KC;
+        const size_t tile = ((size_t)(kc * dof + j) * 2) * (N * KC * 2);
+        const size_t off = (size_t)(n >> 3) * 256 + (kk >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2;
+        *reinterpret_cast<__half*>(img + tile + off) = hi;
+        *reinterpret_cast<__half*>(img + tile + N * KC * 2 + off) = lo;
+    }
+}
+__global__ void kron_gen_max_kernel(const float* __restrict__ LkT, unsigned* __restrict__ maxbits, int N, int dof) {
+    const long long total = (long long)dof * N * N;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+        atomicMax(maxbits + (int)(idx / ((long long)N * N)), __float_as_uint(fabsf(LkT[idx])));
+}
+
+}  // namespace mpb
+
+extern "C" int mpb_sample_gp_kron_gen_supported(int H, int dof) { return (H == 64 && dof == 7) ? 1 : 0; }
+
+extern "C" long long mpb_sample_gp_kron_gen_bytes(int H, int dof) {
+    return (long long)dof * 2 * (2 * H) * (2 * H) * 2 + 64 * 4;       // fp16 hi + lo image, inverse scales (16 words), scratch
+}
+
+extern "C" int mpb_sample_gp_kron_gen_prepare(const float* LkT, void* Limg, int H, int dof, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(LkT && Limg, "mpb_sample_gp_kron_gen_prepare: null pointer");
+    MPB_REQUIRE(mpb_sample_gp_kron_gen_supported(H, dof), "mpb_sample_gp_kron_gen_prepare: shape H=%d dof=%d not supported", H, dof);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int N = 2 * H;
+    const long long total = (long long)dof * N * N;
+    unsigned char* img = static_cast<unsigned char*>(Limg);
+    unsigned* tail = reinterpret_cast<unsigned*>(img + total * 4);
+    cudaError_t e = cudaMemsetAsync(tail, 0, 64 * 4, st);
+    if (e != cudaSuccess) { set_error("mpb_sample_gp_kron_gen_prepare: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+    const int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+    kron_gen_max_kernel<<<grid, 256, 0, st>>>(LkT, tail + 16, N, dof);
+    kron_gen_image_kernel<<<grid, 256, 0, st>>>(LkT, img, tail + 16, dof);
+    return check_launch("mpb_sample_gp_kron_gen_prepare");
+}
+
+extern "C" int mpb_sample_gp_kron_gen(const void* Limg, const float* mu, const mpb_noise_desc* nd, float* x, int P, int S, int H,
+                                      int dof, void* stream) {
+    using namespace mpb;
+    MPB_REQUIRE(Limg && mu && nd && x, "mpb_sample_gp_kron_gen: null pointer");
+    MPB_REQUIRE(P >= 0 && S >= 0, "mpb_sample_gp_kron_gen: bad sizes P=%d S=%d", P, S);
+    MPB_REQUIRE(mpb_sample_gp_kron_gen_supported(H, dof), "mpb_sample_gp_kron_gen: shape H=%d dof=%d not supported", H, dof);
+    MPB_REQUIRE(((uintptr_t)Limg | (uintptr_t)mu | (uintptr_t)x) % 16 == 0, "mpb_sample_gp_kron_gen: pointers must be 16-byte aligned");
+    if (P == 0 || S == 0) return MPB_OK;
+    using C = GenCfg<7>;
+    GenArgs a{};
+    NoiseArgs noise{};
+    const char* why = noise_args(*nd, P, noise);
+    MPB_REQUIRE(!why, "mpb_sample_gp_kron_gen: %s", why);
+    a.Limg = static_cast<const unsigned char*>(Limg);
+    a.mu = mu; a.x = x; a.P = P; a.S = S;
+    a.Ntot = (long long)P * S;
+    a.ntiles = (int)((a.Ntot + C::TS - 1) / C::TS);
+    { const char* v = getenv("MPB_KRON_GEN_DBG"); a.swap_strides = (v && atoi(v) == 1) ? 1 : 0; }
+    cudaError_t e = cudaFuncSetAttribute(sample_gp_kron_gen_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) { set_error("mpb_sample_gp_kron_gen: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
+    const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
+    sample_gp_kron_gen_kernel<7><<<grid, C::THREADS, C::SMEM, static_cast<cudaStream_t>(stream)>>>(a, noise);
+    return check_launch("mpb_sample_gp_kron_gen");
+}

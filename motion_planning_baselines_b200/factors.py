@@ -107,6 +107,7 @@ class MultiMPPrior:
         H = num_steps + 1
         self.scale_tril_kron = None
         self.scale_tril_kron_tc, self.kron_tc_kind = None, 0
+        self.scale_tril_kron_gen = None
         if mode in ('auto', 'kron', 'kron_umma', 'kron_fp32') and state_dim == 2 * dof and _lib.lib().mpb_sample_gp_kron_supported(H, dof):
             packed = torch.empty(dof, 2 * H, 2 * H, **tensor_args)
             ok = C.c_int(0)
@@ -129,6 +130,13 @@ class MultiMPPrior:
                     _lib.check(lib.mpb_sample_gp_kron_tc_prepare(_lib.ptr(packed), _lib.ptr(self.scale_tril_kron_tc),
                                                                  H, dof, _lib.stream_ptr()))
                     self.kron_tc_kind = 1
+                    # Blackwell path for the in-kernel noise draw (tcgen05 + bulk-async copies; noise layout NOISE_SPMD):
+                    # the default wherever it is built; MPB_SAMPLE_GP=kron keeps the warp-MMA kernel for both draws
+                    if mode == 'auto' and lib.mpb_sample_gp_kron_gen_supported(H, dof):
+                        self.scale_tril_kron_gen = torch.empty(lib.mpb_sample_gp_kron_gen_bytes(H, dof),
+                                                               device=tensor_args['device'], dtype=torch.uint8)
+                        _lib.check(lib.mpb_sample_gp_kron_gen_prepare(_lib.ptr(packed), _lib.ptr(self.scale_tril_kron_gen),
+                                                                      H, dof, _lib.stream_ptr()))
         self.scale_tril_split = None
         if self.scale_tril_kron is None and mode != 'simt' and _lib.lib().mpb_sample_gp_tc_supported(1, 1, self.M):
             self.scale_tril_split = torch.empty(2, self.M, self.M, **tensor_args)
@@ -163,6 +171,16 @@ class MultiMPPrior:
         assert means_new.shape == self.means.shape
         self.means = means_new.clone().detach().contiguous()
 
+    @property
+    def noise_layout(self):
+        """Layout of the virtual global noise tensor the in-kernel draw of sample() uses (for _lib.philox_normal replays)."""
+        return _lib.NOISE_SPMD if self.scale_tril_kron_gen is not None else _lib.NOISE_SPM
+
+    def replay_noise(self, noise_desc, num_samples):
+        """The [S,P,M] noise sample(num_samples, noise_desc=noise_desc) draws -- feed it back as ``eps`` to replay a run."""
+        return _lib.philox_normal(noise_desc, self.noise_layout, (num_samples, self.num_modes, self.M),
+                                  self.tensor_args['device'], dof=self.dof)
+
     def sample(self, num_samples, eps=None, out=None, noise_desc=None):
         """-> [num_modes, num_samples, H, state_dim].  ``eps`` ([S,P,M], the layout torch draws) can be injected for
         parity runs; otherwise the noise is drawn on the device by Philox keyed on the global element index
@@ -173,6 +191,10 @@ class MultiMPPrior:
         lib = _lib.lib()
         if eps is None:
             nd = noise_desc if noise_desc is not None else self.noise.next()
+            if self.scale_tril_kron_gen is not None:
+                _lib.check(lib.mpb_sample_gp_kron_gen(_lib.ptr(self.scale_tril_kron_gen), _lib.ptr(self.means), C.byref(nd),
+                                                      _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))
+                return x.view(P, S, self.num_steps + 1, self.state_dim)
             if self.kron_tc_kind == 1:
                 _lib.check(lib.mpb_sample_gp_kron_tc_rng(_lib.ptr(self.scale_tril_kron_tc), _lib.ptr(self.means), C.byref(nd),
                                                          _lib.ptr(x), P, S, self.num_steps + 1, self.dof, _lib.stream_ptr()))

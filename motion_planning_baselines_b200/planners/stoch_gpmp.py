@@ -190,7 +190,14 @@ class StochGPMP(OptimizationPlanner):
                 pos_mean, vel_mean = pre[..., :self.n_dof], pre[..., -self.n_dof:]
             if eps is None:
                 nd = self._noise.next()
-                if sd.kron_tc_kind == 1:        # default: the noise is drawn inside K1
+                if sd.scale_tril_kron_gen is not None:      # default: Blackwell sampler, noise drawn inside K1
+                    _lib.check(lib.mpb_stoch_gpmp_iter_kron_gen(
+                        _lib.ptr(sd.scale_tril_kron_gen), _lib.ptr(self.Sigma_inv), int(self._sinv_structured), C.byref(nd),
+                        _lib.ptr(self._particle_means), _lib.ptr(self.state_samples), _lib.ptr(self.costs), _lib.ptr(self._w_buf),
+                        _lib.ptr(self._is_vec), _lib.ptr(self.free_flags), P, S, H,
+                        C.byref(self.robot.desc), fields, nf, C.byref(gp), self.temperature, self.step_size, _lib.stream_ptr()))
+                    continue
+                if sd.kron_tc_kind == 1:        # warp-MMA sampler, noise drawn inside K1
                     _lib.check(lib.mpb_stoch_gpmp_iter_kron_rng(
                         _lib.ptr(sd.scale_tril_kron_tc), _lib.ptr(self.Sigma_inv), int(self._sinv_structured), C.byref(nd),
                         _lib.ptr(self._particle_means), _lib.ptr(self.state_samples), _lib.ptr(self.costs), _lib.ptr(self._w_buf),

@@ -103,8 +103,10 @@ def test_moments_and_ks(dev):
 
 
 @pytest.mark.parametrize('P,S', [(8, 64), (5, 24), (3, 7)])
-def test_k1_fused_noise_is_bit_identical_to_dump_then_sample(P, S, dev):
+def test_k1_fused_noise_is_bit_identical_to_dump_then_sample(P, S, dev, monkeypatch):
     from motion_planning_baselines_b200.factors import GPFactor, MultiMPPrior, UnaryFactor
+    monkeypatch.setenv('MPB_SAMPLE_GP', 'kron')      # the warp-MMA sampler draws and reads noise in ONE kernel body: bit identity
+
     d, H, dt = 7, 64, 5 / 64
     K = UnaryFactor(2 * d, 1e-3, None, dev).K
     Q = GPFactor(d, 1e-1, dt, H - 1, dev).Q_inv[0]
@@ -217,7 +219,7 @@ def test_planner_default_noise_replays_through_the_oracle(cfg_name, P, S, H, dev
     means0 = pl._particle_means.clone()
     desc = pl._noise.desc()
     traj = pl.optimize(opt_iters=1)                      # no noise argument: drawn inside K1
-    eps = _lib.philox_normal(desc, _lib.NOISE_SPM, (S, P, H * 2 * d), dev['device'])
+    eps = pl._sample_dist.replay_noise(desc, S)
     ref = check.stoch_gpmp_subset(cfg, H, sig, means0, pl._sample_dist.scale_tril, pl.Sigma_inv, eps, range(P))
     amp = float((ref['samples'] - means0.cpu().unsqueeze(1)).abs().max())
     assert_close(pl.state_samples, ref['samples'], rtol=1e-5, atol=1e-5 * amp + 1e-7, what='samples')
