@@ -70,7 +70,9 @@ struct GenArgs {
     int P, S;
     long long Ntot;                 // P * S rows
     int ntiles;
-    int swap_strides;               // debug: exchange the two descriptor strides (MPB_KRON_GEN_DBG=1)
+    long long* trace;               // optional [64] clock stamps of CTA 0 (MPB_KRON_GEN_TRACE = device pointer; timing experiments)
+    int dbg;                        // MPB_KRON_GEN_DBG bit mask (timing experiments only): 1 no Philox (zeros), 2 no MMAs,
+                                    // 4 no output stores, 8 no factor loads, 128 no epilogue TMEM loads, 256 no epilogue smem writes
 };
 
 // fp16 hi / lo parts of four floats -> two 8-byte words
@@ -81,6 +83,10 @@ __device__ __forceinline__ void split4_f16(const float4 v, uint2& hi, uint2& lo)
     const __half2 l23 = __floats2half2_rn(__fsub_rn(v.z, f23.x), __fsub_rn(v.w, f23.y));
     hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
     lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
+
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
 template <int DOF>
@@ -99,6 +105,11 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // slot = 8 * tile ordinal + event: 0 MMA first chunk ready, 1 MMA tile committed, 2 epilogue start, 3 epilogue end,
+    // 4 producer first chunk written, 5 producer last chunk written, 6 MMA got the accumulators
+    auto stamp = [&](int ordinal, int ev) {
+        if (a.trace && blockIdx.x == 0 && ordinal < 8) a.trace[8 * ordinal + ev] = clock64();
+    };
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], C::PROD_WARPS); mbar_init(&b_empty[s], 1); }
@@ -120,8 +131,12 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
                 for (int kc = 0; kc < C::NKC; ++kc) {
                     mbar_wait(&a_empty[stage], phase ^ 1);
-                    mbar_expect_tx(&a_full[stage], C::A_STAGE);
-                    bulk_load(sm + C::OFF_A + stage * C::A_STAGE, a.Limg + (size_t)kc * C::A_STAGE, C::A_STAGE, &a_full[stage]);
+                    if (a.dbg & 8) {
+                        mbar_arrive(&a_full[stage]);
+                    } else {
+                        mbar_expect_tx(&a_full[stage], C::A_STAGE);
+                        bulk_load(sm + C::OFF_A + stage * C::A_STAGE, a.Limg + (size_t)kc * C::A_STAGE, C::A_STAGE, &a_full[stage]);
+                    }
                     if (++stage == C::A_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -132,18 +147,21 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0, acc_ph = 0;
             const uint32_t idesc = make_idesc_f16(C::NOUT, C::TS);
-            const uint32_t lbo = a.swap_strides ? 256u : 128u, sbo = a.swap_strides ? 128u : 256u;
-            for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+            const uint32_t lbo = 128u, sbo = 256u;
+            int ord = 0;
+            for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++ord) {
                 mbar_wait(acc_empty, acc_ph ^ 1);
                 tc_fence_after();
+                stamp(ord, 6);
                 for (int kc = 0; kc < C::NKC; ++kc) {
                     mbar_wait(&a_full[as], aph);
                     mbar_wait(&b_full[bs], bph);
                     tc_fence_after();
+                    if (kc == 0) stamp(ord, 0);
                     const uint32_t abase = smem_u32(sm + C::OFF_A + as * C::A_STAGE);
                     const uint32_t bbase = smem_u32(sm + C::OFF_B + bs * C::B_STAGE);
 #pragma unroll
-                    for (int j = 0; j < DOF; ++j) {
+                    for (int j = 0; j < ((a.dbg & 2) ? 0 : DOF); ++j) {
                         const uint64_t ahi = make_nosw_desc(abase + (2 * j) * C::A_TILE, lbo, sbo);
                         const uint64_t alo = make_nosw_desc(abase + (2 * j + 1) * C::A_TILE, lbo, sbo);
                         const uint64_t bhi = make_nosw_desc(bbase + (2 * j) * C::B_TILE, lbo, sbo);
@@ -159,6 +177,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                     if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
                 }
                 umma_commit(acc_full);
+                stamp(ord, 1);
                 acc_ph ^= 1;
             }
         }
@@ -184,14 +203,20 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             }
             mbar_wait(acc_full, acc_ph);
             tc_fence_after();
+            if (et == 0) stamp((t - blockIdx.x) / gridDim.x, 2);
             for (int b = 0; b < C::TS / C::OUT_ROWS; ++b, buf ^= 1) {
                 if (et == 0) bulk_wait_read<1>();               // the store that last read this buffer has drained it
                 named_bar_sync(1, 128);
                 uint32_t r[DOF][4];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * C::OUT_ROWS);
+                if (!(a.dbg & 128)) {
 #pragma unroll
-                for (int j = 0; j < DOF; ++j) tmem_ld4_nowait(taddr + (uint32_t)(j * C::TS), r[j]);
-                tmem_wait_ld();
+                    for (int j = 0; j < DOF; ++j) tmem_ld4_nowait(taddr + (uint32_t)(j * C::TS), r[j]);
+                    tmem_wait_ld();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < DOF; ++j) r[j][0] = r[j][1] = r[j][2] = r[j][3] = 0u;
+                }
                 float* ob = reinterpret_cast<float*>(sm + C::OFF_OUT + buf * C::OUT_BUF) + DOF * n_out;
 #pragma unroll
                 for (int sl = 0; sl < C::OUT_ROWS; ++sl) {
@@ -202,6 +227,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
 #pragma unroll
                         for (int j = 0; j < DOF; ++j) mrow[j] = __ldg(mp + j);
                     }
+                    if (a.dbg & 256) continue;
 #pragma unroll
                     for (int j = 0; j < DOF; ++j) ob[sl * C::M + j] = fmaf(__uint_as_float(r[j][sl]), inv_scale[j], mrow[j]);
                 }
@@ -211,7 +237,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                     const long long first = row0 + b * C::OUT_ROWS;
                     long long rows = a.Ntot - first;
                     if (rows > C::OUT_ROWS) rows = C::OUT_ROWS;
-                    if (rows > 0)
+                    if (rows > 0 && !(a.dbg & 4))
                         bulk_store(a.x + (size_t)first * C::M, sm + C::OFF_OUT + buf * C::OUT_BUF, (uint32_t)(rows * C::M * 4));
                     bulk_commit();
                 }
@@ -219,6 +245,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
+            if (et == 0) stamp((t - blockIdx.x) / gridDim.x, 3);
             acc_ph ^= 1;
         }
         if (et == 0) bulk_wait<0>();
@@ -236,33 +263,44 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
                 sgrp[it] = g1 + 2 * g2 + 4 * it;
-                const long long n = (long long)t * C::TS + sgrp[it] * 8 + r8;
-                if (n < a.Ntot) {
-                    const long long p = n / a.S, s = n - p * a.S;
-                    grow[it] = (((noise.s_off + s) * noise.P_glob + noise.p_off + p) * DOF + j) * (C::NOUT / 4);
-                } else {
-                    grow[it] = -1;
-                }
+                long long n = (long long)t * C::TS + sgrp[it] * 8 + r8;
+                if (n >= a.Ntot) n = a.Ntot - 1;                  // rows past the end are never stored
+                const long long p = n / a.S, s = n - p * a.S;
+                grow[it] = (((noise.s_off + s) * noise.P_glob + noise.p_off + p) * DOF + j) * (C::NOUT / 4);
             }
             for (int kc = 0; kc < C::NKC; ++kc) {
                 mbar_wait(&b_empty[bs], bph ^ 1);
-                unsigned char* tile = sm + C::OFF_B + bs * C::B_STAGE + (2 * j) * C::B_TILE;
+                const uint32_t tile = smem_u32(sm + C::OFF_B + bs * C::B_STAGE + (2 * j) * C::B_TILE);
+                // the four Philox / Box-Muller chains of this thread are generated together (no branches in between) so
+                // that their long dependency chains interleave; rows past the end draw (unused) values like any other
+                uint2 hi[4], lo[4];
+                if (!(a.dbg & 1)) {
+                    float4 e[4];
 #pragma unroll
-                for (int it = 0; it < 2; ++it) {
+                    for (int it = 0; it < 2; ++it)
+#pragma unroll
+                        for (int qq = 0; qq < 2; ++qq)
+                            e[2 * it + qq] = philox_normal4((unsigned long long)grow[it] + (unsigned)(kc * 4 + 2 * qq + par), noise);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) split4_f16(e[i], hi[i], lo[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) hi[i] = lo[i] = make_uint2(0u, 0u);
+                }
+#pragma unroll
+                for (int it = 0; it < 2; ++it)
 #pragma unroll
                     for (int qq = 0; qq < 2; ++qq) {
                         const int q = 2 * qq + par;                            // 4-k group inside the chunk
-                        uint2 hi = make_uint2(0u, 0u), lo = hi;
-                        if (grow[it] >= 0) split4_f16(philox_normal4((unsigned long long)grow[it] + (unsigned)(kc * 4 + q), noise), hi, lo);
                         // (sample row, k) -> core matrix (row / 8, k / 8): 16-byte rows, K groups 128 B apart, row groups 256 B
-                        const uint32_t off = (uint32_t)(sgrp[it] * 256 + (q >> 1) * 128 + r8 * 16 + (q & 1) * 8);
-                        *reinterpret_cast<uint2*>(tile + off) = hi;
-                        *reinterpret_cast<uint2*>(tile + C::B_TILE + off) = lo;
+                        const uint32_t off = tile + (uint32_t)(sgrp[it] * 256 + (q >> 1) * 128 + r8 * 16 + (q & 1) * 8);
+                        st_shared_v2(off, hi[2 * it + qq]);
+                        st_shared_v2(off + C::B_TILE, lo[2 * it + qq]);
                     }
-                }
                 fence_async_proxy();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&b_full[bs]);
+                if (pw == 0 && lane == 0 && (kc == 0 || kc == C::NKC - 1)) stamp((t - blockIdx.x) / gridDim.x, kc == 0 ? 4 : 5);
                 if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
             }
         }
@@ -344,7 +382,8 @@ extern "C" int mpb_sample_gp_kron_gen(const void* Limg, const float* mu, const m
     a.mu = mu; a.x = x; a.P = P; a.S = S;
     a.Ntot = (long long)P * S;
     a.ntiles = (int)((a.Ntot + C::TS - 1) / C::TS);
-    { const char* v = getenv("MPB_KRON_GEN_DBG"); a.swap_strides = (v && atoi(v) == 1) ? 1 : 0; }
+    { const char* v = getenv("MPB_KRON_GEN_DBG"); a.dbg = v ? atoi(v) : 0; }
+    { const char* v = getenv("MPB_KRON_GEN_TRACE"); a.trace = v ? reinterpret_cast<long long*>(strtoull(v, nullptr, 0)) : nullptr; }
     cudaError_t e = cudaFuncSetAttribute(sample_gp_kron_gen_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) { set_error("mpb_sample_gp_kron_gen: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
     const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
