@@ -85,6 +85,27 @@ __device__ __forceinline__ void split4_f16(const float4 v, uint2& hi, uint2& lo)
     lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
 }
 
+// tcgen05.mma.kind::f16 with the two shared-memory descriptors given as (low word, common high word)
+__device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
@@ -143,41 +164,51 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ===================================
-        if (lane == 0) {
+        {
+            // the whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers); one elected
+            // lane issues
+            const bool leader = elect_one();
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0, acc_ph = 0;
             const uint32_t idesc = make_idesc_f16(C::NOUT, C::TS);
-            const uint32_t lbo = 128u, sbo = 256u;
+            const uint64_t adesc0 = make_nosw_desc(smem_u32(sm + C::OFF_A), 128u, 256u);
+            const uint64_t bdesc0 = make_nosw_desc(smem_u32(sm + C::OFF_B), 128u, 256u);
+            const uint32_t adesc_lo = (uint32_t)adesc0, bdesc_lo = (uint32_t)bdesc0, desc_hi = (uint32_t)(adesc0 >> 32);
             int ord = 0;
             for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++ord) {
                 mbar_wait(acc_empty, acc_ph ^ 1);
                 tc_fence_after();
-                stamp(ord, 6);
+                if (lane == 0) stamp(ord, 6);
                 for (int kc = 0; kc < C::NKC; ++kc) {
                     mbar_wait(&a_full[as], aph);
                     mbar_wait(&b_full[bs], bph);
                     tc_fence_after();
-                    if (kc == 0) stamp(ord, 0);
-                    const uint32_t abase = smem_u32(sm + C::OFF_A + as * C::A_STAGE);
-                    const uint32_t bbase = smem_u32(sm + C::OFF_B + bs * C::B_STAGE);
+                    if (kc == 0 && lane == 0) stamp(ord, 0);
+                    // descriptors differ only in the 14-bit start-address field: one 32-bit add each
+                    const uint32_t alo_w = adesc_lo + (uint32_t)((as * C::A_STAGE) >> 4);
+                    const uint32_t blo_w = bdesc_lo + (uint32_t)((bs * C::B_STAGE) >> 4);
+                    if (leader && !(a.dbg & 2)) {
 #pragma unroll
-                    for (int j = 0; j < ((a.dbg & 2) ? 0 : DOF); ++j) {
-                        const uint64_t ahi = make_nosw_desc(abase + (2 * j) * C::A_TILE, lbo, sbo);
-                        const uint64_t alo = make_nosw_desc(abase + (2 * j + 1) * C::A_TILE, lbo, sbo);
-                        const uint64_t bhi = make_nosw_desc(bbase + (2 * j) * C::B_TILE, lbo, sbo);
-                        const uint64_t blo = make_nosw_desc(bbase + (2 * j + 1) * C::B_TILE, lbo, sbo);
-                        const uint32_t d = tmem_base + (uint32_t)(j * C::TS);
-                        umma_f16(d, alo, bhi, idesc, kc ? 1u : 0u);          // small terms first
-                        umma_f16(d, ahi, blo, idesc, 1u);
-                        umma_f16(d, ahi, bhi, idesc, 1u);
+                        for (int j = 0; j < DOF; ++j) {
+                            const uint32_t ahi = alo_w + (uint32_t)(((2 * j) * C::A_TILE) >> 4), alo = ahi + (C::A_TILE >> 4);
+                            const uint32_t bhi = blo_w + (uint32_t)(((2 * j) * C::B_TILE) >> 4), blo = bhi + (C::B_TILE >> 4);
+                            const uint32_t d = tmem_base + (uint32_t)(j * C::TS);
+                            if (kc == 0) umma_f16_w(d, alo, bhi, desc_hi, idesc, 0u);          // small terms first
+                            else umma_f16_w(d, alo, bhi, desc_hi, idesc, 1u);
+                            umma_f16_w(d, ahi, blo, desc_hi, idesc, 1u);
+                            umma_f16_w(d, ahi, bhi, desc_hi, idesc, 1u);
+                        }
                     }
-                    umma_commit(&a_empty[as]);
-                    umma_commit(&b_empty[bs]);
+                    if (leader) {
+                        umma_commit(&a_empty[as]);
+                        umma_commit(&b_empty[bs]);
+                    }
+                    __syncwarp();
                     if (++as == C::A_STAGES) { as = 0; aph ^= 1; }
                     if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
                 }
-                umma_commit(acc_full);
-                stamp(ord, 1);
+                if (leader) umma_commit(acc_full);
+                if (lane == 0) stamp(ord, 1);
                 acc_ph ^= 1;
             }
         }
@@ -205,8 +236,13 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             tc_fence_after();
             if (et == 0) stamp((t - blockIdx.x) / gridDim.x, 2);
             for (int b = 0; b < C::TS / C::OUT_ROWS; ++b, buf ^= 1) {
-                if (et == 0) bulk_wait_read<1>();               // the store that last read this buffer has drained it
+                const bool tr_ = a.trace && blockIdx.x == 0 && et == 0 && t == blockIdx.x + (int)gridDim.x && (b == 4 || b == 5);
+                long long* tp_ = a.trace + 40 + (b - 4) * 8;
+                if (tr_) tp_[0] = clock64();
+                if (et == 0) bulk_wait_read<1>();
+                if (tr_) tp_[1] = clock64();               // the store that last read this buffer has drained it
                 named_bar_sync(1, 128);
+                if (tr_) tp_[2] = clock64();
                 uint32_t r[DOF][4];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * C::OUT_ROWS);
                 if (!(a.dbg & 128)) {
@@ -217,6 +253,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
 #pragma unroll
                     for (int j = 0; j < DOF; ++j) r[j][0] = r[j][1] = r[j][2] = r[j][3] = 0u;
                 }
+                if (tr_) tp_[3] = clock64();
                 float* ob = reinterpret_cast<float*>(sm + C::OFF_OUT + buf * C::OUT_BUF) + DOF * n_out;
 #pragma unroll
                 for (int sl = 0; sl < C::OUT_ROWS; ++sl) {
@@ -231,8 +268,11 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
 #pragma unroll
                     for (int j = 0; j < DOF; ++j) ob[sl * C::M + j] = fmaf(__uint_as_float(r[j][sl]), inv_scale[j], mrow[j]);
                 }
+                if (tr_) tp_[4] = clock64();
                 fence_async_proxy();
+                if (tr_) tp_[5] = clock64();
                 named_bar_sync(1, 128);
+                if (tr_) tp_[6] = clock64();
                 if (et == 0) {
                     const long long first = row0 + b * C::OUT_ROWS;
                     long long rows = a.Ntot - first;
@@ -240,6 +280,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                     if (rows > 0 && !(a.dbg & 4))
                         bulk_store(a.x + (size_t)first * C::M, sm + C::OFF_OUT + buf * C::OUT_BUF, (uint32_t)(rows * C::M * 4));
                     bulk_commit();
+                    if (tr_) tp_[7] = clock64();
                 }
             }
             tc_fence_before();

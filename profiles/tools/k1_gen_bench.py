@@ -33,7 +33,7 @@ for dbg in [0]:
 
 # timeline of CTA 0 (clock64 stamps through the MPB_KRON_GEN_TRACE debug hook)
 names = ['MMA chunk0 ready', 'MMA tile committed', 'epilogue start', 'epilogue end', 'producer chunk0 written', 'producer chunk7 written', 'MMA got acc_empty']
-for dbg in [0, 4, 128, 256, 1, 2]:
+for dbg in [0]:
     os.environ['MPB_KRON_GEN_DBG'] = str(dbg)
     tr = torch.zeros(64, dtype=torch.int64, device=dev['device'])
     os.environ['MPB_KRON_GEN_TRACE'] = str(tr.data_ptr())
@@ -45,3 +45,8 @@ for dbg in [0, 4, 128, 256, 1, 2]:
     t0 = int(t[t > 0].min())
     print(f'dbg={dbg}: per tile (cycles): ' + ' | '.join(
         f'k-loop {int(t[o, 1] - t[o, 0])}, production c0->c7 {int(t[o, 5] - t[o, 4])}, epilogue {int(t[o, 3] - t[o, 2])}, tile {int(t[o, 3] - t[o, 6])}' for o in range(4)))
+    f = tr.cpu()[40:56].view(2, 8)
+    for i in range(2):
+        v = [int(x) for x in f[i]]
+        print('   epilogue batch %d of tile 1 (cycles): wait_read %d, bar %d, tmem ld+wait %d, ffma+sts %d, fence %d, bar %d, store+commit %d' % (4 + i, v[1]-v[0], v[2]-v[1], v[3]-v[2], v[4]-v[3], v[5]-v[4], v[6]-v[5], v[7]-v[6]))
+    print('   batch 4 start -> batch 5 start', int(f[1][0] - f[0][0]))
