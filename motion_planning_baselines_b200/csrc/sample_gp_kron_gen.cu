@@ -17,7 +17,7 @@
 //   warp 1       MMA issuer: one elected lane, 21 tcgen05.mma.kind::f16 (M128 x N64 x K16) per k-step
 //   warps 4-7    epilogue: tcgen05.ld the accumulators (thread = output row n of every dof), x = mu + acc / scale, dofs
 //                re-interleaved into full trajectory rows in shared memory (conflict-free: lane stride 7 words), rows
-//                leave through bulk-async stores (14 KiB each), double buffered
+//                leave through bulk-async stores (14 KiB each), double buffered, issued by warp 2 (hand-off by mbarrier)
 //   warps 8-21   noise producers: Philox4x32-10 + Box-Muller, split into fp16 hi / lo and written with 8-byte stores
 //                straight into the canonical K-major (no swizzle) operand tiles of a 3-stage ring; the lane mapping makes
 //                every store bank-conflict free
@@ -123,7 +123,9 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
     uint64_t* b_empty = b_full + C::B_STAGES;          // [B_STAGES]
     uint64_t* acc_full = b_empty + C::B_STAGES;        // accumulators of the tile complete
     uint64_t* acc_empty = acc_full + 1;                // accumulators drained (4 epilogue warps)
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    uint64_t* out_full = acc_empty + 1;                // [2] staged rows written (128 epilogue threads)
+    uint64_t* out_empty = out_full + 2;                // [2] the bulk store has read the buffer (store warp)
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(out_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // slot = 8 * tile ordinal + event: 0 MMA first chunk ready, 1 MMA tile committed, 2 epilogue start, 3 epilogue end,
@@ -136,6 +138,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
         for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], C::PROD_WARPS); mbar_init(&b_empty[s], 1); }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 4);
+        for (int s = 0; s < 2; ++s) { mbar_init(&out_full[s], 128); mbar_init(&out_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_base_slot, C::TMEM_COLS);
@@ -222,8 +225,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
 #pragma unroll
         for (int j = 0; j < DOF; ++j) inv_scale[j] = __ldg(inv_scale_g + j);
         const bool one_particle = (a.S % C::TS) == 0;
-        uint32_t acc_ph = 0;
-        int buf = 0;
+        uint32_t acc_ph = 0, use = 0;                           // use: batches staged so far (all tiles)
         for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
             const long long row0 = (long long)t * C::TS;
             float mrow[DOF];
@@ -235,14 +237,8 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             mbar_wait(acc_full, acc_ph);
             tc_fence_after();
             if (et == 0) stamp((t - blockIdx.x) / gridDim.x, 2);
-            for (int b = 0; b < C::TS / C::OUT_ROWS; ++b, buf ^= 1) {
-                const bool tr_ = a.trace && blockIdx.x == 0 && et == 0 && t == blockIdx.x + (int)gridDim.x && (b == 4 || b == 5);
-                long long* tp_ = a.trace + 40 + (b - 4) * 8;
-                if (tr_) tp_[0] = clock64();
-                if (et == 0) bulk_wait_read<1>();
-                if (tr_) tp_[1] = clock64();               // the store that last read this buffer has drained it
-                named_bar_sync(1, 128);
-                if (tr_) tp_[2] = clock64();
+            for (int b = 0; b < C::TS / C::OUT_ROWS; ++b, ++use) {
+                const int buf = use & 1;
                 uint32_t r[DOF][4];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * C::OUT_ROWS);
                 if (!(a.dbg & 128)) {
@@ -253,7 +249,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
 #pragma unroll
                     for (int j = 0; j < DOF; ++j) r[j][0] = r[j][1] = r[j][2] = r[j][3] = 0u;
                 }
-                if (tr_) tp_[3] = clock64();
+                mbar_wait(&out_empty[buf], ((use >> 1) & 1) ^ 1);      // the store that last read this buffer has drained it
                 float* ob = reinterpret_cast<float*>(sm + C::OFF_OUT + buf * C::OUT_BUF) + DOF * n_out;
 #pragma unroll
                 for (int sl = 0; sl < C::OUT_ROWS; ++sl) {
@@ -268,20 +264,8 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
 #pragma unroll
                     for (int j = 0; j < DOF; ++j) ob[sl * C::M + j] = fmaf(__uint_as_float(r[j][sl]), inv_scale[j], mrow[j]);
                 }
-                if (tr_) tp_[4] = clock64();
                 fence_async_proxy();
-                if (tr_) tp_[5] = clock64();
-                named_bar_sync(1, 128);
-                if (tr_) tp_[6] = clock64();
-                if (et == 0) {
-                    const long long first = row0 + b * C::OUT_ROWS;
-                    long long rows = a.Ntot - first;
-                    if (rows > C::OUT_ROWS) rows = C::OUT_ROWS;
-                    if (rows > 0 && !(a.dbg & 4))
-                        bulk_store(a.x + (size_t)first * C::M, sm + C::OFF_OUT + buf * C::OUT_BUF, (uint32_t)(rows * C::M * 4));
-                    bulk_commit();
-                    if (tr_) tp_[7] = clock64();
-                }
+                mbar_arrive(&out_full[buf]);                    // the store warp takes it from here
             }
             tc_fence_before();
             __syncwarp();
@@ -289,7 +273,31 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             if (et == 0) stamp((t - blockIdx.x) / gridDim.x, 3);
             acc_ph ^= 1;
         }
-        if (et == 0) bulk_wait<0>();
+    } else if (warp == 2) {
+        // ================================ store issuer ==================================
+        // one lane: one bulk-async store (14 KiB of finished rows) per staged batch, so that no epilogue thread ever
+        // spends the ~200 cycles a bulk copy takes to issue; a buffer goes back once the store that read it has drained
+        if (lane == 0) {
+            uint32_t n = 0;
+            for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+                const long long row0 = (long long)t * C::TS;
+                for (int b = 0; b < C::TS / C::OUT_ROWS; ++b, ++n) {
+                    const int buf = n & 1;
+                    mbar_wait(&out_full[buf], (n >> 1) & 1);
+                    const long long first = row0 + b * C::OUT_ROWS;
+                    long long rows = a.Ntot - first;
+                    if (rows > C::OUT_ROWS) rows = C::OUT_ROWS;
+                    if (rows > 0 && !(a.dbg & 4))
+                        bulk_store(a.x + (size_t)first * C::M, sm + C::OFF_OUT + buf * C::OUT_BUF, (uint32_t)(rows * C::M * 4));
+                    bulk_commit();
+                    if (n >= 1) {
+                        bulk_wait_read<1>();                    // store n - 1 has read its buffer
+                        mbar_arrive(&out_empty[(n - 1) & 1]);
+                    }
+                }
+            }
+            bulk_wait<0>();
+        }
     } else if (warp >= C::FIRST_PROD_WARP) {
         // ================================ noise producers ==============================
         const int pw = warp - C::FIRST_PROD_WARP;

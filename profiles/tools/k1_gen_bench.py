@@ -17,7 +17,7 @@ mu = torch.randn(P, M, generator=gen, **dev)
 x = torch.empty(P, S, M, **dev)
 Limg = torch.empty(lib.mpb_sample_gp_kron_gen_bytes(H, dof), device=dev['device'], dtype=torch.uint8)
 _lib.check(lib.mpb_sample_gp_kron_gen_prepare(_lib.ptr(LkT), _lib.ptr(Limg), H, dof, _lib.stream_ptr()))
-for dbg in [0]:
+for dbg in [0, 1, 2, 4]:
     os.environ['MPB_KRON_GEN_DBG'] = str(dbg)
     def run(i):
         nd = _lib.NoiseDesc(seed=1, offset=i, s_offset=0, p_offset=0, P_global=P)
@@ -33,7 +33,7 @@ for dbg in [0]:
 
 # timeline of CTA 0 (clock64 stamps through the MPB_KRON_GEN_TRACE debug hook)
 names = ['MMA chunk0 ready', 'MMA tile committed', 'epilogue start', 'epilogue end', 'producer chunk0 written', 'producer chunk7 written', 'MMA got acc_empty']
-for dbg in [0]:
+for dbg in [0, 1, 2, 4]:
     os.environ['MPB_KRON_GEN_DBG'] = str(dbg)
     tr = torch.zeros(64, dtype=torch.int64, device=dev['device'])
     os.environ['MPB_KRON_GEN_TRACE'] = str(tr.data_ptr())
@@ -45,6 +45,7 @@ for dbg in [0]:
     t0 = int(t[t > 0].min())
     print(f'dbg={dbg}: per tile (cycles): ' + ' | '.join(
         f'k-loop {int(t[o, 1] - t[o, 0])}, production c0->c7 {int(t[o, 5] - t[o, 4])}, epilogue {int(t[o, 3] - t[o, 2])}, tile {int(t[o, 3] - t[o, 6])}' for o in range(4)))
+    continue
     f = tr.cpu()[40:56].view(2, 8)
     for i in range(2):
         v = [int(x) for x in f[i]]
