@@ -10,15 +10,16 @@
 // (kind::f16, three MMAs per k-step: hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; the factor is scaled per dof by a
 // power of two so that its fp16 parts stay normal) -- the same arithmetic as the warp-MMA kernel it supersedes.
 //
-// One persistent CTA per SM, warp-specialised (704 threads for the 7-dof arm):
-//   warp 0       factor loader: one elected lane streams the 56 KiB factor chunk of each k-step (16 k x 7 dofs x hi/lo,
+// One persistent CTA per SM, warp-specialised (800 threads for the 7-dof arm):
+//   warp 8       factor loader: one elected lane streams the 56 KiB factor chunk of each k-step (16 k x 7 dofs x hi/lo,
 //                pre-arranged on the host side of the C ABI in the exact shared-memory image) with ONE bulk-async copy
 //                (TMA engine, mbarrier complete_tx) into a 2-stage ring
-//   warp 1       MMA issuer: one elected lane, 21 tcgen05.mma.kind::f16 (M128 x N64 x K16) per k-step
-//   warps 4-7    epilogue: tcgen05.ld the accumulators (thread = output row n of every dof), x = mu + acc / scale, dofs
+//   warp 9       MMA issuer: one elected lane, 21 tcgen05.mma.kind::f16 (M128 x N64 x K16) per k-step
+//   warps 0-7    epilogue (TMEM lane quadrant x half of the samples of a 4-sample batch): tcgen05.ld the accumulators
+//                (thread = output row n of every dof), x = mu + acc / scale, dofs
 //                re-interleaved into full trajectory rows in shared memory (conflict-free: lane stride 7 words), rows
-//                leave through bulk-async stores (14 KiB each), double buffered, issued by warp 2 (hand-off by mbarrier)
-//   warps 8-21   noise producers: Philox4x32-10 + Box-Muller, split into fp16 hi / lo and written with 8-byte stores
+//                leave through bulk-async stores (14 KiB each), double buffered, issued by warp 10 (hand-off by mbarrier)
+//   warps 11-24  noise producers: Philox4x32-10 + Box-Muller, split into fp16 hi / lo and written with 8-byte stores
 //                straight into the canonical K-major (no swizzle) operand tiles of a 3-stage ring; the lane mapping makes
 //                every store bank-conflict free
 // Noise layout MPB_NOISE_SPMD: the virtual global tensor is [S_glob, P_glob, dof, 2H] (dof-major inside a row), so the
@@ -51,7 +52,8 @@ struct GenCfg {
     static constexpr int OUT_ROWS = 4;                       // samples per staged output batch
     static constexpr uint32_t OUT_BUF = OUT_ROWS * M * 4;
     static constexpr int PROD_WARPS = 2 * DOF;
-    static constexpr int FIRST_EPI_WARP = 4, FIRST_PROD_WARP = 8;
+    static constexpr int EPI_WARPS = 8;                      // warps 0-7: TMEM lane quadrant x half of a batch's samples
+    static constexpr int LOAD_WARP = 8, MMA_WARP = 9, STORE_WARP = 10, FIRST_PROD_WARP = 11;
     static constexpr int THREADS = (FIRST_PROD_WARP + PROD_WARPS) * 32;
     static constexpr uint32_t OFF_A = 0;
     static constexpr uint32_t OFF_B = OFF_A + A_STAGES * A_STAGE;
@@ -123,7 +125,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
     uint64_t* b_empty = b_full + C::B_STAGES;          // [B_STAGES]
     uint64_t* acc_full = b_empty + C::B_STAGES;        // accumulators of the tile complete
     uint64_t* acc_empty = acc_full + 1;                // accumulators drained (4 epilogue warps)
-    uint64_t* out_full = acc_empty + 1;                // [2] staged rows written (128 epilogue threads)
+    uint64_t* out_full = acc_empty + 1;                // [2] staged rows written (one arrival per epilogue warp)
     uint64_t* out_empty = out_full + 2;                // [2] the bulk store has read the buffer (store warp)
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(out_empty + 2);
 
@@ -137,17 +139,17 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
         for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], C::PROD_WARPS); mbar_init(&b_empty[s], 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 4);
-        for (int s = 0; s < 2; ++s) { mbar_init(&out_full[s], 128); mbar_init(&out_empty[s], 1); }
+        mbar_init(acc_empty, C::EPI_WARPS);
+        for (int s = 0; s < 2; ++s) { mbar_init(&out_full[s], C::EPI_WARPS); mbar_init(&out_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_base_slot, C::TMEM_COLS);
+    if (warp == C::MMA_WARP) tmem_alloc(tmem_base_slot, C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
-    if (warp == 0) {
+    if (warp == C::LOAD_WARP) {
         // ================================ factor loader ================================
         if (lane == 0) {
             int stage = 0;
@@ -165,7 +167,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == C::MMA_WARP) {
         // ================================ MMA issuer ===================================
         {
             // the whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers); one elected
@@ -215,11 +217,12 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                 acc_ph ^= 1;
             }
         }
-    } else if (warp >= C::FIRST_EPI_WARP && warp < C::FIRST_EPI_WARP + 4) {
+    } else if (warp < C::EPI_WARPS) {
         // ================================ epilogue =====================================
-        const int q4 = warp & 3;
+        // warp (q4, half): TMEM lane quadrant q4, samples 2 half, 2 half + 1 of every 4-sample batch
+        const int q4 = warp & 3, half = warp >> 2;
         const int n_out = 32 * q4 + lane;                       // TMEM lane = output row of every dof
-        const int et = threadIdx.x - C::FIRST_EPI_WARP * 32;    // 0..127
+        const int et = threadIdx.x;                             // 0..255
         const float* inv_scale_g = reinterpret_cast<const float*>(a.Limg + (size_t)C::NKC * C::A_STAGE);
         float inv_scale[DOF];
 #pragma unroll
@@ -239,20 +242,21 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             if (et == 0) stamp((t - blockIdx.x) / gridDim.x, 2);
             for (int b = 0; b < C::TS / C::OUT_ROWS; ++b, ++use) {
                 const int buf = use & 1;
-                uint32_t r[DOF][4];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * C::OUT_ROWS);
+                uint32_t r[DOF][2];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * C::OUT_ROWS + 2 * half);
                 if (!(a.dbg & 128)) {
 #pragma unroll
-                    for (int j = 0; j < DOF; ++j) tmem_ld4_nowait(taddr + (uint32_t)(j * C::TS), r[j]);
+                    for (int j = 0; j < DOF; ++j) tmem_ld2_nowait(taddr + (uint32_t)(j * C::TS), r[j]);
                     tmem_wait_ld();
                 } else {
 #pragma unroll
-                    for (int j = 0; j < DOF; ++j) r[j][0] = r[j][1] = r[j][2] = r[j][3] = 0u;
+                    for (int j = 0; j < DOF; ++j) r[j][0] = r[j][1] = 0u;
                 }
-                mbar_wait(&out_empty[buf], ((use >> 1) & 1) ^ 1);      // the store that last read this buffer has drained it
+                mbar_wait_spin(&out_empty[buf], ((use >> 1) & 1) ^ 1);      // the store that last read this buffer has drained it
                 float* ob = reinterpret_cast<float*>(sm + C::OFF_OUT + buf * C::OUT_BUF) + DOF * n_out;
 #pragma unroll
-                for (int sl = 0; sl < C::OUT_ROWS; ++sl) {
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int sl = 2 * half + s2;
                     if (!one_particle) {
                         const long long row = row0 + b * C::OUT_ROWS + sl;
                         const long long p = (row < a.Ntot ? row : a.Ntot - 1) / a.S;
@@ -262,10 +266,12 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                     }
                     if (a.dbg & 256) continue;
 #pragma unroll
-                    for (int j = 0; j < DOF; ++j) ob[sl * C::M + j] = fmaf(__uint_as_float(r[j][sl]), inv_scale[j], mrow[j]);
+                    for (int j = 0; j < DOF; ++j) ob[sl * C::M + j] = fmaf(__uint_as_float(r[j][s2]), inv_scale[j], mrow[j]);
                 }
                 fence_async_proxy();
-                mbar_arrive(&out_full[buf]);                    // the store warp takes it from here
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&out_full[buf]);     // one arrival per warp (arrivals on one barrier serialise);
+                                                                // the store warp takes it from here
             }
             tc_fence_before();
             __syncwarp();
@@ -273,7 +279,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             if (et == 0) stamp((t - blockIdx.x) / gridDim.x, 3);
             acc_ph ^= 1;
         }
-    } else if (warp == 2) {
+    } else if (warp == C::STORE_WARP) {
         // ================================ store issuer ==================================
         // one lane: one bulk-async store (14 KiB of finished rows) per staged batch, so that no epilogue thread ever
         // spends the ~200 cycles a bulk copy takes to issue; a buffer goes back once the store that read it has drained
@@ -283,17 +289,15 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                 const long long row0 = (long long)t * C::TS;
                 for (int b = 0; b < C::TS / C::OUT_ROWS; ++b, ++n) {
                     const int buf = n & 1;
-                    mbar_wait(&out_full[buf], (n >> 1) & 1);
+                    mbar_wait_spin(&out_full[buf], (n >> 1) & 1);
                     const long long first = row0 + b * C::OUT_ROWS;
                     long long rows = a.Ntot - first;
                     if (rows > C::OUT_ROWS) rows = C::OUT_ROWS;
                     if (rows > 0 && !(a.dbg & 4))
                         bulk_store(a.x + (size_t)first * C::M, sm + C::OFF_OUT + buf * C::OUT_BUF, (uint32_t)(rows * C::M * 4));
                     bulk_commit();
-                    if (n >= 1) {
-                        bulk_wait_read<1>();                    // store n - 1 has read its buffer
-                        mbar_arrive(&out_empty[(n - 1) & 1]);
-                    }
+                    bulk_wait_read<0>();                        // the store has read its buffer: hand it back (the epilogue
+                    mbar_arrive(&out_empty[buf]);               // fills the other buffer meanwhile)
                 }
             }
             bulk_wait<0>();
@@ -356,7 +360,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (warp == C::MMA_WARP) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // Factor image: per k-chunk kc, dof j, part (hi | lo): the [128 x 16] fp16 tile  A[n][k] = L_j[n][16 kc + k] * scale_j

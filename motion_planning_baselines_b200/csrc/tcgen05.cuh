@@ -35,6 +35,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity), "r"(0x989680u)
         : "memory");
 }
+// Plain polling wait (no suspend hint): lowest wake-up latency, for short hand-offs on a critical path.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 // Wait with back-off for the roles whose waits are long (a parked warp must not compete for issue slots with the
 // compute warps of its SM sub-partition): poll, then sleep `ns` nanoseconds between polls.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {

@@ -17,7 +17,7 @@ mu = torch.randn(P, M, generator=gen, **dev)
 x = torch.empty(P, S, M, **dev)
 Limg = torch.empty(lib.mpb_sample_gp_kron_gen_bytes(H, dof), device=dev['device'], dtype=torch.uint8)
 _lib.check(lib.mpb_sample_gp_kron_gen_prepare(_lib.ptr(LkT), _lib.ptr(Limg), H, dof, _lib.stream_ptr()))
-for dbg in [0, 1, 2, 4]:
+for dbg in [0, 1, 4 + 128 + 256]:
     os.environ['MPB_KRON_GEN_DBG'] = str(dbg)
     def run(i):
         nd = _lib.NoiseDesc(seed=1, offset=i, s_offset=0, p_offset=0, P_global=P)
@@ -33,7 +33,7 @@ for dbg in [0, 1, 2, 4]:
 
 # timeline of CTA 0 (clock64 stamps through the MPB_KRON_GEN_TRACE debug hook)
 names = ['MMA chunk0 ready', 'MMA tile committed', 'epilogue start', 'epilogue end', 'producer chunk0 written', 'producer chunk7 written', 'MMA got acc_empty']
-for dbg in [0, 1, 2, 4]:
+for dbg in [0, 1, 4 + 128 + 256]:
     os.environ['MPB_KRON_GEN_DBG'] = str(dbg)
     tr = torch.zeros(64, dtype=torch.int64, device=dev['device'])
     os.environ['MPB_KRON_GEN_TRACE'] = str(tr.data_ptr())
