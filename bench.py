@@ -55,11 +55,22 @@ def ncu_traffic(kernel_name):
         table = json.load(open(path))
     except Exception:
         return None
-    for key, rec in table.items():
+    for key, rec in sorted(table.items(), key=lambda kv: -len(kv[0])):        # longest key first: cost_eval_chain2 before cost_eval
         if key in kernel_name:
             return dict(bytes=rec['dram_read_bytes'] + rec['dram_write_bytes'], unit='B', source=rec.get('source'),
                         algorithmic_bytes=rec.get('algorithmic_bytes'))
     return None
+
+
+def ncu_issue_slots(kernel_key):
+    """Executed warp instructions / issue slots per sample of the named kernel from the committed ncu capture
+    (profiles/ncu_traffic.json), or None."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))[kernel_key]
+        return dict(issue_slots_per_sample=rec['issue_slots_per_sample'], warp_instructions_per_sample=rec['warp_instructions_per_sample'],
+                    source=rec.get('source'))
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -301,6 +312,7 @@ def main():
                         noise_particle_offset=rank * P, noise_particles_global=world * P, **sig)
     assert planner._sample_dist.kron_tc_kind == 1, 'the C4 factor must take the default structured sampler'
     means0 = planner._particle_means.clone()
+    planner_uses_gen = getattr(planner._sample_dist, 'scale_tril_kron_gen', None) is not None     # which K1 draws the noise
 
     def barrier():
         if world > 1:
@@ -481,22 +493,42 @@ def main():
     def kernel_table(stage, k1_reads_eps):
         flop_k1 = DOF * (2 * H) * (2 * H + 1)       # 7 independent [128,128] triangular mat-vecs = 115,584 flop / sample
         bytes_k1 = M * 4 * (2 if k1_reads_eps else 1)
-        k1 = dict(kernel='sample_gp_kron_mma_kernel<7,64,%s> (K1: structured GP sampler, warp MMA fp16x2 split%s)'
-                         % ('false' if k1_reads_eps else 'true', '' if k1_reads_eps else ', Philox noise in-kernel'),
+        gen = (not k1_reads_eps) and planner_uses_gen
+        k1_name = ('sample_gp_kron_gen_kernel<7> (K1: tcgen05 kind::f16 with the factor as the M = 128 operand, 64-sample tiles, 7 '
+                   'accumulators in TMEM, warp-specialised Philox producers, bulk-async factor loads and row stores)' if gen else
+                   'sample_gp_kron_mma_kernel<7,64,%s> (K1: structured GP sampler, warp MMA fp16x2 split%s)'
+                   % ('false' if k1_reads_eps else 'true', '' if k1_reads_eps else ', Philox noise in-kernel'))
+        k1 = dict(kernel=k1_name,
                   ms=float(stage[0]), bound='hbm', achieved=bytes_k1 * n_samp / (stage[0] * 1e-3) / 1e9, peak=pk['hbm'], unit='GB/s',
                   algorithmic_bytes_per_sample=bytes_k1, algorithmic_flop_per_sample=flop_k1,
                   note='HBM floor = x written' + (' + eps read' if k1_reads_eps else '') + '; the factor decouples over the 7 dofs '
-                       '(exact zeros, verified bit-exactly at setup): 115,584 flop / sample instead of the dense 803,712')
+                       '(exact zeros, verified bit-exactly at setup): 115,584 flop / sample instead of the dense 803,712'
+                       + ('; measured limiters (profiles/r02_k1_gen_*.txt): noise generation on the CUDA cores (29.4 M normals: '
+                          'Philox4x32-10 + Box-Muller + fp16 split = ~110 instructions per 4) and the accumulator hand-over between '
+                          'MMA and epilogue (448 of 512 TMEM columns: one accumulator set)' if gen else ''))
         k1['frac'] = k1['achieved'] / k1['peak']
         mv = dict(kernel='prior_matvec_dof_kernel (Sigma^-1 mu)', ms=float(stage[1]), bound='latency')
         flop_k2 = FLOP_FK + FLOP_SDF + FLOP_GP + FLOP_IS
         a2 = flop_k2 * n_samp / (stage[2] * 1e-3) / 1e12
-        k2 = dict(kernel='cost_eval_kernel<1,4,0> (K2: FK + collision + GP cost + IS dot)', ms=float(stage[2]), bound='fp32',
+        slots = ncu_issue_slots('cost_eval_chain2')
+        issue_peak = 148 * 4 * sm_mhz_peak * 1e6            # warp instructions / s: 4 schedulers per SM, one issue per cycle
+        k2 = dict(kernel='cost_eval_chain2_kernel<7,8,2> (K2 packed: FK + collision + GP cost + IS dot, two waypoints per lane on '
+                         'FFMA2 / FADD2 / FMUL2)', ms=float(stage[2]), bound='fp32',
                   achieved=a2, peak=fp32_measured, unit='TFLOP/s', frac=a2 / fp32_measured,
                   peak_nominal=fp32_nominal, frac_of_nominal=a2 / fp32_nominal, algorithmic_flop_per_sample=flop_k2,
                   hbm_gbs=M * 4 * n_samp / (stage[2] * 1e-3) / 1e9, hbm_frac=M * 4 * n_samp / (stage[2] * 1e-3) / 1e9 / pk['hbm'],
-                  note='algorithmic flops count ALL 50 x 16 sphere pairs per waypoint; the broad phase skips provably-zero pairs, '
-                       'so executed instructions are fewer (see profiles/): the kernel is FP32-issue bound')
+                  note='algorithmic flops (SURVEY 8d) count ALL 50 x 16 sphere pairs per waypoint; the broad phase proves most of '
+                       'them zero and never evaluates them, which is why this figure can exceed 1: it measures the kernel against '
+                       'the all-pairs formulation, not pipe utilisation.  The kernel is bound by the ISSUE rate -- see issue_view '
+                       '(executed warp-instruction slots from the committed ncu capture / measured time / issue peak)')
+        if slots:
+            k2['issue_view'] = dict(bound='issue', achieved=slots['issue_slots_per_sample'] * n_samp / (stage[2] * 1e-3) / 1e9,
+                                    peak=issue_peak / 1e9, unit='G warp-instruction slots/s',
+                                    frac=slots['issue_slots_per_sample'] * n_samp / (stage[2] * 1e-3) / issue_peak,
+                                    issue_slots_per_sample=slots['issue_slots_per_sample'],
+                                    warp_instructions_per_sample=slots['warp_instructions_per_sample'], source=slots['source'],
+                                    note='packed f32x2 instructions occupy two issue cycles (profiles/r02_ffma2_microbench.txt) and '
+                                         'are counted twice; round 1 generic kernel: 9,467 warp instructions per sample')
         bytes_k3 = (rows_nonzero * M * 4 + 3 * P * M * 4 + 2 * n_samp * 4)
         a3 = bytes_k3 / (stage[3] * 1e-3) / 1e9
         k3 = dict(kernel='softmax_update_kernel (K3)', ms=float(stage[3]), bound='latency', achieved=a3, peak=pk['hbm'], unit='GB/s',

@@ -20,7 +20,8 @@ STALL = 'smsp__average_warps_issue_stalled_'
 ALGO = {'cost_eval': 32768 * 3584 + 512 * 3584, 'sample_gp_tc': 32768 * 3584 * 2 + 2 * 896 * 896 * 4, 'softmax_update': 32768 * 3584,
         'sample_gp_kron_mma': 32768 * 3584 * 2 + 7 * 128 * 128 * 4 + 512 * 3584,
         'sample_gp_kron_umma': 32768 * 3584 * 2 + 2 * 4 * 8 * 224 * 16 * 4 + 512 * 3584,
-        'prior_matvec_dof': 2 * 512 * 3584 + 7 * 896 * 4}
+        'prior_matvec_dof': 2 * 512 * 3584 + 7 * 896 * 4,
+        'sample_gp_kron_gen': 32768 * 3584 + 7 * 128 * 128 * 4 + 512 * 3584}
 
 
 def main():
