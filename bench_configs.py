@@ -77,6 +77,19 @@ def _collision_cost(cfg, H, sigma_coll, dev, weight=1.0):
                          weights_cost_l=[weight], tensor_args=dev)
 
 
+def launch_floor(dev, n_launches, reps=200):
+    """Measured floor of `n_launches` dependent kernel launches on one stream (ms): the smallest kernel of the library
+    (mpb_softmax_weights on one element) launched back to back through the same ctypes path, CUDA events around the batch."""
+    from motion_planning_baselines_b200 import _lib
+    lib = _lib.lib()
+    c, l, w = torch.zeros(1, 1, **dev), torch.zeros(1, 2, **dev), torch.zeros(1, 1, **dev)
+
+    def batch():
+        for _ in range(n_launches):
+            _lib.check(lib.mpb_softmax_weights(_lib.ptr(c), _lib.ptr(l), _lib.ptr(w), 1.0, 1, 1, _lib.stream_ptr()))
+    return _time(batch, reps)
+
+
 def bench_c1_stomp(dev, iters=200):
     from motion_planning_baselines_b200 import configs
     from motion_planning_baselines_b200.planners import STOMP
@@ -87,9 +100,15 @@ def bench_c1_stomp(dev, iters=200):
                     multi_goal_states=torch.tensor(cfg['goal']).to(**dev).unsqueeze(0), temperature=prm['temperature'],
                     step_size=prm['step_size'], sigma_spectral=prm['sigma_spectral'],
                     initial_particle_means=_straight(cfg, P, H, d, dev), pos_only=False, tensor_args=dev)
-    ms = _time(lambda: planner.optimize(opt_iters=1), iters)
+    ms1 = _time(lambda: planner.optimize(opt_iters=1), iters)
+    n_in = 20          # the reference example runs 20 iterations per optimize() call (pointmass_grid_circles_2d_STOMP.py:76)
+    ms = _time(lambda: planner.optimize(opt_iters=n_in), max(iters // 4, 5)) / n_in
+    floor = launch_floor(dev, 3)
     return dict(config='C1 pointmass_grid_circles_2d STOMP', shape='1 particle x 64 samples x 64 waypoints', ms_per_iter=ms,
-                samples_per_s=P * S / (ms * 1e-3), bound='launch latency (3 kernels + noise draw per iteration)')
+                ms_per_single_iter_call=ms1, samples_per_s=P * S / (ms * 1e-3), launch_floor_ms_per_iter=floor,
+                bound='launch latency', note=f'{n_in} iterations per optimize() call, enqueued by one mpb_stomp_run call (3 launches '
+                'per iteration, no host work in between); launch_floor_ms_per_iter = 3 back-to-back launches of the smallest kernel '
+                'of the library (mpb_softmax_weights on one element) measured the same way')
 
 
 def bench_c2(dev, iters=20):
@@ -124,7 +143,8 @@ def bench_c2(dev, iters=20):
                  ms_per_single_iter_call=ms_c1, trajectories_per_s=P / (ms_c * 1e-3),
                  note=f'{n_in} iterations inside one mpb_chomp_run launch; ms_per_single_iter_call = optimize(opt_iters=1)'),
             dict(config='C2 pointmass_dense_2d GPMP2', shape='1024 trajectories x 64 waypoints', ms_per_iter=ms_g,
-                 trajectories_per_s=P / (ms_g * 1e-3), note='linearize + batch-mean diagonal + block-tridiagonal fp64 Cholesky solve')]
+                 trajectories_per_s=P / (ms_g * 1e-3), launch_floor_ms_per_iter=launch_floor(dev, 3),
+                 note='linearize + batch-mean diagonal + block-tridiagonal fp64 Cholesky solve (3 launches)')]
 
 
 def bench_stoch(dev, name, iters=30):

@@ -316,6 +316,12 @@ int mpb_stoch_gpmp_iter_kron_gen(const void* L_kron_gen, const float* Sigma_inv,
                                  float* is_vec, uint8_t* free_flag, int P, int S, int H, const mpb_robot_desc* robot,
                                  const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp, float temp, float step,
                                  void* stream);
+/* STOMP, n_iters iterations from one call (stomp.py:137-160): mpb_sample_stomp_rng (draw counter noise->offset + it),
+ * mpb_cost_eval, mpb_softmax_update with Sigma_R -- for the launch-latency-bound small configurations.  The caller
+ * advances its draw counter by n_iters. */
+int mpb_stomp_run(const float* L_R, const float* SigmaR, const mpb_noise_desc* noise, float* mu, float* x, float* cost,
+                  float* weights, int P, int S, int H, const mpb_robot_desc* robot, const mpb_field_desc* fields,
+                  int n_fields, const mpb_gp_desc* gp, float temp, float lr, int n_iters, void* stream);
 int mpb_stoch_gpmp_iter(const float* L, const float* L_split, const float* Sigma_inv, const float* eps,
                         float* mu, float* x, float* cost, float* weights, float* is_vec,
                         uint8_t* free_flag,

@@ -82,6 +82,8 @@ _SIGNATURES = {
                                                C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc), _f, _f, _vp]),
     'mpb_stoch_gpmp_iter_kron_gen': (C.c_int, [_vp, _vp, _i, C.POINTER(NoiseDesc), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                                C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc), _f, _f, _vp]),
+    'mpb_stomp_run': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(RobotDesc),
+                                C.POINTER(FieldDesc), _i, C.POINTER(GPDesc), _f, _f, _i, _vp]),
     'mpb_sample_gp_kron_gen_supported': (C.c_int, [_i, _i]),
     'mpb_sample_gp_kron_gen_bytes': (C.c_longlong, [_i, _i]),
     'mpb_sample_gp_kron_gen_prepare': (C.c_int, [_vp, _vp, _i, _i, _vp]),

@@ -168,3 +168,27 @@ extern "C" int mpb_stoch_gpmp_iter_kron_gen(const void* L_kron_gen, const float*
     if (rc) return rc;
     return mpb_softmax_update(cost, x, mu, weights, nullptr, temp, step, nullptr, P, S, H, D, stream);
 }
+
+// STOMP: `n_iters` whole iterations (stomp.py:137-160: sample -> cost -> importance-weighted update) enqueued from ONE
+// call -- sample_stomp (noise drawn in the kernel, draw counter noise->offset + it), cost_eval, softmax_update with Sigma_R.
+// The small STOMP configurations are bound by launch / host latency (BASELINE.json configs[0]: 64 samples), so the
+// per-iteration host work is what matters: three asynchronous launches and nothing else.  cost / x / weights hold the
+// LAST iteration on return, exactly what the planner attributes expose after optimize().
+extern "C" int mpb_stomp_run(const float* L_R, const float* SigmaR, const mpb_noise_desc* noise, float* mu, float* x, float* cost,
+                             float* weights, int P, int S, int H, const mpb_robot_desc* robot, const mpb_field_desc* fields,
+                             int n_fields, const mpb_gp_desc* gp, float temp, float lr, int n_iters, void* stream) {
+    MPB_REQUIRE(robot && noise && L_R && SigmaR && mu && x && cost && weights, "mpb_stomp_run: null pointer");
+    MPB_REQUIRE(n_iters >= 0, "mpb_stomp_run: negative iteration count");
+    const int D = 2 * robot->q_dim;
+    mpb_noise_desc nd = *noise;
+    for (int it = 0; it < n_iters; ++it) {
+        int rc = mpb_sample_stomp_rng(L_R, mu, &nd, x, P, S, H, D, stream);
+        if (rc) return rc;
+        rc = mpb_cost_eval(x, P * S, H, robot, fields, n_fields, gp, nullptr, 1, 0.f, cost, nullptr, nullptr, stream);
+        if (rc) return rc;
+        rc = mpb_softmax_update(cost, x, mu, weights, nullptr, temp, lr, SigmaR, P, S, H, D, stream);
+        if (rc) return rc;
+        ++nd.offset;
+    }
+    return MPB_OK;
+}

@@ -106,9 +106,32 @@ class STOMP(OptimizationPlanner):
     def _run_optimization(self, opt_iters, eps=None, **observation):
         if opt_iters is None:
             opt_iters = self.opt_iters
+        if self._can_run_fused(eps, observation):
+            # all iterations enqueued from one C call (three launches each, no host work in between): the small STOMP
+            # configurations are launch-latency bound
+            P, S, H, D = self.num_particles, self._s_local, self.n_support_points, self.d_state_opt
+            gp, fields, nf, _ = self.cost._build()
+            nd = self._noise.desc()
+            _lib.check(_lib.lib().mpb_stomp_run(
+                _lib.ptr(self._L_R), _lib.ptr(self.Sigma), C.byref(nd), _lib.ptr(self._particle_means), _lib.ptr(self.state_particles),
+                _lib.ptr(self._cost_buf), _lib.ptr(self._w_buf), P, S, H, C.byref(self.cost.robot.desc), fields, nf, C.byref(gp),
+                self.temperature, self.lr, opt_iters, _lib.stream_ptr()))
+            self._noise.offset += opt_iters
+            if opt_iters > 0:
+                self.costs = self._cost_buf.view(P, S)
+                self._weights = self._w_buf.view(P, S, 1, 1)
+            return
         for it in range(opt_iters):
             self.costs = self._sample_and_eval(eps=None if eps is None else eps[it], **observation)
             self._update_distribution(self.costs, self.state_particles)
+
+    def _can_run_fused(self, eps, observation):
+        """mpb_stomp_run applies when nothing needs the host between the three kernels of an iteration."""
+        c = self.cost
+        return (eps is None and not observation and self.split.world == 1 and self._s_local <= self.SPLIT_THRESHOLD
+                and hasattr(c, '_build') and hasattr(c, 'robot') and not c.has_extra_terms
+                and self.d_state_opt == 2 * c.robot.desc.q_dim and type(self)._sample_and_eval is STOMP._sample_and_eval
+                and type(self)._update_distribution is STOMP._update_distribution and self.state_particles.is_contiguous())
 
     def _sample_and_eval(self, eps=None, **observation):
         P, S = self.num_particles, self._s_local
