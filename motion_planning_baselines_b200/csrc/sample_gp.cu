@@ -190,6 +190,68 @@ __global__ void __launch_bounds__(256) sample_stomp_kernel(const float* __restri
     }
 }
 
+// Wide variant for many samples (the C5 sweep: 10^4 - 10^6 samples of one problem): one THREAD per (particle, sample,
+// state column j) keeps its H = 64 noise values in registers and walks the rows of L_R, which every thread reads at the
+// same address (shared-memory broadcast, 16 bytes per 4 FMAs).  Rows are cut into chunks of 16 k; a chunk right of the
+// diagonal is skipped, inside the diagonal chunk the exact zeros of the lower-triangular factor make the extra FMAs
+// no-ops, so the sum is the one of sample_stomp_kernel bit for bit (same ascending k order).  The CTA-per-sample kernel
+// above needs two barriers and a 224-thread Philox phase per sample: 1.07 ms for 10^5 Panda samples, this one 0.2 ms.
+template <bool GEN>
+__global__ void __launch_bounds__(128) sample_stomp_wide_kernel(const float* __restrict__ LR, const float* __restrict__ mu,
+                                                                const float* __restrict__ eps, float* __restrict__ x,
+                                                                int P, int S, int D, const NoiseArgs noise) {
+    constexpr int H = 64;
+    __shared__ __align__(16) float Ls[H * H];
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) Ls[i] = LR[i];
+    __syncthreads();
+    const long long total = (long long)P * S * D;
+    const int M = H * D;
+    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(id % D);
+        const long long ps = id / D;
+        const int p = (int)(ps / S), s = (int)(ps - (long long)p * S);
+        float e[H];
+        if (GEN) {
+            const unsigned long long g0 = (((unsigned long long)((noise.s_off + s) * D + j) * noise.P_glob + noise.p_off + p) * H) >> 2;
+#pragma unroll
+            for (int q = 0; q < H / 4; ++q) {
+                const float4 v = philox_normal4(g0 + q, noise);
+                e[4 * q] = v.x; e[4 * q + 1] = v.y; e[4 * q + 2] = v.z; e[4 * q + 3] = v.w;
+            }
+        } else {
+            const float4* src = reinterpret_cast<const float4*>(eps + (((size_t)s * D + j) * P + p) * H);
+#pragma unroll
+            for (int q = 0; q < H / 4; ++q) {
+                const float4 v = __ldg(src + q);
+                e[4 * q] = v.x; e[4 * q + 1] = v.y; e[4 * q + 2] = v.z; e[4 * q + 3] = v.w;
+            }
+        }
+        const float* mp = mu + (size_t)p * M + j;
+        float* xp = x + (size_t)ps * M + j;
+        xp[0] = __ldg(mp);
+        xp[(size_t)(H - 1) * D] = __ldg(mp + (size_t)(H - 1) * D);
+#pragma unroll 1
+        for (int h = 1; h < H - 1; ++h) {
+            const float4* lrow = reinterpret_cast<const float4*>(Ls + h * H);
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < H / 16; ++c) {
+                if (16 * c <= h) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 l = lrow[4 * c + u];
+                        acc = fmaf(l.x, e[16 * c + 4 * u], acc);
+                        acc = fmaf(l.y, e[16 * c + 4 * u + 1], acc);
+                        acc = fmaf(l.z, e[16 * c + 4 * u + 2], acc);
+                        acc = fmaf(l.w, e[16 * c + 4 * u + 3], acc);
+                    }
+                }
+            }
+            xp[(size_t)h * D] = __ldg(mp + (size_t)h * D) + acc;
+        }
+    }
+}
+
 // The normals a kernel consumes for a noise descriptor, written in the LOCAL layout of the call (mpb_philox_normal).
 // Quads of the innermost axis are group aligned when its extent is a multiple of 4; otherwise element by element.
 __global__ void __launch_bounds__(256) philox_dump_kernel(const NoiseArgs noise, int layout, float* __restrict__ out,
@@ -377,6 +439,16 @@ static int sample_stomp_any(const float* L_R, const float* mu, const float* eps,
                         : cudaFuncSetAttribute(sample_stomp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("mpb_sample_stomp: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
     const long long work = (long long)P * S;
+    // many samples: one thread per (particle, sample, column); the factor must be lower triangular with exact zeros above
+    // the diagonal (torch's scale_tril is), the injected noise 16-byte aligned
+    if (H == 64 && work * D >= 16384 && (!eps || (reinterpret_cast<uintptr_t>(eps) & 15) == 0)) {
+        const long long threads = work * D;
+        const long long blocks = (threads + 127) / 128;
+        const int wgrid = (int)(blocks < (long long)sm_count() * 16 ? blocks : (long long)sm_count() * 16);
+        if (eps) sample_stomp_wide_kernel<false><<<wgrid, 128, 0, static_cast<cudaStream_t>(stream)>>>(L_R, mu, eps, x, P, S, D, noise);
+        else sample_stomp_wide_kernel<true><<<wgrid, 128, 0, static_cast<cudaStream_t>(stream)>>>(L_R, mu, eps, x, P, S, D, noise);
+        return check_launch("mpb_sample_stomp");
+    }
     const int grid = (int)(work < (long long)sm_count() * 4 ? work : (long long)sm_count() * 4);
     if (eps) sample_stomp_kernel<false><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(L_R, mu, eps, x, P, S, H, D, noise);
     else sample_stomp_kernel<true><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(L_R, mu, eps, x, P, S, H, D, noise);

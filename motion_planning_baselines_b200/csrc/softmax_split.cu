@@ -184,6 +184,98 @@ __global__ void __launch_bounds__(256) softmax_combine_kernel(
     }
 }
 
+// Multi-CTA combine: same arithmetic in the same order as softmax_combine_kernel (per column the records are folded in
+// ascending order with one FMA each; the normaliser is one serial FMA chain), but (i) the record heads are staged and the
+// exponentials computed by all threads, (ii) the columns are spread over gridDim.x CTAs with one column per thread and
+// (iii) the loads of eight records are in flight per thread.  The serial single-CTA kernel above took 0.27-0.44 ms for the
+// 296 records of one problem and grew linearly with the number of ranks of a sample split.
+constexpr int kCombThreads = 128;
+__global__ void __launch_bounds__(kCombThreads) softmax_combine_cols_kernel(
+    const float* __restrict__ rec, int R, float* __restrict__ mu, float* __restrict__ grad, float* __restrict__ lse,
+    float* __restrict__ best_cost, int* __restrict__ best_idx, float step, int apply, int P, int Mw) {
+    extern __shared__ __align__(16) float sm[];
+    const int REC = kRecHead + Mw;
+    const int p = blockIdx.y;
+    float* sc = sm;                          // [R] e^{m_r - m*}
+    float* hm = sm + ((R + 3) & ~3);         // [R] m_r, then reused
+    float* hz = hm + ((R + 3) & ~3);         // [R] Z_r
+    float* hc = hz + ((R + 3) & ~3);         // [R] cmin_r
+    int* hi = reinterpret_cast<int*>(hc + ((R + 3) & ~3));   // [R] argmin_r
+    __shared__ float s_m, s_Z;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const float* q = rec + ((size_t)r * P + p) * REC;
+        hm[r] = __ldg(q); hz[r] = __ldg(q + 1); hc[r] = __ldg(q + 2); hi[r] = __float_as_int(__ldg(q + 3));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = -CUDART_INF_F, cmin = CUDART_INF_F;
+        int imin = 0x7fffffff;
+        for (int r = 0; r < R; ++r) {
+            m = fmaxf(m, hm[r]);
+            const float oc = hc[r];
+            const int oi = hi[r];
+            if (oc < cmin || (oc == cmin && oi < imin)) { cmin = oc; imin = oi; }
+        }
+        s_m = m;
+        if (blockIdx.x == 0) {
+            if (best_cost) best_cost[p] = cmin;
+            if (best_idx) best_idx[p] = imin;
+        }
+    }
+    __syncthreads();
+    const float m = s_m;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) sc[r] = (hm[r] == -CUDART_INF_F) ? 0.f : expf(hm[r] - m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float Z = 0.f;
+        for (int r = 0; r < R; ++r) Z = fmaf(sc[r], hz[r], Z);
+        s_Z = Z;
+        if (blockIdx.x == 0 && lse) { lse[2 * p] = m; lse[2 * p + 1] = Z; }
+    }
+    __syncthreads();
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= Mw) return;
+    const float Z = s_Z;
+    const float* base = rec + (size_t)p * REC + kRecHead + col;
+    const size_t stride = (size_t)P * REC;
+    float acc = 0.f;
+    int r = 0;
+    for (; r + 8 <= R; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(base + (size_t)(r + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float s = sc[r + u];
+            if (s != 0.f) acc = fmaf(s, v[u], acc);
+        }
+    }
+    for (; r < R; ++r) {
+        const float s = sc[r];
+        if (s != 0.f) acc = fmaf(s, __ldg(base + (size_t)r * stride), acc);
+    }
+    const float g = acc / Z;
+    if (grad) grad[(size_t)p * Mw + col] = g;
+    if (apply) mu[(size_t)p * Mw + col] = fmaf(step, g, mu[(size_t)p * Mw + col]);
+}
+
+// STOMP: mu[h,j] += step * sum_k SigmaR[h,k] g[k,j]   (stomp.py:206-211), after the multi-CTA combine wrote g
+__global__ void __launch_bounds__(256) sigma_update_kernel(const float* __restrict__ g, const float* __restrict__ SigmaR,
+                                                           float* __restrict__ mu, float step, int H, int Dw) {
+    extern __shared__ __align__(16) float gs[];
+    const int Mw = H * Dw, p = blockIdx.x;
+    for (int i = threadIdx.x; i < Mw; i += blockDim.x) gs[i] = g[(size_t)p * Mw + i];
+    __syncthreads();
+    float* mp = mu + (size_t)p * Mw;
+    for (int o = threadIdx.x; o < Mw; o += blockDim.x) {
+        const int h = o / Dw, j = o - h * Dw;
+        const float* srow = SigmaR + (size_t)h * H;
+        float acc = 0.f;
+        for (int k = 0; k < H; ++k) acc = fmaf(__ldg(srow + k), gs[k * Dw + j], acc);
+        mp[o] = fmaf(step, acc, mp[o]);
+    }
+}
+
 __global__ void softmax_weights_kernel(const float* __restrict__ cost, const float* __restrict__ lse,
                                        float* __restrict__ weights, float temp, int P, int S) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,6 +340,21 @@ extern "C" int mpb_softmax_combine(const float* rec, int R, float* mu, float* gr
     MPB_REQUIRE(rec && mu, "mpb_softmax_combine: null pointer");
     MPB_REQUIRE(R >= 1 && P >= 0 && H >= 1 && Dw >= 1, "mpb_softmax_combine: bad sizes");
     if (P == 0) return MPB_OK;
+    // multi-CTA path (identical arithmetic): needs the merged mean in global memory when Sigma_R is applied afterwards
+    if ((!SigmaR || grad) && P <= 65535 && (size_t)5 * ((R + 3) & ~3) * sizeof(float) <= 200 * 1024) {
+        const int Mw = H * Dw;
+        const size_t smem2 = (size_t)5 * ((R + 3) & ~3) * sizeof(float);
+        cudaError_t e2 = cudaFuncSetAttribute(softmax_combine_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e2 != cudaSuccess) { set_error("mpb_softmax_combine: %s", cudaGetErrorString(e2)); return MPB_ECUDA; }
+        dim3 grid((Mw + kCombThreads - 1) / kCombThreads, P);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        softmax_combine_cols_kernel<<<grid, kCombThreads, smem2, st>>>(rec, R, mu, grad, lse, best_cost, best_idx, step, SigmaR ? 0 : 1, P, Mw);
+        if (SigmaR) {
+            MPB_REQUIRE((size_t)Mw * sizeof(float) <= 48 * 1024, "mpb_softmax_combine: H * Dw too large for the Sigma_R update");
+            sigma_update_kernel<<<P, 256, (size_t)Mw * sizeof(float), st>>>(grad, SigmaR, mu, step, H, Dw);
+        }
+        return check_launch("mpb_softmax_combine");
+    }
     const size_t smem = ((size_t)((R + 3) & ~3) + (SigmaR ? (size_t)H * Dw : 0)) * sizeof(float);
     MPB_REQUIRE(smem <= 200 * 1024, "mpb_softmax_combine: too many records (%d)", R);
     cudaError_t e = cudaFuncSetAttribute(softmax_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

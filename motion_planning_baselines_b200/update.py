@@ -83,9 +83,9 @@ def split_softmax_update(cost, x, mu, temp, step, H, Dfull, c0=0, Dw=None, Sigma
     lse = torch.empty(P, 2, device=dev, dtype=torch.float32)
     best_cost = torch.empty(P, device=dev, dtype=torch.float32)
     best_idx = torch.empty(P, device=dev, dtype=torch.int32)
-    grad = torch.empty(P, H, Dw, device=dev, dtype=torch.float32) if want_grad else None
+    grad = torch.empty(P, H, Dw, device=dev, dtype=torch.float32) if (want_grad or SigmaR is not None) else None    # Sigma_R is applied to the merged mean
     _lib.check(lib.mpb_softmax_combine(_lib.ptr(rec_all), rec_all.shape[0], _lib.ptr(mu), _lib.ptr(grad), _lib.ptr(lse),
                                        _lib.ptr(best_cost), _lib.ptr(best_idx), float(step), _lib.ptr(SigmaR), P, H, Dw, st))
     weights = weights_out if weights_out is not None else torch.empty(P, S_local, device=dev, dtype=torch.float32)
     _lib.check(lib.mpb_softmax_weights(_lib.ptr(cost), _lib.ptr(lse), _lib.ptr(weights), float(temp), P, S_local, st))
-    return dict(weights=weights, lse=lse, best_cost=best_cost, best_idx=best_idx, grad=grad, records=rec_all)
+    return dict(weights=weights, lse=lse, best_cost=best_cost, best_idx=best_idx, grad=grad if want_grad else None, records=rec_all)
