@@ -92,22 +92,34 @@ __global__ void __launch_bounds__(128) gpmp2_linearize_kernel(const __grid_const
 }
 
 // dm[t*d + k] = (1/B) sum_b sum_f inv_sigma2_f * hobs[f,b,t,k]^2      (fixed summation order)
-__global__ void gpmp2_diag_mean_kernel(const float* __restrict__ hobs, double* __restrict__ dm, int B, int H, int d, int nf,
-                                       float w0, float w1, float w2, float w3) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per entry: lane l folds the trajectories b = l, l + 32, ... in ascending order (four independent loads in
+// flight), then the 32 partial sums are combined by a fixed butterfly -- deterministic, and 32 x 4 loads in flight instead
+// of the one dependent load per trajectory of a thread-per-entry walk (50 us at B = 1024).
+__global__ void __launch_bounds__(128) gpmp2_diag_mean_kernel(const float* __restrict__ hobs, double* __restrict__ dm, int B, int H,
+                                                              int d, int nf, float w0, float w1, float w2, float w3) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= H * d) return;
     const float w[4] = {w0, w1, w2, w3};
+    const size_t stride = (size_t)H * d;
     double acc = 0.0;
     for (int f = 0; f < nf; ++f) {
-        const float* hf = hobs + (size_t)f * B * H * d + i;
-        double s = 0.0;
-        for (int b = 0; b < B; ++b) {
-            const double h = (double)__ldg(hf + (size_t)b * H * d);
-            s = fma(h, h, s);
+        const float* hf = hobs + (size_t)f * B * stride + i;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int b = lane;
+        for (; b + 96 < B; b += 128) {
+            const float v0 = __ldg(hf + (size_t)b * stride), v1 = __ldg(hf + (size_t)(b + 32) * stride);
+            const float v2 = __ldg(hf + (size_t)(b + 64) * stride), v3 = __ldg(hf + (size_t)(b + 96) * stride);
+            s0 = fma((double)v0, (double)v0, s0); s1 = fma((double)v1, (double)v1, s1);
+            s2 = fma((double)v2, (double)v2, s2); s3 = fma((double)v3, (double)v3, s3);
         }
+        for (; b < B; b += 32) {
+            const double h = (double)__ldg(hf + (size_t)b * stride);
+            s0 = fma(h, h, s0);
+        }
+        const double s = warp_sum((s0 + s1) + (s2 + s3));
         acc = fma((double)w[f], s, acc);
     }
-    dm[i] = acc / (double)B;
+    if (lane == 0) dm[i] = acc / (double)B;
 }
 
 struct SolveArgs {
@@ -356,6 +368,213 @@ __global__ void __launch_bounds__(128) gpmp2_solve_kernel(const __grid_constant_
     }
 }
 
+// Small state dimensions (point robots: D = 4 or 6): one THREAD per trajectory, every block in registers, all loops
+// unrolled.  The warp-cooperative kernel above is laid out for D up to 16 (the Panda); at D = 4 most of its lanes idle
+// behind __syncwarp()s and index arithmetic (137 M warp instructions for 1024 trajectories, 0.485 ms at C2).  Same
+// formulas in fp64, same elimination order.  Workspace layout (private to this kernel): per (t, slot) a contiguous
+// run over the batch -- C_t lower triangle | W_{t+1} | y_t in 2 D^2 slots -- so that the threads of a warp read and
+// write consecutive doubles.
+template <int D>
+__global__ void __launch_bounds__(32) gpmp2_solve_small_kernel(const __grid_constant__ SolveArgs a) {
+    constexpr int d = D / 2, DD = D * D, SLOTS = 2 * DD, NL = D * (D + 1) / 2;
+    static_assert(NL + DD + D <= SLOTS, "workspace slots");
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int H = a.H, M = H * D, B = a.B;
+    const GPConst gc = make_gpconst(a.gp);
+    const size_t nBH = (size_t)B * H;
+    float* xg = a.x + (size_t)b * M;
+    double W[D][D], y_prev[D], gn[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) { gn[i] = 0.0; y_prev[i] = 0.0; }
+    double cost = 0.0;
+    float xt[D], xn[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) xt[i] = xg[i];
+    for (int t = 0; t < H; ++t) {
+        if (t < H - 1) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) xn[i] = xg[(t + 1) * D + i];
+        }
+        // ---- g_t -----------------------------------------------------------------------------------------
+        double gt[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double g = gn[i];
+            if (t == 0) {
+                const double e0 = (double)(__ldg(a.gp.start_state + i) - xt[i]);
+                g += gc.ks * e0;
+                cost += gc.ks * e0 * e0;
+            }
+            if (t == H - 1 && a.gp.has_goal) {
+                const double eg = (double)(__ldg(a.gp.goal_state + i) - xt[i]);
+                g += gc.kg * eg;
+                cost += gc.kg * eg * eg;
+            }
+            gt[i] = g;
+        }
+        if (t < H - 1) {
+#pragma unroll
+            for (int k = 0; k < d; ++k) {
+                const double ep = (double)(xn[k] - fmaf(a.gp.dt, xt[d + k], xt[k]));
+                const double ev = (double)(xn[d + k] - xt[d + k]);
+                const double qp = gc.a * ep + gc.b * ev, qv = gc.b * ep + gc.c * ev;
+                gt[k] += qp;
+                gt[d + k] += gc.dt * qp + qv;
+                gn[k] = -qp;
+                gn[d + k] = -qv;
+                cost += ep * qp + ev * qv;
+            }
+        }
+        double hsum[d][d];                    // sum_f w_f h_f h_f^T (collision part of the diagonal block)
+#pragma unroll
+        for (int i = 0; i < d; ++i)
+#pragma unroll
+            for (int j = 0; j < d; ++j) hsum[i][j] = 0.0;
+        if (t >= 1) {
+            for (int f = 0; f < a.nf; ++f) {
+                const double e = (double)__ldg(a.err + (size_t)f * nBH + (size_t)b * H + t);
+                const double w = (double)a.wcoll[f];
+                cost += w * e * e;
+                const float* h = a.hobs + ((size_t)f * nBH + (size_t)b * H + t) * d;
+                double hv[d];
+#pragma unroll
+                for (int k = 0; k < d; ++k) hv[k] = (double)__ldg(h + k);
+                if (e != 0.0) {
+#pragma unroll
+                    for (int k = 0; k < d; ++k) gt[k] += w * hv[k] * e;
+                }
+#pragma unroll
+                for (int i = 0; i < d; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) hsum[i][j] += w * hv[i] * hv[j];
+            }
+        }
+        // ---- S = diagonal block t - W W^T (lower triangle), in-place Cholesky ------------------------------
+        double S[D][D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                double v = diag_const(gc, t, H, d, i, j);
+                if (i < d) v += hsum[i][j];
+                if (i == j) {
+                    if (a.diag_mean) {
+                        double dmv = diag_const(gc, t, H, d, i, i);
+                        if (i < d) dmv += a.diag_mean[t * d + i];
+                        v += (double)a.delta * dmv;
+                    } else {
+                        v += (double)a.delta;
+                    }
+                }
+                if (t > 0) {
+                    double s2 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) s2 = fma(W[i][k], W[j][k], s2);
+                    v -= s2;
+                }
+                S[i][j] = v;
+            }
+        }
+        // the diagonal keeps 1 / C_kk: every later division by a pivot (26 per step) becomes a multiplication -- fp64
+        // divisions are ~30 dependent instructions each and were most of this latency-bound kernel
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const double inv = rsqrt(S[k][k]);
+            S[k][k] = inv;
+#pragma unroll
+            for (int i = k + 1; i < D; ++i) S[i][k] *= inv;
+#pragma unroll
+            for (int i = k + 1; i < D; ++i)
+#pragma unroll
+                for (int j = k + 1; j <= i; ++j) S[i][j] -= S[i][k] * S[j][k];
+        }
+        // ---- forward substitution: C y_t = g_t - W y_{t-1} ----------------------------------------------------
+        double r[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double v = gt[i];
+            if (t > 0) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) v -= W[i][k] * y_prev[k];
+            }
+            r[i] = v;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const double yk = r[k] * S[k][k];
+            y_prev[k] = yk;
+#pragma unroll
+            for (int i = k + 1; i < D; ++i) r[i] -= S[i][k] * yk;
+        }
+        // ---- W_{t+1} = O C^-T ------------------------------------------------------------------------------
+        if (t < H - 1) {
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    double v = off_const(gc, d, i, j);
+#pragma unroll
+                    for (int k = 0; k < j; ++k) v -= S[j][k] * W[i][k];     // W[i][k < j] already holds the new row
+                    W[i][j] = v * S[j][j];
+                }
+        }
+        // ---- keep C_t, W_{t+1}, y_t for the backward sweep ------------------------------------------------------
+        double* wst = a.ws + (size_t)t * SLOTS * B + b;
+        int slot = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) wst[(size_t)(slot++) * B] = S[i][j];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) wst[(size_t)(slot++) * B] = (t < H - 1) ? W[i][j] : 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) wst[(size_t)(slot++) * B] = y_prev[i];
+#pragma unroll
+        for (int i = 0; i < D; ++i) xt[i] = xn[i];
+    }
+    // ---- backward sweep: C_t^T dx_t = y_t - W_{t+1}^T dx_{t+1};  x_t += step * dx_t -----------------------------------
+    double dxn[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) dxn[i] = 0.0;
+    for (int t = H - 1; t >= 0; --t) {
+        const double* wst = a.ws + (size_t)t * SLOTS * B + b;
+        double S[D][D], Wn[D][D], r[D];
+        int slot = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) S[i][j] = wst[(size_t)(slot++) * B];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) Wn[i][j] = wst[(size_t)(slot++) * B];
+#pragma unroll
+        for (int i = 0; i < D; ++i) r[i] = wst[(size_t)(slot++) * B];
+        if (t < H - 1) {
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int k = 0; k < D; ++k) r[i] -= Wn[k][i] * dxn[k];
+        }
+#pragma unroll
+        for (int k = D - 1; k >= 0; --k) {
+            const double xk = r[k] * S[k][k];
+            dxn[k] = xk;
+#pragma unroll
+            for (int i = 0; i < k; ++i) r[i] -= S[k][i] * xk;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            if (a.dtheta) a.dtheta[(size_t)b * M + t * D + i] = (float)dxn[i];
+            xg[t * D + i] = xg[t * D + i] + a.step * (float)dxn[i];
+        }
+    }
+    if (a.cost) a.cost[b] = (float)cost;
+}
+
 static size_t solve_smem_per_warp(int H, int D) {
     const int DD = D * D, M = H * D;
     return (size_t)(3 * DD + M + 3 * D) * sizeof(double) + (size_t)((M + 1) & ~1) * sizeof(float);
@@ -429,7 +648,7 @@ extern "C" int mpb_gpmp2_linearize_ex(const float* x, int B, int H, const mpb_ro
         float w[4] = {0.f, 0.f, 0.f, 0.f};
         for (int i = 0; i < n_fields; ++i) w[i] = fields[i].inv_sigma2;
         const int nd = H * a.d;
-        gpmp2_diag_mean_kernel<<<(nd + 127) / 128, 128, 0, st>>>(hobs, diag_mean, B, H, a.d, n_fields, w[0], w[1], w[2], w[3]);
+        gpmp2_diag_mean_kernel<<<(nd + 3) / 4, 128, 0, st>>>(hobs, diag_mean, B, H, a.d, n_fields, w[0], w[1], w[2], w[3]);
         rc = check_launch("mpb_gpmp2_linearize(diag_mean)");
     }
     return rc;
@@ -450,6 +669,12 @@ extern "C" int mpb_gpmp2_solve(float* x, int B, int H, int d, const mpb_gp_desc*
     a.gp = *gp; a.err = err; a.hobs = hobs;
     for (int i = 0; i < n_fields; ++i) a.wcoll[i] = inv_sigma2[i];
     a.diag_mean = diag_mean; a.delta = delta; a.step = step; a.ws = workspace; a.cost = cost; a.dtheta = dtheta;
+    if (a.D == 4 || a.D == 6) {             // point robots: thread per trajectory, blocks in registers
+        const int grid_s = (B + 31) / 32;
+        if (a.D == 4) gpmp2_solve_small_kernel<4><<<grid_s, 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+        else gpmp2_solve_small_kernel<6><<<grid_s, 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+        return check_launch("mpb_gpmp2_solve");
+    }
     const size_t per_warp = solve_smem_per_warp(H, a.D);
     int warps = 4;
     while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
