@@ -43,6 +43,7 @@ struct CostArgs {
     int list_cap;                      // broad-phase list entries per warp (max primitives of one field)
     mpb_extra_cost_desc ex;            // CostGPTrajectory / CostJointLimits (only read by the XF variant)
     float* jl_out;                     // [B] raw joint-limit term per trajectory
+    int k2_local;                      // packed kernel: sphere-only lists are culled in the link frame (MPB_K2_LOCAL=0: world frame)
 };
 
 // Per-warp queue of flagged spheres: structure of arrays in shared memory at byte offset `base`
@@ -670,6 +671,10 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
     MPB_REQUIRE(smem <= 227 * 1024, "mpb_cost_eval: %zu bytes of shared memory needed (H*D too large or too many primitives)", smem);
 
     MPB_REQUIRE(B <= (1 << 30), "mpb_cost_eval: batch too large (%d)", B);
+    {
+        const char* v = getenv("MPB_K2_LOCAL");
+        a.k2_local = !(v && v[0] == '0');
+    }
     a.sched = sched_slot();
     if (!a.sched) { set_error("mpb_cost_eval: could not allocate the scheduler counters"); return MPB_ECUDA; }
     const int blocks_needed = (B + kWarps - 1) / kWarps;
