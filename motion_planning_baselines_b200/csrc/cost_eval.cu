@@ -24,6 +24,11 @@ namespace mpb {
 constexpr int kWarps = 8;
 constexpr int kQCap = 64;            // queue entries per warp (>= 2 * 32)
 
+struct CullTable {       // byte offsets into dynamic shared memory
+    unsigned a;          // float4[n_fields * n_spheres]
+    unsigned b;          // float[n_fields * n_spheres]
+};
+
 struct CostArgs {
     const float* x;
     int B, H, D, d, M;
@@ -43,6 +48,7 @@ struct CostArgs {
     int list_cap;                      // broad-phase list entries per warp (max primitives of one field)
     mpb_extra_cost_desc ex;            // CostGPTrajectory / CostJointLimits (only read by the XF variant)
     float* jl_out;                     // [B] raw joint-limit term per trajectory
+    CullTable ctab;                    // packed kernel: link-frame cull table (cost_eval_packed.cuh)
     int k2_local;                      // packed kernel: sphere-only lists are culled in the link frame (MPB_K2_LOCAL=0: world frame)
 };
 
@@ -667,6 +673,12 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
     a.list_off = off;
     // packed: per-warp primitive DATA lists (52 bytes per entry); generic: index lists
     off += packed ? (unsigned)(nw * a.list_cap * 52) : (unsigned)(nw * 2 * a.list_cap * sizeof(unsigned short));
+    if (packed) {
+        const unsigned nt = (unsigned)(n_fields * robot->n_spheres);
+        off = (off + 15u) & ~15u;
+        a.ctab.a = off; off += nt * 16u;
+        a.ctab.b = off; off += (nt * 4u + 15u) & ~15u;
+    }
     const size_t smem = off;
     MPB_REQUIRE(smem <= 227 * 1024, "mpb_cost_eval: %zu bytes of shared memory needed (H*D too large or too many primitives)", smem);
 
