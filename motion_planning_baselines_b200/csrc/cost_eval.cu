@@ -559,9 +559,9 @@ static cudaError_t launch(const CostArgs& a, int blocks_needed, size_t smem, cud
 
 namespace mpb {
 
-template <int DOF, int NW, int MINB>
-static cudaError_t launch_chain2(const CostArgs& a, size_t smem, cudaStream_t st) {
-    auto kern = cost_eval_chain2_kernel<DOF, NW, MINB>;
+template <int DOF, int NW, int MINB, bool BOXES>
+static cudaError_t launch_chain2b(const CostArgs& a, size_t smem, cudaStream_t st) {
+    auto kern = cost_eval_chain2_kernel<DOF, NW, MINB, BOXES>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -574,6 +574,13 @@ static cudaError_t launch_chain2(const CostArgs& a, size_t smem, cudaStream_t st
     const int grid = blocks_needed < resident ? blocks_needed : resident;
     kern<<<grid, NW * 32, smem, st>>>(a);
     return cudaSuccess;
+}
+
+template <int DOF, int NW, int MINB>
+static cudaError_t launch_chain2(const CostArgs& a, size_t smem, cudaStream_t st) {
+    bool boxes = !a.k2_local;                 // MPB_K2_LOCAL=0 (A/B, tests): the instance with the world-frame cull
+    for (int i = 0; i < a.fields.n_fields; ++i) boxes = boxes || a.fields.f[i].n_boxes > 0;
+    return boxes ? launch_chain2b<DOF, NW, MINB, true>(a, smem, st) : launch_chain2b<DOF, NW, MINB, false>(a, smem, st);
 }
 
 // MPB_COST_EVAL=generic forces the one-waypoint-per-lane kernel (A/B timing and the cross-check in the tests).

@@ -251,3 +251,52 @@ def test_sampling_properties_full_size(dev):
     x2 = torch.empty_like(x)
     _lib.check(lib.mpb_sample_gp(_lib.ptr(L), _lib.ptr(torch.zeros_like(mu)), _lib.ptr(2 * eps), _lib.ptr(x2), P, S, M, _lib.stream_ptr()))
     assert_close(x2, 2 * (x - mu.unsqueeze(1)), rtol=1e-4, atol=1e-5, what='linearity')
+
+
+@pytest.mark.parametrize('n_obst,seed,noise', [(16, 0, 0.4), (40, 1, 0.4), (4, 2, 0.05)])
+def test_link_frame_cull_is_conservative(n_obst, seed, noise, dev, monkeypatch):
+    """The packed kernel culls sphere-only obstacle lists in the link frame (cost_eval_packed.cuh::cull_link_local:
+    expanded pair test with a slack).  That pass only decides which spheres reach the exact pass, so it must flag a
+    superset of the world-frame cull's set: identical collision-free flags, collision term equal up to the order of the
+    per-lane sums, and both equal to the oracle.  Dense random sphere fields around the arm (also > 32 primitives)."""
+    import os
+    from motion_planning_baselines_b200.costs import build_gpmp2_cost_composite
+    from motion_planning_baselines_b200.fields import CollisionField
+    from motion_planning_baselines_b200.models import ObstacleSet
+    from motion_planning_baselines_b200.robots import Robot
+    from oracle.build import TA, oracle_field, oracle_robot
+    from oracle.costs import CostSpec
+    cfg = configs.config('C4')
+    model = cfg['robot']
+    rng = np.random.default_rng(100 + seed)
+    centers = np.stack([rng.uniform(-0.8, 0.8, n_obst), rng.uniform(-0.8, 0.8, n_obst), rng.uniform(0.0, 1.1, n_obst)], 1)
+    obst = ObstacleSet(3, sphere_centers=centers.tolist(), sphere_radii=rng.uniform(0.03, 0.2, n_obst).tolist(),
+                       cutoff_margin=0.05, name='random_spheres')
+    H, d, B = 64, 7, 96
+    gen = torch.Generator().manual_seed(77 + seed)
+    start, goal = T(cfg['start']), T(cfg['goal'])
+    w = torch.linspace(0, 1, H).view(1, H, 1)
+    x = torch.zeros(B, H, 2 * d)
+    x[..., :d] = start * (1 - w) + goal * w + noise * torch.randn(B, H, d, generator=gen).cumsum(1) / np.sqrt(H) + 0.75 * noise * torch.randn(B, 1, d, generator=gen)
+    x[..., d:] = 0.5 * torch.randn(B, H, d, generator=gen)
+    sig = dict(sigma_start=1e-2, sigma_gp=1.0, sigma_goal_prior=1e-2, sigma_coll=1e-1)
+    robot = Robot(model, dt=cfg['dt'], tensor_args=dev)
+    comp = build_gpmp2_cost_composite(robot=robot, n_support_points=H, dt=cfg['dt'], start_state=start.to(**dev),
+                                      multi_goal_states=goal.to(**dev).unsqueeze(0), num_particles_per_goal=B,
+                                      collision_fields=[CollisionField(obst, tensor_args=dev)], num_samples=1,
+                                      tensor_args=dev, **sig)
+    xg = x.to(**dev)
+    res = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('MPB_K2_LOCAL', mode)
+        os.putenv('MPB_K2_LOCAL', mode)          # the C side reads it with getenv() at every call
+        terms, _ = comp.eval(xg, return_invidual_costs_and_weights=True)
+        res[mode] = (torch.stack(terms).cpu(), comp.collision_free(xg).cpu())
+    os.unsetenv('MPB_K2_LOCAL')
+    assert torch.equal(res['0'][1], res['1'][1]), 'collision-free flags: link-frame cull vs world-frame cull'
+    assert_close(res['1'][0], res['0'][0], rtol=2e-6, atol=1e-7, what='terms: link-frame vs world-frame cull')
+    spec = CostSpec(oracle_robot(model, cfg['dt']), H, cfg['dt'], start, goal, [oracle_field(obst, model)], tensor_args=TA, **sig)
+    assert_close(res['1'][0], torch.stack(spec.terms(x)), rtol=1e-5, atol=1e-6, what='terms vs oracle')
+    ref_free = spec.collision_free(x)
+    assert not ref_free.all(), 'test data should contain colliding trajectories'
+    assert torch.equal(res['1'][1], ref_free), 'collision-free flags vs oracle'
