@@ -593,9 +593,9 @@ static bool packed_allowed() {
 // MPB_K2_CFG=<warps>x<ctas> selects one of the compiled experiment shapes (7-dof chains only).
 static int k2_cfg() {
     const char* v = getenv("MPB_K2_CFG");
-    if (!v) return 82;
+    if (!v) return 0;
     int w = 0, c = 0;
-    if (sscanf(v, "%dx%d", &w, &c) != 2) return 82;
+    if (sscanf(v, "%dx%d", &w, &c) != 2) return 0;
     return w * 10 + c;
 }
 
@@ -663,9 +663,19 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
     // serial chains against primitive fields take the packed two-waypoints-per-lane kernel (cost_eval_packed.cuh)
     bool packed = robot->kind == MPB_ROBOT_CHAIN && !a.fields.has_extra && !has_extra_terms && robot->q_dim >= 2 &&
                   robot->q_dim <= 8 && packed_allowed();
-    const int cfg = (packed && robot->q_dim == 7) ? k2_cfg() : 82;
+    int cfg = 82;
+    if (packed && robot->q_dim == 7) {
+        // measured at C4 (profiles/r02_k2_cfg_sweep.txt): without box code the kernel fits 96 registers, and 2 CTAs x 10 warps
+        // (5 warps per scheduler) beat 2 x 8 at 116; the instance with box code spills at 96 and keeps 8 x 2
+        bool boxes = false;
+        for (int i = 0; i < n_fields; ++i) boxes = boxes || fields[i].n_boxes > 0;
+        const char* kl = getenv("MPB_K2_LOCAL");
+        if (kl && kl[0] == '0') boxes = true;
+        cfg = k2_cfg();
+        if (cfg == 0) cfg = boxes ? 82 : 102;
+    }
     int nw = packed ? cfg / 10 : kWarps;
-    if (nw != 4 && nw != 6 && nw != 8) nw = 8;
+    if (nw != 4 && nw != 6 && nw != 8 && nw != 10 && nw != 12) nw = 8;
     a.row_stride = (a.M + 3) & ~3;
     a.rows_off = off;
     off += (unsigned)(nw * 2 * a.row_stride * sizeof(float));       // current + prefetched row per warp
@@ -713,6 +723,8 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
                     case 45: e = launch_chain2<7, 4, 5>(a, smem, st); break;
                     case 46: e = launch_chain2<7, 4, 6>(a, smem, st); break;
                     case 63: e = launch_chain2<7, 6, 3>(a, smem, st); break;
+                    case 102: e = launch_chain2<7, 10, 2>(a, smem, st); break;
+                    case 122: e = launch_chain2<7, 12, 2>(a, smem, st); break;
                     default: e = launch_chain2<7, 8, 2>(a, smem, st); break;
                 }
         }
