@@ -213,6 +213,12 @@ long long mpb_sample_gp_kron_gen_bytes(int H, int dof);
 int mpb_sample_gp_kron_gen_prepare(const float* LkT, void* Limg, int H, int dof, void* stream);
 int mpb_sample_gp_kron_gen(const void* Limg, const float* mu, const mpb_noise_desc* noise, float* x, int P, int S, int H,
                            int dof, void* stream);
+/* The same launch with one more warp per CTA that computes y[p] = Sigma_inv @ mu[p] (the vector of the importance-sampling
+ * term, stoch_gpmp.py:239-241) while the tiles run: bit-identical to mpb_prior_matvec_dof, without its launch.  Sigma_inv
+ * must have the per-dof structure mpb_prior_dof_structured verifies; Sigma_inv and y are both NULL (plain sampler) or
+ * both given. */
+int mpb_sample_gp_kron_gen_mv(const void* Limg, const float* mu, const mpb_noise_desc* noise, float* x, int P, int S, int H,
+                              int dof, const float* Sigma_inv, float* y, void* stream);
 
 /* tcgen05 variant of the structured sampler (csrc/sample_gp_tc.cu, sample_gp_kron_umma_kernel): TMA -> per-dof
  * gather + 3xTF32 split into tensor memory -> one M128 x N32 tcgen05.mma chain per dof with TMEM accumulators -> dofs

@@ -159,11 +159,16 @@ extern "C" int mpb_stoch_gpmp_iter_kron_gen(const void* L_kron_gen, const float*
                                             float step, void* stream) {
     MPB_REQUIRE(robot && L_kron_gen && noise, "mpb_stoch_gpmp_iter_kron_gen: null robot / factor / noise descriptor");
     const int D = 2 * robot->q_dim, M = H * D;
-    int rc = mpb_sample_gp_kron_gen(L_kron_gen, mu, noise, x, P, S, H, robot->q_dim, stream);
-    if (rc) return rc;
-    rc = sigma_inv_structured ? mpb_prior_matvec_dof(Sigma_inv, mu, is_vec, P, H, robot->q_dim, stream)
-                              : mpb_prior_matvec(Sigma_inv, mu, is_vec, P, M, 2 * D - 1, stream);
-    if (rc) return rc;
+    int rc;
+    if (sigma_inv_structured) {      // Sigma^-1 mu rides along in K1 (one extra warp per CTA): no mat-vec launch
+        rc = mpb_sample_gp_kron_gen_mv(L_kron_gen, mu, noise, x, P, S, H, robot->q_dim, Sigma_inv, is_vec, stream);
+        if (rc) return rc;
+    } else {
+        rc = mpb_sample_gp_kron_gen(L_kron_gen, mu, noise, x, P, S, H, robot->q_dim, stream);
+        if (rc) return rc;
+        rc = mpb_prior_matvec(Sigma_inv, mu, is_vec, P, M, 2 * D - 1, stream);
+        if (rc) return rc;
+    }
     rc = mpb_cost_eval(x, P * S, H, robot, fields, n_fields, gp, is_vec, S, temp, cost, nullptr, free_flag, stream);
     if (rc) return rc;
     return mpb_softmax_update(cost, x, mu, weights, nullptr, temp, step, nullptr, P, S, H, D, stream);

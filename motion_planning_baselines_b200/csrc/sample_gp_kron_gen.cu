@@ -10,7 +10,7 @@
 // (kind::f16, three MMAs per k-step: hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; the factor is scaled per dof by a
 // power of two so that its fp16 parts stay normal) -- the same arithmetic as the warp-MMA kernel it supersedes.
 //
-// One persistent CTA per SM, warp-specialised (800 threads for the 7-dof arm):
+// One persistent CTA per SM, warp-specialised (832 threads for the 7-dof arm):
 //   warp 8       factor loader: one elected lane streams the 56 KiB factor chunk of each k-step (16 k x 7 dofs x hi/lo,
 //                pre-arranged on the host side of the C ABI in the exact shared-memory image) with ONE bulk-async copy
 //                (TMA engine, mbarrier complete_tx) into a 2-stage ring
@@ -22,6 +22,7 @@
 //   warps 11-24  noise producers: Philox4x32-10 + Box-Muller, split into fp16 hi / lo and written with 8-byte stores
 //                straight into the canonical K-major (no swizzle) operand tiles of a 3-stage ring; the lane mapping makes
 //                every store bank-conflict free
+//   warp 25      (optional) y_p = Sigma^-1 mu_p of the CTA's particles for the cost kernel's importance-sampling term
 // Noise layout MPB_NOISE_SPMD: the virtual global tensor is [S_glob, P_glob, dof, 2H] (dof-major inside a row), so the
 // four normals of one Philox call are four consecutive k of ONE dof -- one 8-byte store per operand part.  As with the
 // other layouts a value depends only on (seed, offset, global sample, global particle, element): results do not depend
@@ -54,7 +55,8 @@ struct GenCfg {
     static constexpr int PROD_WARPS = 2 * DOF;
     static constexpr int EPI_WARPS = 8;                      // warps 0-7: TMEM lane quadrant x half of a batch's samples
     static constexpr int LOAD_WARP = 8, MMA_WARP = 9, STORE_WARP = 10, FIRST_PROD_WARP = 11;
-    static constexpr int THREADS = (FIRST_PROD_WARP + PROD_WARPS) * 32;
+    static constexpr int MV_WARP = FIRST_PROD_WARP + PROD_WARPS;      // Sigma^-1 mu of this CTA's particles (optional)
+    static constexpr int THREADS = (MV_WARP + 1) * 32;
     static constexpr uint32_t OFF_A = 0;
     static constexpr uint32_t OFF_B = OFF_A + A_STAGES * A_STAGE;
     static constexpr uint32_t OFF_OUT = OFF_B + B_STAGES * B_STAGE;
@@ -72,6 +74,8 @@ struct GenArgs {
     int P, S;
     long long Ntot;                 // P * S rows
     int ntiles;
+    const float* Sinv;              // optional [M, M] prior precision with the per-dof structure (mpb_prior_dof_structured)
+    float* y;                       // optional [P, M]: y[p] = Sinv @ mu[p], computed by warp MV_WARP while the tiles run
     long long* trace;               // optional [64] clock stamps of CTA 0 (MPB_KRON_GEN_TRACE = device pointer; timing experiments)
     int dbg;                        // MPB_KRON_GEN_DBG bit mask (timing experiments only): 1 no Philox (zeros), 2 no MMAs,
                                     // 4 no output stores, 8 no factor loads, 128 no epilogue TMEM loads, 256 no epilogue smem writes
@@ -302,7 +306,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             }
             bulk_wait<0>();
         }
-    } else if (warp >= C::FIRST_PROD_WARP) {
+    } else if (warp >= C::FIRST_PROD_WARP && warp < C::MV_WARP) {
         // ================================ noise producers ==============================
         const int pw = warp - C::FIRST_PROD_WARP;
         const int j = pw % DOF, g2 = pw / DOF;                  // dof, one bit of the 8-sample group
@@ -355,6 +359,55 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                 if (lane == 0) mbar_arrive(&b_full[bs]);
                 if (pw == 0 && lane == 0 && (kc == 0 || kc == C::NKC - 1)) stamp((t - blockIdx.x) / gridDim.x, kc == 0 ? 4 : 5);
                 if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
+            }
+        }
+    } else if (warp == C::MV_WARP && a.y) {
+        // ================================ Sigma^-1 mu ===================================
+        // The importance-sampling term of the cost kernel needs y_p = Sigma^-1 mu_p (stoch_gpmp.py:239-241).  It depends
+        // only on the means this kernel reads anyway, so one otherwise idle warp computes it for the particles
+        // p = blockIdx.x, blockIdx.x + gridDim.x, ... while the tiles run: the 12 us launch + latency chain of a separate
+        // prior_matvec_dof_kernel disappears from the iteration.  Same arithmetic as that kernel (sample_gp.cu: 7
+        // non-zeros per row, double-float accumulation in the order m = -3..3), so y is bit-identical.
+        constexpr int MAXP = 4;
+        for (int pb = blockIdx.x; pb < a.P; pb += MAXP * gridDim.x) {
+            int np = 0;
+            const float* mrow[MAXP];
+#pragma unroll
+            for (int q = 0; q < MAXP; ++q) {
+                const int p = pb + q * gridDim.x;
+                mrow[q] = a.mu + (size_t)(p < a.P ? p : pb) * C::M;
+                if (p < a.P) np = q + 1;
+            }
+#pragma unroll 1
+            for (int i = lane; i < C::M; i += 32) {
+                float sv[7];
+#pragma unroll
+                for (int m = 0; m < 7; ++m) {
+                    const int jj = i + (m - 3) * DOF;
+                    sv[m] = (jj >= 0 && jj < C::M) ? __ldg(a.Sinv + (size_t)jj * C::M + i) : 0.f;
+                }
+                float mv[MAXP][7];
+#pragma unroll
+                for (int q = 0; q < MAXP; ++q)
+#pragma unroll
+                    for (int m = 0; m < 7; ++m) {
+                        const int jj = i + (m - 3) * DOF;
+                        mv[q][m] = (jj >= 0 && jj < C::M) ? __ldg(mrow[q] + jj) : 0.f;
+                    }
+#pragma unroll
+                for (int q = 0; q < MAXP; ++q) {
+                    float hi = 0.f, lo = 0.f;
+#pragma unroll
+                    for (int m = 0; m < 7; ++m) {
+                        const float pr = __fmul_rn(sv[m], mv[q][m]);
+                        const float e = fmaf(sv[m], mv[q][m], -pr);
+                        const float t = __fadd_rn(hi, pr);
+                        const float z = __fsub_rn(t, hi);
+                        lo = __fadd_rn(lo, __fadd_rn(__fadd_rn(__fsub_rn(hi, __fsub_rn(t, z)), __fsub_rn(pr, z)), e));
+                        hi = t;
+                    }
+                    if (q < np) a.y[(size_t)(pb + q * gridDim.x) * C::M + i] = __fadd_rn(hi, lo);
+                }
             }
         }
     }
@@ -420,8 +473,14 @@ extern "C" int mpb_sample_gp_kron_gen_prepare(const float* LkT, void* Limg, int 
 
 extern "C" int mpb_sample_gp_kron_gen(const void* Limg, const float* mu, const mpb_noise_desc* nd, float* x, int P, int S, int H,
                                       int dof, void* stream) {
+    return mpb_sample_gp_kron_gen_mv(Limg, mu, nd, x, P, S, H, dof, nullptr, nullptr, stream);
+}
+
+extern "C" int mpb_sample_gp_kron_gen_mv(const void* Limg, const float* mu, const mpb_noise_desc* nd, float* x, int P, int S, int H,
+                                         int dof, const float* Sigma_inv, float* y, void* stream) {
     using namespace mpb;
     MPB_REQUIRE(Limg && mu && nd && x, "mpb_sample_gp_kron_gen: null pointer");
+    MPB_REQUIRE((Sigma_inv == nullptr) == (y == nullptr), "mpb_sample_gp_kron_gen_mv: Sigma_inv and y go together");
     MPB_REQUIRE(P >= 0 && S >= 0, "mpb_sample_gp_kron_gen: bad sizes P=%d S=%d", P, S);
     MPB_REQUIRE(mpb_sample_gp_kron_gen_supported(H, dof), "mpb_sample_gp_kron_gen: shape H=%d dof=%d not supported", H, dof);
     MPB_REQUIRE(((uintptr_t)Limg | (uintptr_t)mu | (uintptr_t)x) % 16 == 0, "mpb_sample_gp_kron_gen: pointers must be 16-byte aligned");
@@ -433,13 +492,14 @@ extern "C" int mpb_sample_gp_kron_gen(const void* Limg, const float* mu, const m
     MPB_REQUIRE(!why, "mpb_sample_gp_kron_gen: %s", why);
     a.Limg = static_cast<const unsigned char*>(Limg);
     a.mu = mu; a.x = x; a.P = P; a.S = S;
+    a.Sinv = Sigma_inv; a.y = y;
     a.Ntot = (long long)P * S;
     a.ntiles = (int)((a.Ntot + C::TS - 1) / C::TS);
     { const char* v = getenv("MPB_KRON_GEN_DBG"); a.dbg = v ? atoi(v) : 0; }
     { const char* v = getenv("MPB_KRON_GEN_TRACE"); a.trace = v ? reinterpret_cast<long long*>(strtoull(v, nullptr, 0)) : nullptr; }
     cudaError_t e = cudaFuncSetAttribute(sample_gp_kron_gen_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) { set_error("mpb_sample_gp_kron_gen: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
-    const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
+    const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();     // >= 1: the mat-vec warp strides the particles by the grid
     sample_gp_kron_gen_kernel<7><<<grid, C::THREADS, C::SMEM, static_cast<cudaStream_t>(stream)>>>(a, noise);
     return check_launch("mpb_sample_gp_kron_gen");
 }

@@ -256,7 +256,15 @@ class StochGPMP(OptimizationPlanner):
         rec = (lambda i: events[i].record()) if events is not None else (lambda i: None)
         rec(0)
         split = self._sample_dist.scale_tril_split
-        if eps is None:
+        mv_fused = False
+        if eps is None and self._sample_dist.scale_tril_kron_gen is not None and self._sinv_structured:
+            # the tcgen05 sampler computes Sigma^-1 mu on one extra warp per CTA (as mpb_stoch_gpmp_iter_kron_gen runs it)
+            nd = self._sample_dist.noise.next()
+            _lib.check(lib.mpb_sample_gp_kron_gen_mv(_lib.ptr(self._sample_dist.scale_tril_kron_gen), _lib.ptr(self._particle_means),
+                                                     C.byref(nd), _lib.ptr(self.state_samples), P, S, H, self.n_dof,
+                                                     _lib.ptr(self.Sigma_inv), _lib.ptr(self._is_vec), st))
+            mv_fused = True
+        elif eps is None:
             self._sample_dist.means = self._particle_means.view(P, -1)
             self._sample_dist.sample(S, out=self.state_samples.view(P, S, M))
         elif self._sample_dist.kron_tc_kind == 2:
@@ -275,7 +283,8 @@ class StochGPMP(OptimizationPlanner):
             _lib.check(lib.mpb_sample_gp(_lib.ptr(self._sample_dist.scale_tril), _lib.ptr(self._particle_means), _lib.ptr(eps),
                                          _lib.ptr(self.state_samples), P, S, M, st))
         rec(1)
-        self._prior_matvec(st)
+        if not mv_fused:
+            self._prior_matvec(st)
         rec(2)
         _lib.check(lib.mpb_cost_eval(_lib.ptr(self.state_samples), P * S, H, C.byref(self.robot.desc), fields, nf,
                                      C.byref(gp), _lib.ptr(self._is_vec), S, self.temperature, _lib.ptr(self.costs), None,

@@ -97,3 +97,30 @@ def test_gen_sampler_rejects_bad_arguments(dev):
                                       _lib.stream_ptr()) != 0
     assert lib.mpb_sample_gp_kron_gen(_lib.ptr(prior.scale_tril_kron_gen), _lib.ptr(means), C.byref(d), _lib.ptr(x), 0, 4, 64, 7,
                                       _lib.stream_ptr()) == 0
+
+
+@pytest.mark.parametrize('P,S', [(512, 64), (5, 24), (1, 1), (300, 7)])
+def test_gen_sampler_with_prior_matvec_warp(P, S, dev):
+    """mpb_sample_gp_kron_gen_mv: the extra warp's y = Sigma^-1 mu (IS term, stoch_gpmp.py:239-241) is bit-identical to
+    mpb_prior_matvec_dof, and the samples are bit-identical to the plain launch."""
+    import ctypes as C
+    prior, means = make_prior(P, dev)
+    lib = _lib.lib()
+    Sinv = prior.Sigma_inv.contiguous()
+    ok = C.c_int(0)
+    _lib.check(lib.mpb_prior_dof_structured(_lib.ptr(Sinv), 64, 7, C.byref(ok), _lib.stream_ptr()))
+    assert ok.value == 1
+    desc = nd(5, 9, P_glob=P)
+    x0 = prior.sample(S, noise_desc=desc).clone()
+    y_ref = torch.empty(P, 64 * 14, **dev)
+    _lib.check(lib.mpb_prior_matvec_dof(_lib.ptr(Sinv), _lib.ptr(means), _lib.ptr(y_ref), P, 64, 7, _lib.stream_ptr()))
+    x1 = torch.empty_like(x0)
+    y = torch.full((P, 64 * 14), float('nan'), **dev)
+    _lib.check(lib.mpb_sample_gp_kron_gen_mv(_lib.ptr(prior.scale_tril_kron_gen), _lib.ptr(means.contiguous()), C.byref(desc),
+                                             _lib.ptr(x1), P, S, 64, 7, _lib.ptr(Sinv), _lib.ptr(y), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(x1, x0)
+    assert torch.equal(y, y_ref)
+    with pytest.raises(_lib.MpbError):
+        _lib.check(lib.mpb_sample_gp_kron_gen_mv(_lib.ptr(prior.scale_tril_kron_gen), _lib.ptr(means), C.byref(desc), _lib.ptr(x1),
+                                                 P, S, 64, 7, _lib.ptr(Sinv), None, _lib.stream_ptr()))
