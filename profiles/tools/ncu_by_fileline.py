@@ -23,7 +23,8 @@ for l in dis:
     if m: cur = (os.path.basename(m.group(1)), int(m.group(2))); continue     # with -gi the last line of a chain is the outermost frame
     m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)', l)
     if m: line_of[int(m.group(1), 16)] = cur; op_of[int(m.group(1), 16)] = m.group(2)
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+kern = [a[len('--kernel='):] for a in sys.argv if a.startswith('--kernel=')]      # ncu -k filter when the report holds several kernels
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + (['-k', kern[0]] if kern else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hi = [i for i, r in enumerate(rows) if 'Source' in r and 'Address' in r][0]
 hdr = rows[hi]
