@@ -393,31 +393,29 @@ def main():
     consumed = [torch.cuda.Event() for _ in range(2)]
     Ke = max(3, min(K, 20))
 
-    def upload_problem(i):
-        b = i % 2
-        with torch.cuda.stream(up_stream):
-            up_stream.wait_event(consumed[b])
-            d_means[b].copy_(h_means, non_blocking=True)
-            ready[b].record(up_stream)
-
     def e2e_steps(n):
-        for b in range(2):
-            consumed[b].record(main_stream)
-        upload_problem(0)
+        # ONE copy stream and two cross-stream edges per step (each edge costs ~10 us of front-end latency on this box,
+        # profiles/tools/e2e_probe.py): the main stream waits for the upload of its problem; the copy stream waits for the
+        # result.  Copy-stream order: upload of problem i + 1 (its buffer was last read by step i - 1, whose download -- queued
+        # earlier on this stream -- waited for that step), then the download of result i.
+        torch.cuda.synchronize()
+        with torch.cuda.stream(up_stream):
+            d_means[0].copy_(h_means, non_blocking=True)
+            ready[0].record(up_stream)
         for i in range(n):
             b = i % 2
-            if i + 1 < n:
-                upload_problem(i + 1)
             main_stream.wait_event(ready[b])
             planner._particle_means = d_means[b]
             traj = planner.optimize(opt_iters=1)
-            consumed[b].record(main_stream)
             done = torch.cuda.Event()
             done.record(main_stream)
-            with torch.cuda.stream(down_stream):
-                down_stream.wait_event(done)
+            with torch.cuda.stream(up_stream):
+                if i + 1 < n:
+                    d_means[1 - b].copy_(h_means, non_blocking=True)
+                    ready[1 - b].record(up_stream)
+                up_stream.wait_event(done)
                 h_trajs[b].copy_(traj, non_blocking=True)
-            traj.record_stream(down_stream)
+            traj.record_stream(up_stream)
         torch.cuda.synchronize()
     e2e_steps(3)
     barrier()
@@ -567,8 +565,8 @@ def main():
                          steps=Ke, ms_per_step=ms_e2e / Ke,
                          note='planner.optimize(opt_iters=1) exactly as the reference is called (no noise argument: drawn in K1); '
                               'per step the initial particle trajectories come from pinned host memory and the optimised '
-                              'trajectories go back to pinned host memory (copy streams: the next upload / previous download '
-                              "overlap this step's kernels)",
+                              'trajectories go back to pinned host memory (one copy stream: the next upload / this download '
+                              "overlap the kernels)",
                          injected_noise=dict(value=world * P * S * Kj / (ms_e2e_inj * 1e-3), unit=UNIT, ms_per_step=ms_e2e_inj / Kj,
                                              h2d_bytes_per_step=S * P * M * 4, d2h_bytes_per_step=P * H * D * 4,
                                              h2d_gb_per_s=S * P * M * 4 / (ms_e2e_inj / Kj * 1e-3) / 1e9,

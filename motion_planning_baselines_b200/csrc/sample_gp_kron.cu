@@ -582,7 +582,13 @@ static int launch_kron(const void* Lp, const float* mu, const float* eps, float*
 
 }  // namespace mpb
 
-#define MPB_KRON_SHAPES(X) X(2, 32) X(2, 64) X(2, 128) X(3, 32) X(3, 64) X(3, 128) X(7, 32) X(7, 64)
+// Any (dof, H) with H % 16 == 0 and dof * H <= 512 (one warp per dof and 32-row output pair: <= 1024 threads) fits the
+// kernels; the list instantiates the horizons the reference's examples use (32 / 64 / 128 support points, plus 16 and 48
+// for short horizons) for 2-D / 3-D point robots and chains of 4..8 joints.  Other shapes take the dense samplers.
+#define MPB_KRON_SHAPES(X)                                                                            \
+    X(2, 16) X(2, 32) X(2, 48) X(2, 64) X(2, 128) X(3, 16) X(3, 32) X(3, 48) X(3, 64) X(3, 128)      \
+    X(4, 32) X(4, 64) X(5, 32) X(5, 64) X(6, 32) X(6, 64) X(7, 16) X(7, 32) X(7, 48) X(7, 64)         \
+    X(8, 32) X(8, 64)
 
 extern "C" int mpb_sample_gp_kron_supported(int H, int dof) {
 #define X(d, h) if (dof == d && H == h) return 1;

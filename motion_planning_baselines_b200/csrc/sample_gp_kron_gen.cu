@@ -38,17 +38,26 @@
 
 namespace mpb {
 
-template <int DOF>
+// TS_ = 64: one accumulator set (7 x 64 = 448 of the 512 tensor-memory columns): the epilogue of a tile and the MMAs of
+// the next are serial.  TS_ = 32: TWO sets of 7 x 32 columns, ping-pong: the epilogue of tile t drains one set while the
+// MMAs of tile t + 1 fill the other, so noise production (the longest stage) runs without the epilogue gap; the price is
+// that every factor chunk is streamed once per 32 samples instead of once per 64 (twice the L2 -> shared-memory traffic,
+// twice as many, half as wide MMAs).  A noise stage holds 64 / TS_ k-chunks, so a producer thread always runs four Philox
+// chains per stage.
+template <int DOF, int TS_>
 struct GenCfg {
     static constexpr int NOUT = 128;                         // 2H = rows of a per-dof block (UMMA M); H = 64
-    static constexpr int TS = 64;                            // samples per tile (UMMA N)
-    static constexpr int KC = 16;                            // k per stage = one kind::f16 MMA
+    static constexpr int TS = TS_;                           // samples per tile (UMMA N)
+    static constexpr int NSETS = TS == 32 ? 2 : 1;           // accumulator sets in tensor memory
+    static constexpr int KPS = 64 / TS;                      // k-chunks per noise stage
+    static constexpr int KC = 16;                            // k per factor stage = one kind::f16 MMA
     static constexpr int NKC = NOUT / KC;
     static constexpr int M = NOUT * DOF;                     // floats per trajectory row
-    static constexpr uint32_t B_TILE = TS * KC * 2;          // noise tile of one (dof, part): 2 KiB
+    static constexpr uint32_t B_TILE = TS * KC * 2;          // noise tile of one (chunk, dof, part): 2 / 1 KiB
     static constexpr uint32_t A_TILE = NOUT * KC * 2;        // factor tile of one (dof, part): 4 KiB
-    static constexpr uint32_t B_STAGE = DOF * 2 * B_TILE;
+    static constexpr uint32_t B_STAGE = KPS * DOF * 2 * B_TILE;
     static constexpr uint32_t A_STAGE = DOF * 2 * A_TILE;
+    static_assert(TS == 64 || TS == 32, "tile of 64 or 32 samples");
     static constexpr int B_STAGES = 3, A_STAGES = 2;
     static constexpr int OUT_ROWS = 4;                       // samples per staged output batch
     static constexpr uint32_t OUT_BUF = OUT_ROWS * M * 4;
@@ -62,8 +71,8 @@ struct GenCfg {
     static constexpr uint32_t OFF_OUT = OFF_B + B_STAGES * B_STAGE;
     static constexpr uint32_t OFF_BAR = OFF_OUT + 2 * OUT_BUF;
     static constexpr uint32_t SMEM = OFF_BAR + 256 + 128 /*alignment slack*/;
-    static constexpr uint32_t TMEM_COLS = DOF * TS <= 256 ? 256 : 512;
-    static_assert(DOF * TS <= 512, "accumulators must fit tensor memory");
+    static constexpr uint32_t TMEM_COLS = NSETS * DOF * TS <= 256 ? 256 : 512;
+    static_assert(NSETS * DOF * TS <= 512, "accumulators must fit tensor memory");
     static_assert(SMEM <= 227 * 1024, "shared-memory budget");
 };
 
@@ -116,10 +125,10 @@ __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
-template <int DOF>
-__global__ void __launch_bounds__(GenCfg<DOF>::THREADS, 1)
+template <int DOF, int TS_>
+__global__ void __launch_bounds__(GenCfg<DOF, TS_>::THREADS, 1)
 sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
-    using C = GenCfg<DOF>;
+    using C = GenCfg<DOF, TS_>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
@@ -127,9 +136,9 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
     uint64_t* a_empty = a_full + C::A_STAGES;          // [A_STAGES] MMAs that read it completed
     uint64_t* b_full = a_empty + C::A_STAGES;          // [B_STAGES] noise chunk written (PROD_WARPS arrivals)
     uint64_t* b_empty = b_full + C::B_STAGES;          // [B_STAGES]
-    uint64_t* acc_full = b_empty + C::B_STAGES;        // accumulators of the tile complete
-    uint64_t* acc_empty = acc_full + 1;                // accumulators drained (4 epilogue warps)
-    uint64_t* out_full = acc_empty + 1;                // [2] staged rows written (one arrival per epilogue warp)
+    uint64_t* acc_full = b_empty + C::B_STAGES;        // [NSETS] accumulators of the tile complete
+    uint64_t* acc_empty = acc_full + C::NSETS;         // [NSETS] accumulators drained (epilogue warps)
+    uint64_t* out_full = acc_empty + C::NSETS;         // [2] staged rows written (one arrival per epilogue warp)
     uint64_t* out_empty = out_full + 2;                // [2] the bulk store has read the buffer (store warp)
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(out_empty + 2);
 
@@ -142,8 +151,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], C::PROD_WARPS); mbar_init(&b_empty[s], 1); }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, C::EPI_WARPS);
+        for (int s = 0; s < C::NSETS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], C::EPI_WARPS); }
         for (int s = 0; s < 2; ++s) { mbar_init(&out_full[s], C::EPI_WARPS); mbar_init(&out_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -178,30 +186,32 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             // lane issues
             const bool leader = elect_one();
             int as = 0, bs = 0;
-            uint32_t aph = 0, bph = 0, acc_ph = 0;
+            uint32_t aph = 0, bph = 0;
             const uint32_t idesc = make_idesc_f16(C::NOUT, C::TS);
             const uint64_t adesc0 = make_nosw_desc(smem_u32(sm + C::OFF_A), 128u, 256u);
             const uint64_t bdesc0 = make_nosw_desc(smem_u32(sm + C::OFF_B), 128u, 256u);
             const uint32_t adesc_lo = (uint32_t)adesc0, bdesc_lo = (uint32_t)bdesc0, desc_hi = (uint32_t)(adesc0 >> 32);
             int ord = 0;
             for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++ord) {
-                mbar_wait(acc_empty, acc_ph ^ 1);
+                const int set = ord % C::NSETS;
+                mbar_wait(&acc_empty[set], (((uint32_t)(ord / C::NSETS)) & 1u) ^ 1u);
                 tc_fence_after();
                 if (lane == 0) stamp(ord, 6);
                 for (int kc = 0; kc < C::NKC; ++kc) {
+                    const int u = kc % C::KPS;                      // chunk inside the noise stage
                     mbar_wait(&a_full[as], aph);
-                    mbar_wait(&b_full[bs], bph);
+                    if (u == 0) mbar_wait(&b_full[bs], bph);
                     tc_fence_after();
                     if (kc == 0 && lane == 0) stamp(ord, 0);
                     // descriptors differ only in the 14-bit start-address field: one 32-bit add each
                     const uint32_t alo_w = adesc_lo + (uint32_t)((as * C::A_STAGE) >> 4);
-                    const uint32_t blo_w = bdesc_lo + (uint32_t)((bs * C::B_STAGE) >> 4);
+                    const uint32_t blo_w = bdesc_lo + (uint32_t)((bs * C::B_STAGE + u * (DOF * 2 * C::B_TILE)) >> 4);
                     if (leader && !(a.dbg & 2)) {
 #pragma unroll
                         for (int j = 0; j < DOF; ++j) {
                             const uint32_t ahi = alo_w + (uint32_t)(((2 * j) * C::A_TILE) >> 4), alo = ahi + (C::A_TILE >> 4);
                             const uint32_t bhi = blo_w + (uint32_t)(((2 * j) * C::B_TILE) >> 4), blo = bhi + (C::B_TILE >> 4);
-                            const uint32_t d = tmem_base + (uint32_t)(j * C::TS);
+                            const uint32_t d = tmem_base + (uint32_t)(set * (DOF * C::TS) + j * C::TS);
                             if (kc == 0) umma_f16_w(d, alo, bhi, desc_hi, idesc, 0u);          // small terms first
                             else umma_f16_w(d, alo, bhi, desc_hi, idesc, 1u);
                             umma_f16_w(d, ahi, blo, desc_hi, idesc, 1u);
@@ -210,15 +220,14 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                     }
                     if (leader) {
                         umma_commit(&a_empty[as]);
-                        umma_commit(&b_empty[bs]);
+                        if (u == C::KPS - 1) umma_commit(&b_empty[bs]);
                     }
                     __syncwarp();
                     if (++as == C::A_STAGES) { as = 0; aph ^= 1; }
-                    if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
+                    if (u == C::KPS - 1 && ++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
                 }
-                if (leader) umma_commit(acc_full);
+                if (leader) umma_commit(&acc_full[set]);
                 if (lane == 0) stamp(ord, 1);
-                acc_ph ^= 1;
             }
         }
     } else if (warp < C::EPI_WARPS) {
@@ -232,8 +241,10 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
 #pragma unroll
         for (int j = 0; j < DOF; ++j) inv_scale[j] = __ldg(inv_scale_g + j);
         const bool one_particle = (a.S % C::TS) == 0;
-        uint32_t acc_ph = 0, use = 0;                           // use: batches staged so far (all tiles)
-        for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        uint32_t use = 0;                                       // batches staged so far (all tiles)
+        int ord = 0;
+        for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++ord) {
+            const int set = ord % C::NSETS;
             const long long row0 = (long long)t * C::TS;
             float mrow[DOF];
             if (one_particle) {
@@ -241,13 +252,13 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
 #pragma unroll
                 for (int j = 0; j < DOF; ++j) mrow[j] = __ldg(mp + j);
             }
-            mbar_wait(acc_full, acc_ph);
+            mbar_wait(&acc_full[set], ((uint32_t)(ord / C::NSETS)) & 1u);
             tc_fence_after();
-            if (et == 0) stamp((t - blockIdx.x) / gridDim.x, 2);
+            if (et == 0) stamp(ord, 2);
             for (int b = 0; b < C::TS / C::OUT_ROWS; ++b, ++use) {
                 const int buf = use & 1;
                 uint32_t r[DOF][2];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * C::OUT_ROWS + 2 * half);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * (DOF * C::TS) + b * C::OUT_ROWS + 2 * half);
                 if (!(a.dbg & 128)) {
 #pragma unroll
                     for (int j = 0; j < DOF; ++j) tmem_ld2_nowait(taddr + (uint32_t)(j * C::TS), r[j]);
@@ -279,9 +290,8 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);
-            if (et == 0) stamp((t - blockIdx.x) / gridDim.x, 3);
-            acc_ph ^= 1;
+            if (lane == 0) mbar_arrive(&acc_empty[set]);
+            if (et == 0) stamp(ord, 3);
         }
     } else if (warp == C::STORE_WARP) {
         // ================================ store issuer ==================================
@@ -314,20 +324,21 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
         int bs = 0;
         uint32_t bph = 0;
         for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-            // the two samples of this thread in the tile and their rows in the virtual global noise tensor
+            // the thread's two work units of a noise stage: TS = 64 -- two samples (8-sample groups g and g + 4) of ONE
+            // k-chunk; TS = 32 -- one sample of TWO consecutive k-chunks.  Either way four Philox calls per stage.
             long long grow[2];
             int sgrp[2];
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
-                sgrp[it] = g1 + 2 * g2 + 4 * it;
+                sgrp[it] = g1 + 2 * g2 + (C::KPS == 1 ? 4 * it : 0);
                 long long n = (long long)t * C::TS + sgrp[it] * 8 + r8;
                 if (n >= a.Ntot) n = a.Ntot - 1;                  // rows past the end are never stored
                 const long long p = n / a.S, s = n - p * a.S;
                 grow[it] = (((noise.s_off + s) * noise.P_glob + noise.p_off + p) * DOF + j) * (C::NOUT / 4);
             }
-            for (int kc = 0; kc < C::NKC; ++kc) {
+            for (int ks = 0; ks < C::NKC / C::KPS; ++ks) {
                 mbar_wait(&b_empty[bs], bph ^ 1);
-                const uint32_t tile = smem_u32(sm + C::OFF_B + bs * C::B_STAGE + (2 * j) * C::B_TILE);
+                const uint32_t stage = smem_u32(sm + C::OFF_B + bs * C::B_STAGE + (2 * j) * C::B_TILE);
                 // the four Philox / Box-Muller chains of this thread are generated together (no branches in between) so
                 // that their long dependency chains interleave; rows past the end draw (unused) values like any other
                 uint2 hi[4], lo[4];
@@ -336,8 +347,10 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
 #pragma unroll
                     for (int it = 0; it < 2; ++it)
 #pragma unroll
-                        for (int qq = 0; qq < 2; ++qq)
+                        for (int qq = 0; qq < 2; ++qq) {
+                            const int kc = C::KPS == 1 ? ks : 2 * ks + it;
                             e[2 * it + qq] = philox_normal4((unsigned long long)grow[it] + (unsigned)(kc * 4 + 2 * qq + par), noise);
+                        }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) split4_f16(e[i], hi[i], lo[i]);
                 } else {
@@ -350,14 +363,15 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                     for (int qq = 0; qq < 2; ++qq) {
                         const int q = 2 * qq + par;                            // 4-k group inside the chunk
                         // (sample row, k) -> core matrix (row / 8, k / 8): 16-byte rows, K groups 128 B apart, row groups 256 B
-                        const uint32_t off = tile + (uint32_t)(sgrp[it] * 256 + (q >> 1) * 128 + r8 * 16 + (q & 1) * 8);
+                        const uint32_t off = stage + (uint32_t)((C::KPS == 1 ? 0 : it) * (DOF * 2 * C::B_TILE)) +
+                                             (uint32_t)(sgrp[it] * 256 + (q >> 1) * 128 + r8 * 16 + (q & 1) * 8);
                         st_shared_v2(off, hi[2 * it + qq]);
                         st_shared_v2(off + C::B_TILE, lo[2 * it + qq]);
                     }
                 fence_async_proxy();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&b_full[bs]);
-                if (pw == 0 && lane == 0 && (kc == 0 || kc == C::NKC - 1)) stamp((t - blockIdx.x) / gridDim.x, kc == 0 ? 4 : 5);
+                if (pw == 0 && lane == 0 && (ks == 0 || ks == C::NKC / C::KPS - 1)) stamp((t - blockIdx.x) / gridDim.x, ks == 0 ? 4 : 5);
                 if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
             }
         }
@@ -485,7 +499,7 @@ extern "C" int mpb_sample_gp_kron_gen_mv(const void* Limg, const float* mu, cons
     MPB_REQUIRE(mpb_sample_gp_kron_gen_supported(H, dof), "mpb_sample_gp_kron_gen: shape H=%d dof=%d not supported", H, dof);
     MPB_REQUIRE(((uintptr_t)Limg | (uintptr_t)mu | (uintptr_t)x) % 16 == 0, "mpb_sample_gp_kron_gen: pointers must be 16-byte aligned");
     if (P == 0 || S == 0) return MPB_OK;
-    using C = GenCfg<7>;
+    using C = GenCfg<7, 64>;
     GenArgs a{};
     NoiseArgs noise{};
     const char* why = noise_args(*nd, P, noise);
@@ -494,12 +508,17 @@ extern "C" int mpb_sample_gp_kron_gen_mv(const void* Limg, const float* mu, cons
     a.mu = mu; a.x = x; a.P = P; a.S = S;
     a.Sinv = Sigma_inv; a.y = y;
     a.Ntot = (long long)P * S;
-    a.ntiles = (int)((a.Ntot + C::TS - 1) / C::TS);
+    // MPB_KRON_GEN_TS=64: the one-accumulator-set variant (A/B timing); default: 32-sample tiles, two sets
+    int ts = 32;
+    { const char* v = getenv("MPB_KRON_GEN_TS"); if (v && atoi(v) == 64) ts = 64; }
+    a.ntiles = (int)((a.Ntot + ts - 1) / ts);
     { const char* v = getenv("MPB_KRON_GEN_DBG"); a.dbg = v ? atoi(v) : 0; }
     { const char* v = getenv("MPB_KRON_GEN_TRACE"); a.trace = v ? reinterpret_cast<long long*>(strtoull(v, nullptr, 0)) : nullptr; }
-    cudaError_t e = cudaFuncSetAttribute(sample_gp_kron_gen_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    static_assert(GenCfg<7, 32>::SMEM == C::SMEM && GenCfg<7, 32>::THREADS == C::THREADS, "both variants share the launch shape");
+    auto kern = ts == 64 ? sample_gp_kron_gen_kernel<7, 64> : sample_gp_kron_gen_kernel<7, 32>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) { set_error("mpb_sample_gp_kron_gen: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
     const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();     // >= 1: the mat-vec warp strides the particles by the grid
-    sample_gp_kron_gen_kernel<7><<<grid, C::THREADS, C::SMEM, static_cast<cudaStream_t>(stream)>>>(a, noise);
+    kern<<<grid, C::THREADS, C::SMEM, static_cast<cudaStream_t>(stream)>>>(a, noise);
     return check_launch("mpb_sample_gp_kron_gen");
 }

@@ -51,7 +51,9 @@ def sample_both(L, LkT, mu, eps, H, dof, dev):
 
 
 @pytest.mark.parametrize('dof,H,P,S', [(2, 32, 3, 7), (2, 64, 1, 64), (2, 128, 5, 13), (3, 32, 4, 8), (3, 64, 7, 33),
-                                       (3, 128, 2, 31), (7, 32, 3, 11), (7, 64, 5, 13), (7, 64, 16, 64), (7, 64, 1, 1)])
+                                       (3, 128, 2, 31), (7, 32, 3, 11), (7, 64, 5, 13), (7, 64, 16, 64), (7, 64, 1, 1),
+                                       (2, 16, 4, 9), (3, 48, 2, 5), (4, 32, 3, 6), (4, 64, 2, 9), (5, 64, 3, 5), (6, 32, 2, 8),
+                                       (6, 64, 2, 5), (7, 16, 3, 7), (7, 48, 2, 6), (8, 32, 2, 7), (8, 64, 2, 5)])
 def test_kron_bit_identical_to_dense_fp32(dof, H, P, S, dev):
     from motion_planning_baselines_b200 import _lib
     assert _lib.lib().mpb_sample_gp_kron_supported(H, dof)
@@ -154,7 +156,9 @@ def test_kron_full_size_properties(dev):
 
 
 @pytest.mark.parametrize('dof,H,P,S', [(2, 32, 3, 7), (2, 64, 1, 64), (2, 128, 5, 13), (3, 32, 4, 8), (3, 64, 7, 33),
-                                       (3, 128, 2, 31), (7, 32, 3, 11), (7, 64, 5, 13), (7, 64, 16, 64), (7, 64, 1, 1)])
+                                       (3, 128, 2, 31), (7, 32, 3, 11), (7, 64, 5, 13), (7, 64, 16, 64), (7, 64, 1, 1),
+                                       (2, 48, 4, 9), (3, 16, 2, 5), (4, 64, 3, 6), (5, 32, 2, 9), (6, 64, 3, 5), (7, 16, 3, 7),
+                                       (7, 48, 2, 6), (8, 32, 2, 7), (8, 64, 2, 33)])
 def test_kron_tc_matches_fp64(dof, H, P, S, dev):
     """Tensor-core variant (warp MMA, two-term fp16 split): within 5e-6 of the noise amplitude of an fp64 product, zero noise
     returns the means exactly, and rows past the ragged end are untouched."""
@@ -254,8 +258,10 @@ def test_structured_entry_points_reject_bad_arguments(dev):
     empty batches are a no-op."""
     from motion_planning_baselines_b200 import _lib
     lib = _lib.lib()
-    assert lib.mpb_sample_gp_kron_supported(64, 7) == 1 and lib.mpb_sample_gp_kron_supported(48, 7) == 0
-    assert lib.mpb_sample_gp_kron_supported(64, 5) == 0 and lib.mpb_sample_gp_kron_umma_supported(24, 7) == 0
+    assert lib.mpb_sample_gp_kron_supported(64, 7) == 1 and lib.mpb_sample_gp_kron_supported(48, 7) == 1
+    assert lib.mpb_sample_gp_kron_supported(64, 5) == 1 and lib.mpb_sample_gp_kron_supported(64, 8) == 1
+    assert lib.mpb_sample_gp_kron_supported(40, 7) == 0 and lib.mpb_sample_gp_kron_supported(128, 7) == 0      # H % 16, dof * H <= 512
+    assert lib.mpb_sample_gp_kron_supported(64, 9) == 0 and lib.mpb_sample_gp_kron_umma_supported(24, 7) == 0
     H, dof, P, S = 64, 7, 2, 4
     M = 2 * H * dof
     buf = torch.zeros(dof * 4 * H * H + 64, **dev)
