@@ -267,7 +267,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
 #pragma unroll
                     for (int j = 0; j < DOF; ++j) r[j][0] = r[j][1] = 0u;
                 }
-                mbar_wait_spin(&out_empty[buf], ((use >> 1) & 1) ^ 1);      // the store that last read this buffer has drained it
+                mbar_wait(&out_empty[buf], ((use >> 1) & 1) ^ 1);      // the store that last read this buffer has drained it
                 float* ob = reinterpret_cast<float*>(sm + C::OFF_OUT + buf * C::OUT_BUF) + DOF * n_out;
 #pragma unroll
                 for (int s2 = 0; s2 < 2; ++s2) {

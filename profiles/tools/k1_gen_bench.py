@@ -43,8 +43,11 @@ for dbg in [0, 1, 4 + 128 + 256]:
     del os.environ['MPB_KRON_GEN_TRACE']
     t = tr.cpu().view(8, 8)
     t0 = int(t[t > 0].min())
+    nt = 4 if os.environ.get('MPB_KRON_GEN_TS') == '64' else 8
     print(f'dbg={dbg}: per tile (cycles): ' + ' | '.join(
-        f'k-loop {int(t[o, 1] - t[o, 0])}, production c0->c7 {int(t[o, 5] - t[o, 4])}, epilogue {int(t[o, 3] - t[o, 2])}, tile {int(t[o, 3] - t[o, 6])}' for o in range(4)))
+        f'k-loop {int(t[o, 1] - t[o, 0])}, production c0->c7 {int(t[o, 5] - t[o, 4])}, epilogue {int(t[o, 3] - t[o, 2])}, tile {int(t[o, 3] - t[o, 6])}' for o in range(nt)))
+    print('   absolute (cycles since the first stamp): ' + ' | '.join(
+        f'mma {int(t[o, 0] - t0)}-{int(t[o, 1] - t0)} epi {int(t[o, 2] - t0)}-{int(t[o, 3] - t0)} prod {int(t[o, 4] - t0)}-{int(t[o, 5] - t0)}' for o in range(nt)))
     continue
     f = tr.cpu()[40:56].view(2, 8)
     for i in range(2):
