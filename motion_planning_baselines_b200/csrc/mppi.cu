@@ -41,11 +41,12 @@ struct MppiArgs {
     int N, T, C, sd;
     float dt, discount, w_pos, w_ctrl, w_posT;
     int l_in_smem;
+    int tp;                // row pitch of the staged factors in floats (T + 4 when T % 4 == 0: 16-byte rows, else T + 1)
 };
 
 __global__ void __launch_bounds__(kMppiWarps * 32) mppi_rollout_kernel(const __grid_constant__ MppiArgs a) {
     extern __shared__ __align__(16) float sm[];
-    const int T = a.T, C = a.C, sd = a.sd, W = sd + C, TP = T + 1;
+    const int T = a.T, C = a.C, sd = a.sd, W = sd + C, TP = a.tp;
     // shared layout: v[C][T] (Cov_inv_i @ mean_i) | disc[T] | per-warp: es[C][T], us[T][C], xs[T][sd] | L[C][T][T+1] (optional)
     float* vs = sm;
     float* disc = vs + C * T;
@@ -98,6 +99,44 @@ __global__ void __launch_bounds__(kMppiWarps * 32) mppi_rollout_kernel(const __g
         }
         __syncwarp();
         // U[t,i] = mean[t,i] + sum_{k<=t} L_i[t,k] eps_i[k]
+        if (T == 64 && a.l_in_smem && TP == 68) {
+            // lane l owns rows l and 63 - l: together 65 factor entries whatever l is, so the triangular work is balanced
+            // across the lanes (rows l and l + 32 made the warp run 32 + 64 iterations for 32.5 useful ones on average).
+            // 16-byte loads of the factor rows (pitch 68 floats: the eight lanes of a quarter-warp hit 32 distinct banks)
+            // and of the noise (one address per chunk: broadcast).  A chunk that crosses the diagonal multiplies the exact
+            // zeros torch's scale_tril holds above it: the sum is the ascending-k sum of the generic loop bit for bit.
+            const int ta = lane, tb = 63 - lane;
+            const int na = (ta >> 2) + 1, nb = (tb >> 2) + 1;           // 1..8 and 9..16 chunks of four
+            for (int i = 0; i < C; ++i) {
+                const float4* er4 = reinterpret_cast<const float4*>(es + i * T);
+                const float4* la4 = reinterpret_cast<const float4*>(Ls + ((size_t)i * T + ta) * TP);
+                const float4* lb4 = reinterpret_cast<const float4*>(Ls + ((size_t)i * T + tb) * TP);
+                float acc_a = 0.f, acc_b = 0.f;
+#pragma unroll 4
+                for (int c = 0; c < 8; ++c) {
+                    const float4 e = er4[c];
+                    const float4 lb = lb4[c];
+                    acc_b = fmaf(lb.x, e.x, acc_b); acc_b = fmaf(lb.y, e.y, acc_b);
+                    acc_b = fmaf(lb.z, e.z, acc_b); acc_b = fmaf(lb.w, e.w, acc_b);
+                    if (c < na) {
+                        const float4 la = la4[c];
+                        acc_a = fmaf(la.x, e.x, acc_a); acc_a = fmaf(la.y, e.y, acc_a);
+                        acc_a = fmaf(la.z, e.z, acc_a); acc_a = fmaf(la.w, e.w, acc_a);
+                    }
+                }
+#pragma unroll 4
+                for (int c = 8; c < 16; ++c) {
+                    if (c < nb) {
+                        const float4 e = er4[c];
+                        const float4 lb = lb4[c];
+                        acc_b = fmaf(lb.x, e.x, acc_b); acc_b = fmaf(lb.y, e.y, acc_b);
+                        acc_b = fmaf(lb.z, e.z, acc_b); acc_b = fmaf(lb.w, e.w, acc_b);
+                    }
+                }
+                us[ta * C + i] = __ldg(a.mean_s + (size_t)ta * C + i) + acc_a;
+                us[tb * C + i] = __ldg(a.mean_s + (size_t)tb * C + i) + acc_b;
+            }
+        } else
         for (int t = lane; t < T; t += 32) {
             for (int i = 0; i < C; ++i) {
                 float acc = 0.f;
@@ -207,7 +246,8 @@ extern "C" int mpb_mppi_rollout_ex(const float* L_ctrl, const float* Cov_inv, co
     a.ctrl_min = ctrl_min; a.ctrl_max = ctrl_max; a.xu = xu; a.quad = quad; a.isv = isv;
     a.N = N; a.T = T; a.C = C; a.sd = sd; a.dt = dt; a.discount = discount; a.w_pos = w_pos; a.w_ctrl = w_ctrl; a.w_posT = w_posT;
     const size_t base = (size_t)(C * T + T + kMppiWarps * (C * T + T * C + T * sd)) * sizeof(float);
-    const size_t lbytes = (size_t)C * T * (T + 1) * sizeof(float);
+    a.tp = (T % 4 == 0) ? T + 4 : T + 1;
+    const size_t lbytes = (size_t)C * T * a.tp * sizeof(float);
     // L in shared memory when two CTAs still fit per SM (or when it fits at all); else it is read through L1
     a.l_in_smem = (base + lbytes <= 200 * 1024) ? 1 : 0;
     const size_t smem = base + (a.l_in_smem ? lbytes : 0);
