@@ -157,7 +157,18 @@ __global__ void __launch_bounds__(kMppiWarps * 32) mppi_rollout_kernel(const __g
             float xj = __ldg(a.state0 + j);
             const float lo = __ldg(a.ctrl_min + j), hi = __ldg(a.ctrl_max + j);
             xs[j] = xj;
-            for (int t = 0; t + 1 < T; ++t) {
+            int t = 0;
+            for (; t + 8 < T; t += 8) {             // eight increments fetched before the dependent adds (the stores to xs
+                float du[8];                        // would otherwise order every load of us behind them)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) du[q] = __fmul_rn(fminf(fmaxf(us[(t + q) * C + j], lo), hi), a.dt);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    xj = __fadd_rn(xj, du[q]);
+                    xs[(t + q + 1) * sd + j] = xj;
+                }
+            }
+            for (; t + 1 < T; ++t) {
                 const float u = fminf(fmaxf(us[t * C + j], lo), hi);
                 xj = __fadd_rn(xj, __fmul_rn(u, a.dt));
                 xs[(t + 1) * sd + j] = xj;
