@@ -35,7 +35,9 @@ __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
     __shared__ float red[32];
     const int M = H * D;
     float* ws = sm;                    // [S] weights of this particle
-    float* gs = sm + ((S + 3) & ~3);   // [M] weighted mean (only when SigmaR)
+    int* nzs = reinterpret_cast<int*>(sm + ((S + 3) & ~3));      // [S] indices of the samples with a non-zero weight, ascending
+    float* gs = sm + 2 * ((S + 3) & ~3);   // [M] weighted mean (only when SigmaR)
+    __shared__ int s_nnz;
     const int p = blockIdx.x;
     const float* cp = cost + (size_t)p * S;
 
@@ -60,6 +62,21 @@ __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
         weights[(size_t)p * S + s] = w;
     }
     __syncthreads();
+    // rows whose weight underflowed to exactly 0 are not fetched: list the others (ascending, so the sums keep their
+    // order); at T = 1 the weights are nearly one-hot and walking all S of them per column was most of the kernel
+    if (threadIdx.x < 32) {
+        int n = 0;
+        for (int s0 = 0; s0 < S; s0 += 32) {
+            const int s = s0 + (int)threadIdx.x;
+            const bool nz = s < S && ws[s] != 0.f;
+            const unsigned m = __ballot_sync(MPB_FULL_MASK, nz);
+            if (nz) nzs[n + __popc(m & ((1u << threadIdx.x) - 1u))] = s;
+            n += __popc(m);
+        }
+        if (threadIdx.x == 0) s_nnz = n;
+    }
+    __syncthreads();
+    const int nnz = s_nnz;
 
     // ---- phase 2: g = sum_s w_s (x_s - mu) ------------------------------------------------
     const float* xp = x + (size_t)p * S * M;
@@ -69,13 +86,12 @@ __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
         for (int c = threadIdx.x * 4; c < M; c += blockDim.x * 4) {
             const float4 m4 = *reinterpret_cast<const float4*>(mp + c);
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s = 0; s < S; ++s) {
+            for (int k = 0; k < nnz; ++k) {
+                const int s = nzs[k];
                 const float w = ws[s];
-                if (w != 0.f) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(xp + (size_t)s * M + c));
-                    g.x = fmaf(w, v.x - m4.x, g.x); g.y = fmaf(w, v.y - m4.y, g.y);
-                    g.z = fmaf(w, v.z - m4.z, g.z); g.w = fmaf(w, v.w - m4.w, g.w);
-                }
+                const float4 v = __ldg(reinterpret_cast<const float4*>(xp + (size_t)s * M + c));
+                g.x = fmaf(w, v.x - m4.x, g.x); g.y = fmaf(w, v.y - m4.y, g.y);
+                g.z = fmaf(w, v.z - m4.z, g.z); g.w = fmaf(w, v.w - m4.w, g.w);
             }
             if (grad) *reinterpret_cast<float4*>(grad + (size_t)p * M + c) = g;
             if (SigmaR) {
@@ -91,9 +107,9 @@ __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
         for (int c = threadIdx.x; c < M; c += blockDim.x) {
             const float m1 = mp[c];
             float g = 0.f;
-            for (int s = 0; s < S; ++s) {
-                const float w = ws[s];
-                if (w != 0.f) g = fmaf(w, __ldg(xp + (size_t)s * M + c) - m1, g);
+            for (int k = 0; k < nnz; ++k) {
+                const int s = nzs[k];
+                g = fmaf(ws[s], __ldg(xp + (size_t)s * M + c) - m1, g);
             }
             if (grad) grad[(size_t)p * M + c] = g;
             if (SigmaR) gs[c] = g; else mp[c] = fmaf(step, g, m1);
@@ -121,7 +137,7 @@ extern "C" int mpb_softmax_update(const float* cost, const float* x, float* mu, 
     MPB_REQUIRE(P >= 0 && S >= 1 && H >= 1 && D >= 1, "mpb_softmax_update: bad sizes");
     MPB_REQUIRE(temp > 0.f, "mpb_softmax_update: temperature must be positive");
     if (P == 0) return MPB_OK;
-    const size_t smem = ((size_t)((S + 3) & ~3) + (SigmaR ? (size_t)H * D : 0)) * sizeof(float);
+    const size_t smem = (2 * (size_t)((S + 3) & ~3) + (SigmaR ? (size_t)H * D : 0)) * sizeof(float);
     MPB_REQUIRE(smem <= 200 * 1024, "mpb_softmax_update: S=%d too large for the single-CTA path", S);
     cudaError_t e = cudaFuncSetAttribute(softmax_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("mpb_softmax_update: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
