@@ -416,6 +416,9 @@ inline unsigned layout_robot(const mpb_robot_desc& r, RobotLayout& l, unsigned b
     return (p + 15u) & ~15u;
 }
 
+// Called by ALL threads of the CTA (contains a barrier).  Phase A copies the raw tables to shared memory in one global
+// round trip; phase B derives the rotation patterns and the per-link bounding spheres from shared memory (deriving them
+// from global memory cost three to four more dependent round trips at the start of every CTA).
 __device__ __forceinline__ void stage_robot(const mpb_robot_desc& r, const RobotLayout& l, unsigned char* smem) {
     float4* sp = reinterpret_cast<float4*>(smem + l.sphere);
     float* tf = reinterpret_cast<float*>(smem + l.tf);
@@ -425,8 +428,9 @@ __device__ __forceinline__ void stage_robot(const mpb_robot_desc& r, const Robot
         lk[s] = r.sphere_link[s];
     }
     for (int i = threadIdx.x; i < r.q_dim * 12; i += blockDim.x) tf[i] = r.fixed_tf[i];
+    __syncthreads();
     for (int j = threadIdx.x; j < r.q_dim; j += blockDim.x) {
-        const float* F = r.fixed_tf + j * 12;       // row-major 3x4
+        const float* F = tf + j * 12;               // row-major 3x4
         int pat = MPB_TF_GENERAL;
         if (F[0] == 1.f && F[1] == 0.f && F[2] == 0.f && F[4] == 0.f && F[8] == 0.f) {
             if (F[5] == 1.f && F[6] == 0.f && F[9] == 0.f && F[10] == 1.f) pat = MPB_TF_IDENTITY;
@@ -435,15 +439,15 @@ __device__ __forceinline__ void stage_robot(const mpb_robot_desc& r, const Robot
         }
         reinterpret_cast<int*>(smem + l.pat)[j] = pat;
     }
-    // per-link bounding spheres: warp w handles links w, w+nwarps, ... with lanes over the sphere table, so the
-    // global-memory round trips overlap instead of forming one long dependent chain per link
+    // per-link bounding spheres: warp w handles links w, w+nwarps, ... with lanes over the sphere table
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
     for (int j = wid; j < r.q_dim; j += nwarp) {
         float mx = 0.f, my = 0.f, mz = 0.f;
         int n = 0, end = 0;
         for (int s = lane; s < r.n_spheres; s += 32) {
-            const int ls = r.sphere_link[s];
-            if (ls == j) { mx += r.sphere_off[3 * s]; my += r.sphere_off[3 * s + 1]; mz += r.sphere_off[3 * s + 2]; ++n; }
+            const int ls = lk[s];
+            const float4 o = sp[s];
+            if (ls == j) { mx += o.x; my += o.y; mz += o.z; ++n; }
             if (ls <= j) end = max(end, s + 1);
         }
         mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
@@ -453,9 +457,10 @@ __device__ __forceinline__ void stage_robot(const mpb_robot_desc& r, const Robot
         if (n > 0) {
             mx /= n; my /= n; mz /= n;
             for (int s = lane; s < r.n_spheres; s += 32) {
-                if (r.sphere_link[s] != j) continue;
-                const float dx = r.sphere_off[3 * s] - mx, dy = r.sphere_off[3 * s + 1] - my, dz = r.sphere_off[3 * s + 2] - mz;
-                R = fmaxf(R, sqrtf(dx * dx + dy * dy + dz * dz) + r.sphere_r[s]);
+                if (lk[s] != j) continue;
+                const float4 o = sp[s];
+                const float dx = o.x - mx, dy = o.y - my, dz = o.z - mz;
+                R = fmaxf(R, sqrtf(dx * dx + dy * dy + dz * dz) + o.w);
             }
             R = warp_max(R);
         }
