@@ -216,9 +216,9 @@ int mpb_sample_gp_kron_gen(const void* Limg, const float* mu, const mpb_noise_de
 /* The same launch with one more warp per CTA that computes y[p] = Sigma_inv @ mu[p] (the vector of the importance-sampling
  * term, stoch_gpmp.py:239-241) while the tiles run: bit-identical to mpb_prior_matvec_dof, without its launch.  Sigma_inv
  * must have the per-dof structure mpb_prior_dof_structured verifies; Sigma_inv and y are both NULL (plain sampler) or
- * both given. */
+ * both given.  mu_copy (optional, needs y): a copy of mu written by the same warp -- the planner's pre-update means. */
 int mpb_sample_gp_kron_gen_mv(const void* Limg, const float* mu, const mpb_noise_desc* noise, float* x, int P, int S, int H,
-                              int dof, const float* Sigma_inv, float* y, void* stream);
+                              int dof, const float* Sigma_inv, float* y, float* mu_copy, void* stream);
 
 /* tcgen05 variant of the structured sampler (csrc/sample_gp_tc.cu, sample_gp_kron_umma_kernel): TMA -> per-dof
  * gather + 3xTF32 split into tensor memory -> one M128 x N32 tcgen05.mma chain per dof with TMEM accumulators -> dofs
@@ -293,6 +293,11 @@ int mpb_smoothness_cost(const float* x, const float* R, float* out, int B, int H
 int mpb_softmax_update(const float* cost, const float* x, float* mu, float* weights, float* grad,
                        float temp, float step, const float* SigmaR,
                        int P, int S, int H, int D, void* stream);
+/* The same update that also writes the new means to mu_copy [P, H*D] (optional): the clone StochGPMP.optimize returns
+ * (stoch_gpmp.py:309) without a device copy of its own. */
+int mpb_softmax_update_ex(const float* cost, const float* x, float* mu, float* weights, float* grad,
+                          float temp, float step, const float* SigmaR, float* mu_copy, int P, int S, int H, int D,
+                          void* stream);
 
 /* One fused Stoch-GPMP iteration = sample_gp -> prior_matvec -> cost_eval(+IS) -> softmax_update.
  * Replaces the body of StochGPMP.optimize (stoch_gpmp.py:291-299).
@@ -322,6 +327,14 @@ int mpb_stoch_gpmp_iter_kron_gen(const void* L_kron_gen, const float* Sigma_inv,
                                  float* is_vec, uint8_t* free_flag, int P, int S, int H, const mpb_robot_desc* robot,
                                  const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp, float temp, float step,
                                  void* stream);
+/* ... with mu_prev [P, H*D] (the pre-update means, written by K1's mat-vec warp) and mu_out [P, H*D] (the updated means,
+ * written by K3) as side outputs, either may be NULL: the two copies of the particle means the reference API implies
+ * (`_recent_*_particles`, the clone optimize() returns: stoch_gpmp.py:300-309) cost no launches of their own. */
+int mpb_stoch_gpmp_iter_kron_gen_ex(const void* L_kron_gen, const float* Sigma_inv, int sigma_inv_structured,
+                                    const mpb_noise_desc* noise, float* mu, float* x, float* cost, float* weights,
+                                    float* is_vec, uint8_t* free_flag, float* mu_prev, float* mu_out, int P, int S, int H,
+                                    const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
+                                    const mpb_gp_desc* gp, float temp, float step, void* stream);
 /* STOMP, n_iters iterations from one call (stomp.py:137-160): mpb_sample_stomp_rng (draw counter noise->offset + it),
  * mpb_cost_eval, mpb_softmax_update with Sigma_R -- for the launch-latency-bound small configurations.  The caller
  * advances its draw counter by n_iters. */

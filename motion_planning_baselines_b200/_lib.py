@@ -82,13 +82,15 @@ _SIGNATURES = {
                                                C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc), _f, _f, _vp]),
     'mpb_stoch_gpmp_iter_kron_gen': (C.c_int, [_vp, _vp, _i, C.POINTER(NoiseDesc), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                                C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc), _f, _f, _vp]),
+    'mpb_stoch_gpmp_iter_kron_gen_ex': (C.c_int, [_vp, _vp, _i, C.POINTER(NoiseDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                                  C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc), _f, _f, _vp]),
     'mpb_stomp_run': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(RobotDesc),
                                 C.POINTER(FieldDesc), _i, C.POINTER(GPDesc), _f, _f, _i, _vp]),
     'mpb_sample_gp_kron_gen_supported': (C.c_int, [_i, _i]),
     'mpb_sample_gp_kron_gen_bytes': (C.c_longlong, [_i, _i]),
     'mpb_sample_gp_kron_gen_prepare': (C.c_int, [_vp, _vp, _i, _i, _vp]),
     'mpb_sample_gp_kron_gen': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _i, _i, _i, _i, _vp]),
-    'mpb_sample_gp_kron_gen_mv': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'mpb_sample_gp_kron_gen_mv': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'mpb_mppi_rollout_ex': (C.c_int, [_vp] * 5 + [C.POINTER(NoiseDesc)] + [_vp] * 7 + [_i, _i, _i, _i, _f, _f, _f, _f, _f, _vp]),
     'mpb_prior_matvec': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'mpb_cost_eval': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
@@ -97,6 +99,7 @@ _SIGNATURES = {
                                    _vp, _i, _f, _vp, _vp, _vp, C.POINTER(ExtraCostDesc), _vp, _vp]),
     'mpb_smoothness_cost': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'mpb_softmax_update': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _vp]),
+    'mpb_softmax_update_ex': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
     'mpb_stoch_gpmp_iter': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                       C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
                                       _f, _f, _vp]),

@@ -157,13 +157,30 @@ extern "C" int mpb_stoch_gpmp_iter_kron_gen(const void* L_kron_gen, const float*
                                             float* is_vec, uint8_t* free_flag, int P, int S, int H, const mpb_robot_desc* robot,
                                             const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp, float temp,
                                             float step, void* stream) {
+    return mpb_stoch_gpmp_iter_kron_gen_ex(L_kron_gen, Sigma_inv, sigma_inv_structured, noise, mu, x, cost, weights, is_vec, free_flag,
+                                           nullptr, nullptr, P, S, H, robot, fields, n_fields, gp, temp, step, stream);
+}
+
+// ... with the two copies of the particle means the reference API implies written by the kernels that touch the means
+// anyway: mu_prev (the pre-update means, `_recent_*_particles` of stoch_gpmp.py:300-306) by K1's mat-vec warp, mu_out (the
+// clone optimize() returns, stoch_gpmp.py:309) by K3 -- instead of two extra device copies per call.  Either may be NULL.
+extern "C" int mpb_stoch_gpmp_iter_kron_gen_ex(const void* L_kron_gen, const float* Sigma_inv, int sigma_inv_structured,
+                                               const mpb_noise_desc* noise, float* mu, float* x, float* cost, float* weights,
+                                               float* is_vec, uint8_t* free_flag, float* mu_prev, float* mu_out, int P, int S, int H,
+                                               const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
+                                               const mpb_gp_desc* gp, float temp, float step, void* stream) {
     MPB_REQUIRE(robot && L_kron_gen && noise, "mpb_stoch_gpmp_iter_kron_gen: null robot / factor / noise descriptor");
     const int D = 2 * robot->q_dim, M = H * D;
     int rc;
     if (sigma_inv_structured) {      // Sigma^-1 mu rides along in K1 (one extra warp per CTA): no mat-vec launch
-        rc = mpb_sample_gp_kron_gen_mv(L_kron_gen, mu, noise, x, P, S, H, robot->q_dim, Sigma_inv, is_vec, stream);
+        rc = mpb_sample_gp_kron_gen_mv(L_kron_gen, mu, noise, x, P, S, H, robot->q_dim, Sigma_inv, is_vec, mu_prev, stream);
         if (rc) return rc;
     } else {
+        if (mu_prev) {
+            const cudaError_t e = cudaMemcpyAsync(mu_prev, mu, (size_t)P * M * sizeof(float), cudaMemcpyDeviceToDevice,
+                                                  static_cast<cudaStream_t>(stream));
+            MPB_REQUIRE(e == cudaSuccess, "mpb_stoch_gpmp_iter_kron_gen: %s", cudaGetErrorString(e));
+        }
         rc = mpb_sample_gp_kron_gen(L_kron_gen, mu, noise, x, P, S, H, robot->q_dim, stream);
         if (rc) return rc;
         rc = mpb_prior_matvec(Sigma_inv, mu, is_vec, P, M, 2 * D - 1, stream);
@@ -171,7 +188,7 @@ extern "C" int mpb_stoch_gpmp_iter_kron_gen(const void* L_kron_gen, const float*
     }
     rc = mpb_cost_eval(x, P * S, H, robot, fields, n_fields, gp, is_vec, S, temp, cost, nullptr, free_flag, stream);
     if (rc) return rc;
-    return mpb_softmax_update(cost, x, mu, weights, nullptr, temp, step, nullptr, P, S, H, D, stream);
+    return mpb_softmax_update_ex(cost, x, mu, weights, nullptr, temp, step, nullptr, mu_out, P, S, H, D, stream);
 }
 
 // STOMP: `n_iters` whole iterations (stomp.py:137-160: sample -> cost -> importance-weighted update) enqueued from ONE

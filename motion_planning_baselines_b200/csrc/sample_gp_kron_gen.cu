@@ -85,6 +85,7 @@ struct GenArgs {
     int ntiles;
     const float* Sinv;              // optional [M, M] prior precision with the per-dof structure (mpb_prior_dof_structured)
     float* y;                       // optional [P, M]: y[p] = Sinv @ mu[p], computed by warp MV_WARP while the tiles run
+    float* mu_copy;                 // optional [P, M]: copy of mu written by the same warp (the planner's pre-update means)
     long long* trace;               // optional [64] clock stamps of CTA 0 (MPB_KRON_GEN_TRACE = device pointer; timing experiments)
     int dbg;                        // MPB_KRON_GEN_DBG bit mask (timing experiments only): 1 no Philox (zeros), 2 no MMAs,
                                     // 4 no output stores, 8 no factor loads, 128 no epilogue TMEM loads, 256 no epilogue smem writes
@@ -420,7 +421,10 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                         lo = __fadd_rn(lo, __fadd_rn(__fadd_rn(__fsub_rn(hi, __fsub_rn(t, z)), __fsub_rn(pr, z)), e));
                         hi = t;
                     }
-                    if (q < np) a.y[(size_t)(pb + q * gridDim.x) * C::M + i] = __fadd_rn(hi, lo);
+                    if (q < np) {
+                        a.y[(size_t)(pb + q * gridDim.x) * C::M + i] = __fadd_rn(hi, lo);
+                        if (a.mu_copy) a.mu_copy[(size_t)(pb + q * gridDim.x) * C::M + i] = mv[q][3];      // mv[q][3] = mu[p][i]
+                    }
                 }
             }
         }
@@ -487,14 +491,15 @@ extern "C" int mpb_sample_gp_kron_gen_prepare(const float* LkT, void* Limg, int 
 
 extern "C" int mpb_sample_gp_kron_gen(const void* Limg, const float* mu, const mpb_noise_desc* nd, float* x, int P, int S, int H,
                                       int dof, void* stream) {
-    return mpb_sample_gp_kron_gen_mv(Limg, mu, nd, x, P, S, H, dof, nullptr, nullptr, stream);
+    return mpb_sample_gp_kron_gen_mv(Limg, mu, nd, x, P, S, H, dof, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int mpb_sample_gp_kron_gen_mv(const void* Limg, const float* mu, const mpb_noise_desc* nd, float* x, int P, int S, int H,
-                                         int dof, const float* Sigma_inv, float* y, void* stream) {
+                                         int dof, const float* Sigma_inv, float* y, float* mu_copy, void* stream) {
     using namespace mpb;
     MPB_REQUIRE(Limg && mu && nd && x, "mpb_sample_gp_kron_gen: null pointer");
     MPB_REQUIRE((Sigma_inv == nullptr) == (y == nullptr), "mpb_sample_gp_kron_gen_mv: Sigma_inv and y go together");
+    MPB_REQUIRE(!mu_copy || y, "mpb_sample_gp_kron_gen_mv: mu_copy needs the mat-vec warp (Sigma_inv, y)");
     MPB_REQUIRE(P >= 0 && S >= 0, "mpb_sample_gp_kron_gen: bad sizes P=%d S=%d", P, S);
     MPB_REQUIRE(mpb_sample_gp_kron_gen_supported(H, dof), "mpb_sample_gp_kron_gen: shape H=%d dof=%d not supported", H, dof);
     MPB_REQUIRE(((uintptr_t)Limg | (uintptr_t)mu | (uintptr_t)x) % 16 == 0, "mpb_sample_gp_kron_gen: pointers must be 16-byte aligned");
@@ -506,7 +511,7 @@ extern "C" int mpb_sample_gp_kron_gen_mv(const void* Limg, const float* mu, cons
     MPB_REQUIRE(!why, "mpb_sample_gp_kron_gen: %s", why);
     a.Limg = static_cast<const unsigned char*>(Limg);
     a.mu = mu; a.x = x; a.P = P; a.S = S;
-    a.Sinv = Sigma_inv; a.y = y;
+    a.Sinv = Sigma_inv; a.y = y; a.mu_copy = mu_copy;
     a.Ntot = (long long)P * S;
     // MPB_KRON_GEN_TS=64: the one-accumulator-set variant (A/B timing); default: 32-sample tiles, two sets
     int ts = 32;

@@ -30,7 +30,8 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 
 __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
     const float* __restrict__ cost, const float* __restrict__ x, float* __restrict__ mu, float* __restrict__ weights,
-    float* __restrict__ grad, float temp, float step, const float* __restrict__ SigmaR, int S, int H, int D) {
+    float* __restrict__ grad, float temp, float step, const float* __restrict__ SigmaR, float* __restrict__ mu_copy, int S, int H,
+    int D) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float red[32];
     const int M = H * D;
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
                 o.x = fmaf(step, g.x, m4.x); o.y = fmaf(step, g.y, m4.y);
                 o.z = fmaf(step, g.z, m4.z); o.w = fmaf(step, g.w, m4.w);
                 *reinterpret_cast<float4*>(mp + c) = o;
+                if (mu_copy) *reinterpret_cast<float4*>(mu_copy + (size_t)p * M + c) = o;
             }
         }
     } else {
@@ -112,7 +114,12 @@ __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
                 g = fmaf(ws[s], __ldg(xp + (size_t)s * M + c) - m1, g);
             }
             if (grad) grad[(size_t)p * M + c] = g;
-            if (SigmaR) gs[c] = g; else mp[c] = fmaf(step, g, m1);
+            if (SigmaR) gs[c] = g;
+            else {
+                const float o = fmaf(step, g, m1);
+                mp[c] = o;
+                if (mu_copy) mu_copy[(size_t)p * M + c] = o;
+            }
         }
     }
     if (SigmaR) {       // STOMP: mu[h,j] += step * sum_k SigmaR[h,k] g[k,j]
@@ -122,7 +129,9 @@ __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
             const float* srow = SigmaR + (size_t)h * H;
             float acc = 0.f;
             for (int k = 0; k < H; ++k) acc = fmaf(__ldg(srow + k), gs[k * D + j], acc);
-            mp[o] = fmaf(step, acc, mp[o]);
+            const float v = fmaf(step, acc, mp[o]);
+            mp[o] = v;
+            if (mu_copy) mu_copy[(size_t)p * M + o] = v;
         }
     }
 }
@@ -132,6 +141,12 @@ __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
 extern "C" int mpb_softmax_update(const float* cost, const float* x, float* mu, float* weights, float* grad,
                                   float temp, float step, const float* SigmaR, int P, int S, int H, int D,
                                   void* stream) {
+    return mpb_softmax_update_ex(cost, x, mu, weights, grad, temp, step, SigmaR, nullptr, P, S, H, D, stream);
+}
+
+extern "C" int mpb_softmax_update_ex(const float* cost, const float* x, float* mu, float* weights, float* grad,
+                                     float temp, float step, const float* SigmaR, float* mu_copy, int P, int S, int H, int D,
+                                     void* stream) {
     using namespace mpb;
     MPB_REQUIRE(cost && x && mu && weights, "mpb_softmax_update: null pointer");
     MPB_REQUIRE(P >= 0 && S >= 1 && H >= 1 && D >= 1, "mpb_softmax_update: bad sizes");
@@ -142,6 +157,6 @@ extern "C" int mpb_softmax_update(const float* cost, const float* x, float* mu, 
     cudaError_t e = cudaFuncSetAttribute(softmax_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("mpb_softmax_update: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
     softmax_update_kernel<<<P, kUpdThreads, smem, static_cast<cudaStream_t>(stream)>>>(cost, x, mu, weights, grad, temp,
-                                                                                      step, SigmaR, S, H, D);
+                                                                                      step, SigmaR, mu_copy, S, H, D);
     return check_launch("mpb_softmax_update");
 }

@@ -184,17 +184,25 @@ class StochGPMP(OptimizationPlanner):
         lib = _lib.lib()
         pos_mean = vel_mean = None
         sd = self._sample_dist
+        traj_out = None
         for it in range(opt_iters):
-            if it == opt_iters - 1:     # the reference returns the pre-update particle means of the last iteration
-                pre = self._particle_means.clone()          # one private copy; the two halves are views of it
-                pos_mean, vel_mean = pre[..., :self.n_dof], pre[..., -self.n_dof:]
+            last = it == opt_iters - 1
+            gen_path = eps is None and sd.scale_tril_kron_gen is not None
+            if last:                    # the reference returns the pre-update particle means of the last iteration
+                # default path: the kernels that touch the means anyway write both copies the reference API implies (the
+                # pre-update means: K1's mat-vec warp; the returned clone: K3) -- no device copies of their own
+                pre = torch.empty_like(self._particle_means) if gen_path else self._particle_means.clone()
+                pos_mean, vel_mean = pre[..., :self.n_dof], pre[..., -self.n_dof:]       # the two halves are views of it
             if eps is None:
                 nd = self._noise.next()
                 if sd.scale_tril_kron_gen is not None:      # default: Blackwell sampler, noise drawn inside K1
-                    _lib.check(lib.mpb_stoch_gpmp_iter_kron_gen(
+                    if last:
+                        traj_out = torch.empty_like(self._particle_means)
+                    _lib.check(lib.mpb_stoch_gpmp_iter_kron_gen_ex(
                         _lib.ptr(sd.scale_tril_kron_gen), _lib.ptr(self.Sigma_inv), int(self._sinv_structured), C.byref(nd),
                         _lib.ptr(self._particle_means), _lib.ptr(self.state_samples), _lib.ptr(self.costs), _lib.ptr(self._w_buf),
-                        _lib.ptr(self._is_vec), _lib.ptr(self.free_flags), P, S, H,
+                        _lib.ptr(self._is_vec), _lib.ptr(self.free_flags), _lib.ptr(pre) if last else None,
+                        _lib.ptr(traj_out) if last else None, P, S, H,
                         C.byref(self.robot.desc), fields, nf, C.byref(gp), self.temperature, self.step_size, _lib.stream_ptr()))
                     continue
                 if sd.kron_tc_kind == 1:        # warp-MMA sampler, noise drawn inside K1
@@ -230,7 +238,7 @@ class StochGPMP(OptimizationPlanner):
         self._recent_control_particles = vel_mean
         self._recent_state_particles = pos_mean
         self._recent_weights = self._weights
-        return self._get_traj()
+        return traj_out if traj_out is not None else self._get_traj()
 
     def _optimize_staged(self, opt_iters, eps=None, **observation):
         """optimize() through sample_and_eval + _update_distribution (composites with extra cost terms)."""
@@ -262,7 +270,7 @@ class StochGPMP(OptimizationPlanner):
             nd = self._sample_dist.noise.next()
             _lib.check(lib.mpb_sample_gp_kron_gen_mv(_lib.ptr(self._sample_dist.scale_tril_kron_gen), _lib.ptr(self._particle_means),
                                                      C.byref(nd), _lib.ptr(self.state_samples), P, S, H, self.n_dof,
-                                                     _lib.ptr(self.Sigma_inv), _lib.ptr(self._is_vec), st))
+                                                     _lib.ptr(self.Sigma_inv), _lib.ptr(self._is_vec), None, st))
             mv_fused = True
         elif eps is None:
             self._sample_dist.means = self._particle_means.view(P, -1)

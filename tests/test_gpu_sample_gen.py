@@ -116,11 +116,13 @@ def test_gen_sampler_with_prior_matvec_warp(P, S, dev):
     _lib.check(lib.mpb_prior_matvec_dof(_lib.ptr(Sinv), _lib.ptr(means), _lib.ptr(y_ref), P, 64, 7, _lib.stream_ptr()))
     x1 = torch.empty_like(x0)
     y = torch.full((P, 64 * 14), float('nan'), **dev)
+    mu_c = torch.full((P, 64 * 14), float('nan'), **dev)
     _lib.check(lib.mpb_sample_gp_kron_gen_mv(_lib.ptr(prior.scale_tril_kron_gen), _lib.ptr(means.contiguous()), C.byref(desc),
-                                             _lib.ptr(x1), P, S, 64, 7, _lib.ptr(Sinv), _lib.ptr(y), _lib.stream_ptr()))
+                                             _lib.ptr(x1), P, S, 64, 7, _lib.ptr(Sinv), _lib.ptr(y), _lib.ptr(mu_c), _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert torch.equal(x1, x0)
     assert torch.equal(y, y_ref)
+    assert torch.equal(mu_c, means.view(P, -1)), 'the copy of the means written by the mat-vec warp'
     with pytest.raises(_lib.MpbError):
         _lib.check(lib.mpb_sample_gp_kron_gen_mv(_lib.ptr(prior.scale_tril_kron_gen), _lib.ptr(means), C.byref(desc), _lib.ptr(x1),
-                                                 P, S, 64, 7, _lib.ptr(Sinv), None, _lib.stream_ptr()))
+                                                 P, S, 64, 7, _lib.ptr(Sinv), None, None, _lib.stream_ptr()))
