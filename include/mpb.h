@@ -207,7 +207,8 @@ int mpb_sample_gp_kron_tc(const void* LkF, const float* mu, const float* eps, fl
  * stores.  Replaces MultiMPPrior.sample (mp_priors_multi.py:253-256) INCLUDING torch's noise draw.
  *   mpb_sample_gp_kron_gen_prepare : LkT (from mpb_sample_gp_kron_pack) -> Limg, mpb_sample_gp_kron_gen_bytes(H, dof) bytes,
  *                                    16-byte aligned; one-off setup, stream-ordered.
- * Same numbers as mpb_philox_normal(MPB_NOISE_SPMD) + mpb_sample_gp_kron_tc up to the fp32 accumulation order. */
+ * Same numbers as mpb_philox_normal(MPB_NOISE_SPMD) + mpb_sample_gp_kron_tc up to the fp32 accumulation order.
+ * Supported: H = 64 (2H = 128 rows = the MMA's M) with 2..7 dofs. */
 int mpb_sample_gp_kron_gen_supported(int H, int dof);
 long long mpb_sample_gp_kron_gen_bytes(int H, int dof);
 int mpb_sample_gp_kron_gen_prepare(const float* LkT, void* Limg, int H, int dof, void* stream);

@@ -466,7 +466,31 @@ __global__ void kron_gen_max_kernel(const float* __restrict__ LkT, unsigned* __r
 
 }  // namespace mpb
 
-extern "C" int mpb_sample_gp_kron_gen_supported(int H, int dof) { return (H == 64 && dof == 7) ? 1 : 0; }
+// H = 64 (2H = 128 = the UMMA M) and 2..7 dofs: two accumulator sets of dof x 32 columns fit tensor memory up to 8 dofs, the
+// shared-memory rings (32 KiB per dof) up to 7
+extern "C" int mpb_sample_gp_kron_gen_supported(int H, int dof) { return (H == 64 && dof >= 2 && dof <= 7) ? 1 : 0; }
+
+namespace mpb {
+template <int DOF>
+static cudaError_t launch_kron_gen(GenArgs& a, const NoiseArgs& noise, int ts, cudaStream_t st) {
+    using C = GenCfg<DOF, 32>;
+    a.ntiles = (int)((a.Ntot + ts - 1) / ts);
+    const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();     // >= 1: the mat-vec warp strides the particles by the grid
+    if (DOF == 7 && ts == 64) {         // the one-accumulator-set variant is kept for the 7-dof arm only (A/B timing)
+        using C64 = GenCfg<7, 64>;
+        auto kern = sample_gp_kron_gen_kernel<7, 64>;
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C64::SMEM);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, C64::THREADS, C64::SMEM, st>>>(a, noise);
+        return cudaSuccess;
+    }
+    auto kern = sample_gp_kron_gen_kernel<DOF, 32>;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, C::THREADS, C::SMEM, st>>>(a, noise);
+    return cudaSuccess;
+}
+}  // namespace mpb
 
 extern "C" long long mpb_sample_gp_kron_gen_bytes(int H, int dof) {
     return (long long)dof * 2 * (2 * H) * (2 * H) * 2 + 64 * 4;       // fp16 hi + lo image, inverse scales (16 words), scratch
@@ -504,7 +528,6 @@ extern "C" int mpb_sample_gp_kron_gen_mv(const void* Limg, const float* mu, cons
     MPB_REQUIRE(mpb_sample_gp_kron_gen_supported(H, dof), "mpb_sample_gp_kron_gen: shape H=%d dof=%d not supported", H, dof);
     MPB_REQUIRE(((uintptr_t)Limg | (uintptr_t)mu | (uintptr_t)x) % 16 == 0, "mpb_sample_gp_kron_gen: pointers must be 16-byte aligned");
     if (P == 0 || S == 0) return MPB_OK;
-    using C = GenCfg<7, 64>;
     GenArgs a{};
     NoiseArgs noise{};
     const char* why = noise_args(*nd, P, noise);
@@ -513,17 +536,21 @@ extern "C" int mpb_sample_gp_kron_gen_mv(const void* Limg, const float* mu, cons
     a.mu = mu; a.x = x; a.P = P; a.S = S;
     a.Sinv = Sigma_inv; a.y = y; a.mu_copy = mu_copy;
     a.Ntot = (long long)P * S;
-    // MPB_KRON_GEN_TS=64: the one-accumulator-set variant (A/B timing); default: 32-sample tiles, two sets
+    // MPB_KRON_GEN_TS=64: the one-accumulator-set variant (A/B timing, 7 dofs); default: 32-sample tiles, two sets
     int ts = 32;
-    { const char* v = getenv("MPB_KRON_GEN_TS"); if (v && atoi(v) == 64) ts = 64; }
-    a.ntiles = (int)((a.Ntot + ts - 1) / ts);
+    { const char* v = getenv("MPB_KRON_GEN_TS"); if (v && atoi(v) == 64 && dof == 7) ts = 64; }
     { const char* v = getenv("MPB_KRON_GEN_DBG"); a.dbg = v ? atoi(v) : 0; }
     { const char* v = getenv("MPB_KRON_GEN_TRACE"); a.trace = v ? reinterpret_cast<long long*>(strtoull(v, nullptr, 0)) : nullptr; }
-    static_assert(GenCfg<7, 32>::SMEM == C::SMEM && GenCfg<7, 32>::THREADS == C::THREADS, "both variants share the launch shape");
-    auto kern = ts == 64 ? sample_gp_kron_gen_kernel<7, 64> : sample_gp_kron_gen_kernel<7, 32>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (dof) {
+        case 2: e = launch_kron_gen<2>(a, noise, ts, st); break;
+        case 3: e = launch_kron_gen<3>(a, noise, ts, st); break;
+        case 4: e = launch_kron_gen<4>(a, noise, ts, st); break;
+        case 5: e = launch_kron_gen<5>(a, noise, ts, st); break;
+        case 6: e = launch_kron_gen<6>(a, noise, ts, st); break;
+        case 7: e = launch_kron_gen<7>(a, noise, ts, st); break;
+    }
     if (e != cudaSuccess) { set_error("mpb_sample_gp_kron_gen: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
-    const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();     // >= 1: the mat-vec warp strides the particles by the grid
-    kern<<<grid, C::THREADS, C::SMEM, static_cast<cudaStream_t>(stream)>>>(a, noise);
     return check_launch("mpb_sample_gp_kron_gen");
 }

@@ -21,9 +21,9 @@ def nd(seed, offset, p_off=0, P_glob=1, s_off=0):
     return _lib.NoiseDesc(seed=seed, offset=offset, s_offset=s_off, p_offset=p_off, P_global=P_glob)
 
 
-def make_prior(P, dev, means=None, seed=0):
+def make_prior(P, dev, means=None, seed=0, d=7):
     from motion_planning_baselines_b200.factors import GPFactor, MultiMPPrior, UnaryFactor
-    d, H, dt = 7, 64, 5 / 64
+    H, dt = 64, 5 / 64
     K = UnaryFactor(2 * d, 1e-3, None, dev).K
     Q = GPFactor(d, 1e-1, dt, H - 1, dev).Q_inv[0]
     if means is None:
@@ -88,6 +88,7 @@ def test_gen_sampler_is_independent_of_the_sharding(dev):
 def test_gen_sampler_rejects_bad_arguments(dev):
     lib = _lib.lib()
     assert lib.mpb_sample_gp_kron_gen_supported(64, 7) == 1 and lib.mpb_sample_gp_kron_gen_supported(32, 7) == 0
+    assert lib.mpb_sample_gp_kron_gen_supported(64, 2) == 1 and lib.mpb_sample_gp_kron_gen_supported(64, 8) == 0
     prior, means = make_prior(2, dev)
     x = torch.empty(2, 4, prior.M, **dev)
     import ctypes as C
@@ -126,3 +127,34 @@ def test_gen_sampler_with_prior_matvec_warp(P, S, dev):
     with pytest.raises(_lib.MpbError):
         _lib.check(lib.mpb_sample_gp_kron_gen_mv(_lib.ptr(prior.scale_tril_kron_gen), _lib.ptr(means), C.byref(desc), _lib.ptr(x1),
                                                  P, S, 64, 7, _lib.ptr(Sinv), None, None, _lib.stream_ptr()))
+
+
+@pytest.mark.parametrize('d,P,S', [(2, 9, 64), (3, 256, 128), (4, 5, 24), (5, 3, 7), (6, 40, 64)])
+def test_gen_sampler_other_robots(d, P, S, dev):
+    """The tcgen05 sampler for 2..6 dofs at H = 64 (point robots, 6-dof arms): samples against fp64 on its own dumped noise,
+    the mat-vec warp's y and copy of the means bit-identical to mpb_prior_matvec_dof / the means, sharding-independent."""
+    import ctypes as C
+    prior, means = make_prior(P, dev, d=d)
+    assert prior.scale_tril_kron_gen is not None, f'the tcgen05 sampler must be the default at (H, dof) = (64, {d})'
+    lib = _lib.lib()
+    M = 64 * 2 * d
+    desc = nd(21, 3, p_off=1, P_glob=P + 2)
+    x = prior.sample(S, noise_desc=desc).clone()
+    eps = prior.replay_noise(desc, S)
+    ref = means.view(P, 1, -1).double() + torch.einsum('ik,spk->psi', prior.scale_tril.double(), eps.double())
+    amp = float((ref - means.view(P, 1, -1).double()).abs().max())
+    assert float((x.view(P, S, -1).double() - ref).abs().max()) / amp < 5e-6
+    Sinv = prior.Sigma_inv.contiguous()
+    y_ref = torch.empty(P, M, **dev)
+    _lib.check(lib.mpb_prior_matvec_dof(_lib.ptr(Sinv), _lib.ptr(means), _lib.ptr(y_ref), P, 64, d, _lib.stream_ptr()))
+    x1, y, mu_c = torch.empty_like(x), torch.full((P, M), float('nan'), **dev), torch.full((P, M), float('nan'), **dev)
+    _lib.check(lib.mpb_sample_gp_kron_gen_mv(_lib.ptr(prior.scale_tril_kron_gen), _lib.ptr(means.contiguous()), C.byref(desc),
+                                             _lib.ptr(x1), P, S, 64, d, _lib.ptr(Sinv), _lib.ptr(y), _lib.ptr(mu_c), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(x1, x) and torch.equal(y, y_ref) and torch.equal(mu_c, means.view(P, -1))
+    # the second half of the particles as its own "rank": same bits
+    h = P // 2
+    if h:
+        lo = make_prior(h, dev, means=means[:h].contiguous(), d=d)[0].sample(S, noise_desc=nd(21, 3, p_off=1, P_glob=P + 2))
+        hi = make_prior(P - h, dev, means=means[h:].contiguous(), d=d)[0].sample(S, noise_desc=nd(21, 3, p_off=1 + h, P_glob=P + 2))
+        assert torch.equal(torch.cat((lo, hi)), x)
