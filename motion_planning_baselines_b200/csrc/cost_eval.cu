@@ -559,9 +559,9 @@ static cudaError_t launch(const CostArgs& a, int blocks_needed, size_t smem, cud
 
 namespace mpb {
 
-template <int DOF, int NW, int MINB, bool BOXES>
+template <int DOF, int NW, int MINB, bool BOXES, bool SPH>
 static cudaError_t launch_chain2b(const CostArgs& a, size_t smem, cudaStream_t st) {
-    auto kern = cost_eval_chain2_kernel<DOF, NW, MINB, BOXES>;
+    auto kern = cost_eval_chain2_kernel<DOF, NW, MINB, BOXES, SPH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -579,8 +579,13 @@ static cudaError_t launch_chain2b(const CostArgs& a, size_t smem, cudaStream_t s
 template <int DOF, int NW, int MINB>
 static cudaError_t launch_chain2(const CostArgs& a, size_t smem, cudaStream_t st) {
     bool boxes = !a.k2_local;                 // MPB_K2_LOCAL=0 (A/B, tests): the instance with the world-frame cull
-    for (int i = 0; i < a.fields.n_fields; ++i) boxes = boxes || a.fields.f[i].n_boxes > 0;
-    return boxes ? launch_chain2b<DOF, NW, MINB, true>(a, smem, st) : launch_chain2b<DOF, NW, MINB, false>(a, smem, st);
+    bool spheres = !a.k2_local;
+    for (int i = 0; i < a.fields.n_fields; ++i) {
+        boxes = boxes || a.fields.f[i].n_boxes > 0;
+        spheres = spheres || a.fields.f[i].n_spheres > 0;
+    }
+    if (!boxes) return launch_chain2b<DOF, NW, MINB, false, true>(a, smem, st);
+    return spheres ? launch_chain2b<DOF, NW, MINB, true, true>(a, smem, st) : launch_chain2b<DOF, NW, MINB, true, false>(a, smem, st);
 }
 
 // MPB_COST_EVAL=generic forces the one-waypoint-per-lane kernel (A/B timing and the cross-check in the tests).
@@ -666,13 +671,17 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
     int cfg = 82;
     if (packed && robot->q_dim == 7) {
         // measured at C4 (profiles/r02_k2_cfg_sweep.txt): without box code the kernel fits 96 registers, and 2 CTAs x 10 warps
-        // (5 warps per scheduler) beat 2 x 8 at 116; the instance with box code spills at 96 and keeps 8 x 2
-        bool boxes = false;
-        for (int i = 0; i < n_fields; ++i) boxes = boxes || fields[i].n_boxes > 0;
+        // (5 warps per scheduler) beat 2 x 8 at 116; the mixed instance (boxes and spheres) spills at 96 and keeps 8 x 2
+        bool boxes = false, spheres = false;
+        for (int i = 0; i < n_fields; ++i) {
+            boxes = boxes || fields[i].n_boxes > 0;
+            spheres = spheres || fields[i].n_spheres > 0;
+        }
         const char* kl = getenv("MPB_K2_LOCAL");
-        if (kl && kl[0] == '0') boxes = true;
+        if (kl && kl[0] == '0') boxes = spheres = true;
         cfg = k2_cfg();
-        if (cfg == 0) cfg = boxes ? 82 : 102;
+        // box-only instance (C5, table + shelf; profiles/tools/c5_cfg.py): 6 x 3 at 96 registers is the best of 8x2 / 10x2 / 6x3
+        if (cfg == 0) cfg = boxes ? (spheres ? 82 : 63) : 102;
     }
     int nw = packed ? cfg / 10 : kWarps;
     if (nw != 4 && nw != 6 && nw != 8 && nw != 10 && nw != 12) nw = 8;
