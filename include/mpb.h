@@ -444,6 +444,15 @@ int mpb_mppi_rollout_ex(const float* L_ctrl, const float* Cov_inv, const float* 
                         const float* ctrl_min, const float* ctrl_max, float* xu, float* quad, float* isv,
                         int N, int T, int C, int sd, float dt, float discount, float w_pos, float w_ctrl, float w_posT,
                         void* stream);
+/* mpb_mppi_rollout_opt: flags = MPB_MPPI_SHARED_FACTOR promises that the C factors L_ctrl[i] are identical (the reference's
+ * `cov_prior_type='const_ctrl'` with one control_std: gaussian.py:271-333), so only L_ctrl[0] is staged in shared memory
+ * (17 KiB instead of 119 KiB at T = 64, C = 7) and twice as many warps are resident.  Same results bit for bit. */
+#define MPB_MPPI_SHARED_FACTOR 1
+int mpb_mppi_rollout_opt(const float* L_ctrl, const float* Cov_inv, const float* mean, const float* mean_sample,
+                         const float* eps, const mpb_noise_desc* noise, const float* state0, const float* goal,
+                         const float* ctrl_min, const float* ctrl_max, float* xu, float* quad, float* isv, int N,
+                         int T, int C, int sd, float dt, float discount, float w_pos, float w_ctrl, float w_posT,
+                         int flags, void* stream);
 /* cost[n] = (quad[n] + energy[0]) + temp*isv[n,0] + temp*isv[n,1] + ...; energy (device fp64 scalar | NULL) is the
  * obstacle cost SUMMED OVER THE BATCH, which the reference adds to every sample (point.py:196, quirk B2). */
 int mpb_mppi_finalize(const float* quad, const float* isv, const double* energy, float temp, float* cost,

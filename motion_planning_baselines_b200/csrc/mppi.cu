@@ -41,6 +41,7 @@ struct MppiArgs {
     int N, T, C, sd;
     float dt, discount, w_pos, w_ctrl, w_posT;
     int l_in_smem;
+    int l_shared;          // every control dimension has the same factor: only L[0] is staged (caller's promise, mpb_mppi_rollout_opt)
     int tp;                // row pitch of the staged factors in floats (T + 4 when T % 4 == 0: 16-byte rows, else T + 1)
 };
 
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(kMppiWarps * 32) mppi_rollout_kernel(const __g
         for (int t = 0; t < T; ++t) { disc[t] = dsc; dsc *= a.discount; }
     }
     if (a.l_in_smem)
-        for (int o = threadIdx.x; o < C * T * T; o += blockDim.x) {
+        for (int o = threadIdx.x; o < (a.l_shared ? 1 : C) * T * T; o += blockDim.x) {
             const int i = o / (T * T), r = (o / T) % T, k = o % T;
             Ls[((size_t)i * T + r) * TP + k] = __ldg(a.L + o);
         }
@@ -109,8 +110,9 @@ __global__ void __launch_bounds__(kMppiWarps * 32) mppi_rollout_kernel(const __g
             const int na = (ta >> 2) + 1, nb = (tb >> 2) + 1;           // 1..8 and 9..16 chunks of four
             for (int i = 0; i < C; ++i) {
                 const float4* er4 = reinterpret_cast<const float4*>(es + i * T);
-                const float4* la4 = reinterpret_cast<const float4*>(Ls + ((size_t)i * T + ta) * TP);
-                const float4* lb4 = reinterpret_cast<const float4*>(Ls + ((size_t)i * T + tb) * TP);
+                const int il = a.l_shared ? 0 : i;
+                const float4* la4 = reinterpret_cast<const float4*>(Ls + ((size_t)il * T + ta) * TP);
+                const float4* lb4 = reinterpret_cast<const float4*>(Ls + ((size_t)il * T + tb) * TP);
                 float acc_a = 0.f, acc_b = 0.f;
 #pragma unroll 4
                 for (int c = 0; c < 8; ++c) {
@@ -142,10 +144,10 @@ __global__ void __launch_bounds__(kMppiWarps * 32) mppi_rollout_kernel(const __g
                 float acc = 0.f;
                 const float* er = es + i * T;
                 if (a.l_in_smem) {
-                    const float* lr = Ls + ((size_t)i * T + t) * TP;
+                    const float* lr = Ls + ((size_t)(a.l_shared ? 0 : i) * T + t) * TP;
                     for (int k = 0; k <= t; ++k) acc = fmaf(lr[k], er[k], acc);
                 } else {
-                    const float* lr = a.L + ((size_t)i * T + t) * T;
+                    const float* lr = a.L + ((size_t)(a.l_shared ? 0 : i) * T + t) * T;
                     for (int k = 0; k <= t; ++k) acc = fmaf(__ldg(lr + k), er[k], acc);
                 }
                 us[t * C + i] = __ldg(a.mean_s + (size_t)t * C + i) + acc;
@@ -240,6 +242,15 @@ extern "C" int mpb_mppi_rollout_ex(const float* L_ctrl, const float* Cov_inv, co
                                    const float* ctrl_min, const float* ctrl_max, float* xu, float* quad, float* isv, int N,
                                    int T, int C, int sd, float dt, float discount, float w_pos, float w_ctrl, float w_posT,
                                    void* stream) {
+    return mpb_mppi_rollout_opt(L_ctrl, Cov_inv, mean, mean_sample, eps, noise, state0, goal, ctrl_min, ctrl_max, xu, quad, isv, N, T,
+                                C, sd, dt, discount, w_pos, w_ctrl, w_posT, 0, stream);
+}
+
+extern "C" int mpb_mppi_rollout_opt(const float* L_ctrl, const float* Cov_inv, const float* mean, const float* mean_sample,
+                                    const float* eps, const mpb_noise_desc* noise, const float* state0, const float* goal,
+                                    const float* ctrl_min, const float* ctrl_max, float* xu, float* quad, float* isv, int N,
+                                    int T, int C, int sd, float dt, float discount, float w_pos, float w_ctrl, float w_posT,
+                                    int flags, void* stream) {
     using namespace mpb;
     MPB_REQUIRE(N >= 0, "mpb_mppi_rollout: negative N");
     if (N == 0) return MPB_OK;
@@ -258,7 +269,8 @@ extern "C" int mpb_mppi_rollout_ex(const float* L_ctrl, const float* Cov_inv, co
     a.N = N; a.T = T; a.C = C; a.sd = sd; a.dt = dt; a.discount = discount; a.w_pos = w_pos; a.w_ctrl = w_ctrl; a.w_posT = w_posT;
     const size_t base = (size_t)(C * T + T + kMppiWarps * (C * T + T * C + T * sd)) * sizeof(float);
     a.tp = (T % 4 == 0) ? T + 4 : T + 1;
-    const size_t lbytes = (size_t)C * T * a.tp * sizeof(float);
+    a.l_shared = (flags & MPB_MPPI_SHARED_FACTOR) ? 1 : 0;
+    const size_t lbytes = (size_t)(a.l_shared ? 1 : C) * T * a.tp * sizeof(float);
     // L in shared memory when two CTAs still fit per SM (or when it fits at all); else it is read through L1
     a.l_in_smem = (base + lbytes <= 200 * 1024) ? 1 : 0;
     const size_t smem = base + (a.l_in_smem ? lbytes : 0);

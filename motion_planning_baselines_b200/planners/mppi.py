@@ -43,6 +43,10 @@ class MPPI(MPPlanner):
                                                      mu_init=self._mean, tensor_args=self.tensor_args)
         Cov_cpu = self.ctrl_dist.Cov.to(**_CPU32)
         self.Cov_inv = torch.stack([Cov_cpu[..., i].inverse() for i in range(self.control_dim)]).to(**self.tensor_args).contiguous()
+        # one control_std for every dimension (the reference's 'const_ctrl' prior, gaussian.py:271-333): the C factors are
+        # identical and the rollout kernel stages only one of them (checked once, bit for bit, on the host)
+        L_cpu = self.ctrl_dist.scale_tril.detach().cpu()
+        self._rollout_flags = 1 if all(torch.equal(L_cpu[0], L_cpu[i]) for i in range(1, self.control_dim)) else 0
         self.best_cost = torch.full((), float('inf'), **self.tensor_args)
         self.best_traj = torch.zeros(rollout_steps, self.state_dim, **self.tensor_args)
         self.split = sample_split or SampleSplit(world=1, rank=0)
@@ -89,12 +93,12 @@ class MPPI(MPPlanner):
         cw = self.system._c_weights
         # controls are sampled around ctrl_dist.mu (refreshed by update_ctrl_dist only), the IS term uses self._mean:
         # they differ after pop()/shift(), exactly as in the reference (mppi.py:68-70,125-128,171-178)
-        _lib.check(lib.mpb_mppi_rollout_ex(
+        _lib.check(lib.mpb_mppi_rollout_opt(
             _lib.ptr(self.ctrl_dist.scale_tril), _lib.ptr(self.Cov_inv), _lib.ptr(self._mean.contiguous()), _lib.ptr(self.ctrl_dist.mu.contiguous()),
             _lib.ptr(eps_l), nd, _lib.ptr(state0),
             _lib.ptr(goal), _lib.ptr(self.system.ctrl_min), _lib.ptr(self.system.ctrl_max), _lib.ptr(self._xu), _lib.ptr(self._quad),
             _lib.ptr(self._isv), N, T, C_, sd, float(self.system.dt), float(self.system.discount), float(cw['pos']),
-            float(cw['ctrl']), float(cw['pos_T']), st))
+            float(cw['ctrl']), float(cw['pos_T']), self._rollout_flags, st))
         cost = observation.get('cost', None)
         energy = None
         if cost is not None:

@@ -211,3 +211,30 @@ def test_mppi_large_batch_properties(dev):
     planner.optimize(opt_iters=1, eps=[eps], **obs)
     planner2.optimize(opt_iters=1, eps=[eps], state=obs['state'], goal_state=obs['goal_state'])
     assert_close(planner2.costs + float(planner._energy), planner.costs, rtol=1e-5, what='constant shift')
+
+
+def test_rollout_shared_factor_flag_is_bit_identical(dev):
+    """mpb_mppi_rollout_opt(MPB_MPPI_SHARED_FACTOR): staging one factor for all control dimensions (identical factors, the
+    reference's const_ctrl prior) gives the same rows, quadratic costs and IS dots bit for bit as staging all of them."""
+    import ctypes as C
+    lib = _lib.lib()
+    N, Tn, Cn = 777, 64, 7
+    gen = torch.Generator().manual_seed(3)
+    A = torch.randn(Tn, Tn, generator=gen) * 0.1
+    L1 = torch.linalg.cholesky(A @ A.T + 0.05 * torch.eye(Tn))
+    L = L1.unsqueeze(0).repeat(Cn, 1, 1).contiguous().to(**dev)
+    Cinv = torch.cholesky_inverse(L1).unsqueeze(0).repeat(Cn, 1, 1).contiguous().to(**dev)
+    mean = (0.1 * torch.randn(Tn, Cn, generator=gen)).to(**dev)
+    state0, goal = torch.zeros(Cn, **dev), torch.ones(Cn, **dev)
+    lo, hi = torch.full((Cn,), -100.0, **dev), torch.full((Cn,), 100.0, **dev)
+    nd = _lib.NoiseDesc(seed=5, offset=2, s_offset=0, p_offset=0, P_global=N)
+    out = []
+    for flags in (0, 1):
+        xu, quad, isv = torch.empty(N, Tn, 2 * Cn, **dev), torch.empty(N, **dev), torch.empty(N, Cn, **dev)
+        _lib.check(lib.mpb_mppi_rollout_opt(_lib.ptr(L), _lib.ptr(Cinv), _lib.ptr(mean), _lib.ptr(mean), None, C.byref(nd),
+                                            _lib.ptr(state0), _lib.ptr(goal), _lib.ptr(lo), _lib.ptr(hi), _lib.ptr(xu), _lib.ptr(quad),
+                                            _lib.ptr(isv), N, Tn, Cn, Cn, 0.04, 1.0, 1.0, 1.0, 1000.0, flags, _lib.stream_ptr()))
+        out.append((xu, quad, isv))
+    torch.cuda.synchronize()
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
