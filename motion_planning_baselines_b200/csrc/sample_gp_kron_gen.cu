@@ -88,7 +88,8 @@ struct GenArgs {
     float* mu_copy;                 // optional [P, M]: copy of mu written by the same warp (the planner's pre-update means)
     long long* trace;               // optional [64] clock stamps of CTA 0 (MPB_KRON_GEN_TRACE = device pointer; timing experiments)
     int dbg;                        // MPB_KRON_GEN_DBG bit mask (timing experiments only): 1 no Philox (zeros), 2 no MMAs,
-                                    // 4 no output stores, 8 no factor loads, 128 no epilogue TMEM loads, 256 no epilogue smem writes
+                                    // 4 no output stores, 8 no factor loads, 128 no epilogue TMEM loads, 256 no epilogue smem writes,
+                                    // 512 factor tiles staged in tensor memory by tcgen05.cp (+ 1024: only the hi tile) -- bit-identical, slower
 };
 
 // fp16 hi / lo parts of four floats -> two 8-byte words
@@ -113,6 +114,32 @@ __device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint3
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
         "}\n" ::"r"(d_tmem),
         "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// the same MMA with the A operand read from tensor memory (128 lanes x 8 columns per [128 x 16] fp16 tile)
+__device__ __forceinline__ void umma_f16_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 db;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// shared memory -> tensor memory: one [128 rows x 32 bytes] tile (the canonical no-swizzle K-major image) into 8 columns
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint32_t s_lo, uint32_t desc_hi) {
+    asm volatile(
+        "{\n"
+        ".reg .b64 ds;\n"
+        "mov.b64 ds, {%1, %2};\n"
+        "tcgen05.cp.cta_group::1.128x256b [%0], ds;\n"
+        "}\n" ::"r"(taddr),
+        "r"(s_lo), "r"(desc_hi)
         : "memory");
 }
 
@@ -207,7 +234,28 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
                     // descriptors differ only in the 14-bit start-address field: one 32-bit add each
                     const uint32_t alo_w = adesc_lo + (uint32_t)((as * C::A_STAGE) >> 4);
                     const uint32_t blo_w = bdesc_lo + (uint32_t)((bs * C::B_STAGE + u * (DOF * 2 * C::B_TILE)) >> 4);
-                    if (leader && !(a.dbg & 2)) {
+                    if (leader && (a.dbg & 512)) {
+                        // experiment: the factor tiles go shared -> tensor memory once (tcgen05.cp) and the three MMAs of a
+                        // (dof, k-step) read them from there; cp and mma of one thread execute in issue order
+#pragma unroll
+                        for (int j = 0; j < DOF; ++j) {
+                            const uint32_t ahi = alo_w + (uint32_t)(((2 * j) * C::A_TILE) >> 4), alo = ahi + (C::A_TILE >> 4);
+                            const uint32_t bhi = blo_w + (uint32_t)(((2 * j) * C::B_TILE) >> 4), blo = bhi + (C::B_TILE >> 4);
+                            const uint32_t d = tmem_base + (uint32_t)(set * (DOF * C::TS) + j * C::TS);
+                            const uint32_t slot = tmem_base + (uint32_t)(C::NSETS * DOF * C::TS) + (uint32_t)(((kc * DOF + j) & 3) * 16);
+                            tmem_cp_128x256b(slot, ahi, desc_hi);
+                            if (a.dbg & 1024) {                     // only the hi tile (used twice) goes through tensor memory
+                                if (kc == 0) umma_f16_w(d, alo, bhi, desc_hi, idesc, 0u);
+                                else umma_f16_w(d, alo, bhi, desc_hi, idesc, 1u);
+                            } else {
+                                tmem_cp_128x256b(slot + 8, alo, desc_hi);
+                                if (kc == 0) umma_f16_ts_w(d, slot + 8, bhi, desc_hi, idesc, 0u);
+                                else umma_f16_ts_w(d, slot + 8, bhi, desc_hi, idesc, 1u);
+                            }
+                            umma_f16_ts_w(d, slot, blo, desc_hi, idesc, 1u);
+                            umma_f16_ts_w(d, slot, bhi, desc_hi, idesc, 1u);
+                        }
+                    } else if (leader && !(a.dbg & 2)) {
 #pragma unroll
                         for (int j = 0; j < DOF; ++j) {
                             const uint32_t ahi = alo_w + (uint32_t)(((2 * j) * C::A_TILE) >> 4), alo = ahi + (C::A_TILE >> 4);
