@@ -1,4 +1,5 @@
 // C-ABI glue of libmpb_b200.so: error reporting, device queries and the fused iteration drivers.
+#include <cstdlib>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -67,6 +68,11 @@ unsigned* pool_of_current_device(bool rezero) {
 unsigned* sched_slot() {
     unsigned* pool = pool_of_current_device(false);
     return pool ? pool + 2 * (g_slot_seq.fetch_add(1u) % kSlots) : nullptr;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("MPB_PDL"); return !(v && v[0] == '0'); }();
+    return on;
 }
 
 int init_current_device() { return pool_of_current_device(true) ? MPB_OK : MPB_ECUDA; }

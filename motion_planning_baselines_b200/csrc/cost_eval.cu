@@ -572,8 +572,7 @@ static cudaError_t launch_chain2b(const CostArgs& a, size_t smem, cudaStream_t s
     if (per_sm < 1) per_sm = 1;
     const int resident = sm_count() * per_sm, blocks_needed = (a.B + NW - 1) / NW;
     const int grid = blocks_needed < resident ? blocks_needed : resident;
-    kern<<<grid, NW * 32, smem, st>>>(a);
-    return cudaSuccess;
+    return launch_pdl(kern, dim3(grid), dim3(NW * 32), smem, st, a);
 }
 
 template <int DOF, int NW, int MINB>

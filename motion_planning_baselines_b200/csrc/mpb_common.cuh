@@ -20,6 +20,28 @@ int sm_count();                         // SMs of the current device (cached per
 unsigned* sched_slot();
 int init_current_device();              // allocate + zero the pool of the current device (mpb_init)
 
+// Programmatic dependent launch (the three kernels of a Stoch-GPMP iteration run back to back on one stream): a kernel
+// launched with launch_pdl may start while its predecessor drains -- its CTAs become resident as the predecessor's exit --
+// and runs everything that does not depend on the predecessor (staging of the robot / field tables, barrier and
+// tensor-memory set-up) before pdl_wait(), which returns once the predecessor grid has completed and its writes are visible.
+// pdl_trigger() at the top of a kernel lets ITS successor be scheduled as early as resources allow.  Without the launch
+// attribute (or after a kernel that never triggers) both instructions are no-ops / ordinary stream order.  MPB_PDL=0 disables it.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 #define MPB_REQUIRE(cond, ...)                       \
     do {                                             \
         if (!(cond)) {                               \

@@ -170,6 +170,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
     uint64_t* out_empty = out_full + 2;                // [2] the bulk store has read the buffer (store warp)
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(out_empty + 2);
 
+    pdl_trigger();                                     // the cost kernel may be scheduled as CTAs of this grid exit
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // slot = 8 * tile ordinal + event: 0 MMA first chunk ready, 1 MMA tile committed, 2 epilogue start, 3 epilogue end,
     // 4 producer first chunk written, 5 producer last chunk written, 6 MMA got the accumulators
@@ -188,6 +189,7 @@ sample_gp_kron_gen_kernel(const GenArgs a, const NoiseArgs noise) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    pdl_wait();                                        // the means come from the previous iteration's update kernel
 
     if (warp == C::LOAD_WARP) {
         // ================================ factor loader ================================
@@ -529,14 +531,12 @@ static cudaError_t launch_kron_gen(GenArgs& a, const NoiseArgs& noise, int ts, c
         auto kern = sample_gp_kron_gen_kernel<7, 64>;
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C64::SMEM);
         if (e != cudaSuccess) return e;
-        kern<<<grid, C64::THREADS, C64::SMEM, st>>>(a, noise);
-        return cudaSuccess;
+        return launch_pdl(kern, dim3(grid), dim3(C64::THREADS), C64::SMEM, st, a, noise);
     }
     auto kern = sample_gp_kron_gen_kernel<DOF, 32>;
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;
-    kern<<<grid, C::THREADS, C::SMEM, st>>>(a, noise);
-    return cudaSuccess;
+    return launch_pdl(kern, dim3(grid), dim3(C::THREADS), C::SMEM, st, a, noise);
 }
 }  // namespace mpb
 

@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
     __shared__ int s_nnz;
     const int p = blockIdx.x;
     const float* cp = cost + (size_t)p * S;
+    pdl_trigger();
+    pdl_wait();                        // the costs come from the kernel in front
 
     // ---- phase 1: softmax over samples ----------------------------------------------------
     float mx = -CUDART_INF_F;
@@ -156,7 +158,8 @@ extern "C" int mpb_softmax_update_ex(const float* cost, const float* x, float* m
     MPB_REQUIRE(smem <= 200 * 1024, "mpb_softmax_update: S=%d too large for the single-CTA path", S);
     cudaError_t e = cudaFuncSetAttribute(softmax_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("mpb_softmax_update: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
-    softmax_update_kernel<<<P, kUpdThreads, smem, static_cast<cudaStream_t>(stream)>>>(cost, x, mu, weights, grad, temp,
-                                                                                      step, SigmaR, mu_copy, S, H, D);
+    e = launch_pdl(softmax_update_kernel, dim3(P), dim3(kUpdThreads), smem, static_cast<cudaStream_t>(stream), cost, x, mu, weights, grad,
+                   temp, step, SigmaR, mu_copy, S, H, D);
+    if (e != cudaSuccess) { set_error("mpb_softmax_update: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
     return check_launch("mpb_softmax_update");
 }
