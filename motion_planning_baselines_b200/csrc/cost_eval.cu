@@ -66,19 +66,26 @@ struct HingeAcc {
 
 // Exact pass over `count` (<= 32) queue entries starting at `first`, one entry per lane.  Deliberately NOT
 // inlined: it is the rare path, and keeping one copy keeps the hot loops resident in the instruction cache.
-__device__ __noinline__ void drain(const FieldArgs& fa, unsigned qbase, int first, int count, int lane, HingeAcc& acc) {
+// It returns the lane's (hinge, field index) and the caller accumulates: accumulators handed over by reference would
+// live in local memory (lanes past `count` return (0, field 0); adding +0 is exact).
+__device__ __noinline__ float2 drain(const FieldArgs& fa, unsigned qbase, int first, int count, int lane) {
     extern __shared__ __align__(16) unsigned char smem[];
+    float2 out = make_float2(0.f, __int_as_float(0));
     if (lane < count) {
         const int i = first + lane;
         const float* qb = reinterpret_cast<const float*>(smem + qbase);
         const int f = __float_as_int(qb[4 * kQCap + i]);
-        const float h = exact_hinge(smem, fa.l[f], qb[i], qb[kQCap + i], qb[2 * kQCap + i], qb[3 * kQCap + i]);
-        acc.all_zero = acc.all_zero && (h == 0.f);
-#pragma unroll
-        for (int k = 0; k < MPB_MAX_FIELDS; ++k)
-            if (k == f) acc.h[k] += h;
+        out = make_float2(exact_hinge(smem, fa.l[f], qb[i], qb[kQCap + i], qb[2 * kQCap + i], qb[3 * kQCap + i]), __int_as_float(f));
     }
     __syncwarp();
+    return out;
+}
+
+__device__ __forceinline__ void acc_add2(HingeAcc& acc, const float2 hf) {
+    const int f = __float_as_int(hf.y);
+    acc.all_zero = acc.all_zero && (hf.x == 0.f);
+#pragma unroll
+    for (int k = 0; k < MPB_MAX_FIELDS; ++k) acc.h[k] += (k == f) ? hf.x : 0.f;
 }
 
 // Append the lanes whose `pred` is set; drain a full batch of 32 when available.
@@ -94,7 +101,7 @@ __device__ __forceinline__ void enqueue(unsigned char* smem, const FieldArgs& fa
     __syncwarp();
     if (q.n >= 32) {
         q.n -= 32;
-        drain(fa, q.base, q.n, 32, lane, acc);
+        acc_add2(acc, drain(fa, q.base, q.n, 32, lane));
     }
 }
 
@@ -473,7 +480,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) cost_eval_kernel(const __grid_
             }
         }
         if (q.n > 0) {
-            drain(a.fields, q.base, 0, q.n, lane, hacc);
+            acc_add2(hacc, drain(a.fields, q.base, 0, q.n, lane));
             q.n = 0;
         }
 
@@ -688,7 +695,8 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
     a.rows_off = off;
     off += (unsigned)(nw * 2 * a.row_stride * sizeof(float));       // current + prefetched row per warp
     a.queue_off = off;
-    off += (unsigned)(nw * kQCap * (packed ? 7 : 5) * sizeof(float));   // generic: 5 words per entry; packed: + primitive masks
+    // generic: 5 words per entry; packed: + primitive masks, and each warp's per-lane hinge sums behind its queue
+    off += packed ? (unsigned)nw * kQ2Stride : (unsigned)(nw * kQCap * 5 * sizeof(float));
     a.list_cap = 8;
     for (int i = 0; i < n_fields; ++i) {
         if (fields[i].kind != MPB_FIELD_PRIMITIVES) continue;
