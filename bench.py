@@ -498,8 +498,9 @@ def main():
         flop_k1 = DOF * (2 * H) * (2 * H + 1)       # 7 independent [128,128] triangular mat-vecs = 115,584 flop / sample
         bytes_k1 = M * 4 * (2 if k1_reads_eps else 1)
         gen = (not k1_reads_eps) and planner_uses_gen
-        k1_name = ('sample_gp_kron_gen_kernel<7> (K1: tcgen05 kind::f16 with the factor as the M = 128 operand, 64-sample tiles, 7 '
-                   'accumulators in TMEM, warp-specialised Philox producers, bulk-async factor loads and row stores)' if gen else
+        k1_name = ('sample_gp_kron_gen_kernel<7,32> (K1: tcgen05 kind::f16 with the factor as the M = 128 operand, 32-sample tiles, two '
+                   'sets of 7 accumulators in TMEM (the epilogue of a tile overlaps the MMAs of the next), warp-specialised Philox '
+                   'producers, bulk-async factor loads and row stores, Sigma^-1 mu on an extra warp)' if gen else
                    'sample_gp_kron_mma_kernel<7,64,%s> (K1: structured GP sampler, warp MMA fp16x2 split%s)'
                    % ('false' if k1_reads_eps else 'true', '' if k1_reads_eps else ', Philox noise in-kernel'))
         k1 = dict(kernel=k1_name,
@@ -507,9 +508,10 @@ def main():
                   algorithmic_bytes_per_sample=bytes_k1, algorithmic_flop_per_sample=flop_k1,
                   note='HBM floor = x written' + (' + eps read' if k1_reads_eps else '') + '; the factor decouples over the 7 dofs '
                        '(exact zeros, verified bit-exactly at setup): 115,584 flop / sample instead of the dense 803,712'
-                       + ('; measured limiters (profiles/r02_k1_gen_*.txt): noise generation on the CUDA cores (29.4 M normals: '
-                          'Philox4x32-10 + Box-Muller + fp16 split = ~110 instructions per 4) and the accumulator hand-over between '
-                          'MMA and epilogue (448 of 512 TMEM columns: one accumulator set)' if gen else ''))
+                       + ('; measured limiters (profiles/r02_k1_gen_*.txt, DESIGN 4c): the MMAs themselves -- three fp16 MMAs per '
+                          'k-step for the two-term split, each fetching its 4 KiB factor tile from shared memory (55 cycles per '
+                          'M128 x N32 x K16 MMA: floor 0.047 ms) -- and the noise generation on the CUDA cores (29.4 M normals: '
+                          'Philox4x32-10 + Box-Muller + fp16 split = ~110 instructions per 4: issue floor 0.023 ms)' if gen else ''))
         k1['frac'] = k1['achieved'] / k1['peak']
         if gen and mv_in_k1:
             mv = dict(kernel='(no launch) Sigma^-1 mu is computed by warp 25 of K1 while the tiles run (mpb_sample_gp_kron_gen_mv); '
@@ -550,9 +552,22 @@ def main():
 
     kernels = kernel_table(stage_ms, k1_reads_eps=False)
     dom = max(kernels, key=lambda k: k['ms'])
-    roofline = dict(bound=dom['bound'], achieved=dom['achieved'], peak=dom['peak'], unit=dom['unit'], frac=dom['frac'],
-                    traffic=ncu_traffic(dom['kernel']), kernel=dom['kernel'], ms_per_launch=dom['ms'],
-                    peak_source='FP32 FFMA rate MEASURED in this run (mpb_bench_fp32_peak: 8 independent FMA chains per thread, '
+    # The dominant kernel (K2) is bound by the instruction-issue rate, not by HBM or a math pipe: the headline fraction is
+    # executed issue slots / issue peak (<= 1 by construction).  The SURVEY 8d algorithmic-flop figure counts all 800 sphere
+    # pairs per waypoint, which the broad phase never evaluates -- it can exceed the FP32 peak and is reported next to it
+    # (algorithmic_fp32_view), not as the roofline fraction.
+    head = dom.get('issue_view')
+    if head:
+        roofline = dict(bound='issue', achieved=head['achieved'], peak=head['peak'], unit=head['unit'], frac=head['frac'],
+                        issue_source=head['source'], issue_slots_per_sample=head['issue_slots_per_sample'],
+                        algorithmic_fp32_view=dict(bound=dom['bound'], achieved=dom['achieved'], peak=dom['peak'], unit=dom['unit'],
+                                                   frac=dom['frac'], note=dom['note']))
+    else:
+        roofline = dict(bound=dom['bound'], achieved=dom['achieved'], peak=dom['peak'], unit=dom['unit'], frac=dom['frac'])
+    roofline.update(traffic=ncu_traffic(dom['kernel']), kernel=dom['kernel'], ms_per_launch=dom['ms'],
+                    peak_source='issue peak = 148 SMs x 4 schedulers x clocks.max.sm (one warp instruction per scheduler and cycle; '
+                                'FFMA2 / FADD2 / FMUL2 take two cycles: profiles/r02_ffma2_microbench.txt); FP32 FFMA rate of the '
+                                'algorithmic view MEASURED in this run (mpb_bench_fp32_peak: 8 independent FMA chains per thread, '
                                 'best of 6 launches); nominal 148 SMs x 128 lanes x 2 x clocks.max.sm = %.1f TFLOP/s' % fp32_nominal,
                     peak_nominal=fp32_nominal, frac_of_nominal=dom.get('frac_of_nominal'),
                     algorithmic_flop_per_sample=dom.get('algorithmic_flop_per_sample'),
