@@ -336,6 +336,37 @@ int mpb_stoch_gpmp_iter_kron_gen_ex(const void* L_kron_gen, const float* Sigma_i
                                     float* is_vec, uint8_t* free_flag, float* mu_prev, float* mu_out, int P, int S, int H,
                                     const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
                                     const mpb_gp_desc* gp, float temp, float step, void* stream);
+/* ---- dof-major sample rows (the fused Stoch-GPMP iteration of the 7-dof arm at H = 64) --------------------------------
+ * The reference keeps a sampled trajectory as [H][2 dof] (mp_priors_multi.py:253-256 returns [S, P, H, 2 dof]).  Between the
+ * kernels of ONE fused iteration nothing but our own code reads the samples, and in the order [dof][2H] (column
+ * 2H j + 2 h + pv; pv = 0 position, 1 velocity) the dofs of the structured factor stay independent all the way to global
+ * memory: the sampler's work unit becomes (64 samples, one dof), its factor is loaded once per CTA and dof, and its time
+ * halves.  Values are bit-identical to the natural-layout entry points; only the memory order differs.
+ *
+ * mpb_sample_gp_kron_gen_dm       MultiMPPrior.sample incl. the noise draw (mp_priors_multi.py:253-256), as
+ *                                 mpb_sample_gp_kron_gen_mv but writing x_dm [P, S, dof, 2H]; Sigma_inv / y / mu_copy optional
+ * mpb_cost_eval_dm(_supported)    mpb_cost_eval (cost_functions.py:41-53,171-189; stoch_gpmp.py:235-245) on dof-major rows;
+ *                                 is_vec, start / goal states stay in the reference layout.  Supported: 7-dof chain, H = 64,
+ *                                 primitive fields (the packed kernel's default instances)
+ * mpb_softmax_update_dm           mpb_softmax_update_ex (stoch_gpmp.py:267-279) reading dof-major rows; mu / grad / mu_copy in
+ *                                 the reference layout
+ * mpb_traj_from/to_dof_major      the permutation itself, [B, dof, 2H] <-> [B, H, 2 dof] (state_samples accessors, tests)
+ * mpb_stoch_gpmp_iter_kron_gen_dm the three kernels of mpb_stoch_gpmp_iter_kron_gen_ex on x_dm (stoch_gpmp.py:235-279) */
+int mpb_sample_gp_kron_gen_dm(const void* Limg, const float* mu, const mpb_noise_desc* nd, float* x_dm, int P, int S, int H, int dof,
+                              const float* Sigma_inv, float* y, float* mu_copy, void* stream);
+int mpb_cost_eval_dm_supported(const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields, int H);
+int mpb_cost_eval_dm(const float* x_dm, int B, int H, const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields,
+                     const mpb_gp_desc* gp, const float* is_vec, int samples_per_particle, float is_scale, float* cost,
+                     float* terms, uint8_t* free_flag, void* stream);
+int mpb_softmax_update_dm(const float* cost, const float* x_dm, float* mu, float* weights, float* grad, float temp, float step,
+                          float* mu_copy, int P, int S, int H, int D, void* stream);
+int mpb_traj_from_dof_major(const float* x_dm, float* x, long long B, int H, int dof, void* stream);
+int mpb_traj_to_dof_major(const float* x, float* x_dm, long long B, int H, int dof, void* stream);
+int mpb_stoch_gpmp_iter_kron_gen_dm(const void* L_kron_gen, const float* Sigma_inv, const mpb_noise_desc* noise, float* mu,
+                                    float* x_dm, float* cost, float* weights, float* is_vec, uint8_t* free_flag, float* mu_prev,
+                                    float* mu_out, int P, int S, int H, const mpb_robot_desc* robot,
+                                    const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp, float temp, float step,
+                                    void* stream);
 /* STOMP, n_iters iterations from one call (stomp.py:137-160): mpb_sample_stomp_rng (draw counter noise->offset + it),
  * mpb_cost_eval, mpb_softmax_update with Sigma_R -- for the launch-latency-bound small configurations.  The caller
  * advances its draw counter by n_iters. */

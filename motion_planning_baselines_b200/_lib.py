@@ -91,6 +91,15 @@ _SIGNATURES = {
     'mpb_sample_gp_kron_gen_prepare': (C.c_int, [_vp, _vp, _i, _i, _vp]),
     'mpb_sample_gp_kron_gen': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _i, _i, _i, _i, _vp]),
     'mpb_sample_gp_kron_gen_mv': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'mpb_sample_gp_kron_gen_dm': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'mpb_cost_eval_dm_supported': (C.c_int, [C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, _i]),
+    'mpb_cost_eval_dm': (C.c_int, [_vp, _i, _i, C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc),
+                                   _vp, _i, _f, _vp, _vp, _vp, _vp]),
+    'mpb_softmax_update_dm': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _vp]),
+    'mpb_traj_from_dof_major': (C.c_int, [_vp, _vp, C.c_longlong, _i, _i, _vp]),
+    'mpb_traj_to_dof_major': (C.c_int, [_vp, _vp, C.c_longlong, _i, _i, _vp]),
+    'mpb_stoch_gpmp_iter_kron_gen_dm': (C.c_int, [_vp, _vp, C.POINTER(NoiseDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                                  C.POINTER(RobotDesc), C.POINTER(FieldDesc), _i, C.POINTER(GPDesc), _f, _f, _vp]),
     'mpb_mppi_rollout_ex': (C.c_int, [_vp] * 5 + [C.POINTER(NoiseDesc)] + [_vp] * 7 + [_i, _i, _i, _i, _f, _f, _f, _f, _f, _vp]),
     'mpb_mppi_rollout_opt': (C.c_int, [_vp] * 5 + [C.POINTER(NoiseDesc)] + [_vp] * 7 + [_i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _vp]),
     'mpb_prior_matvec': (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),

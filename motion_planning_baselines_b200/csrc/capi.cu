@@ -197,6 +197,25 @@ extern "C" int mpb_stoch_gpmp_iter_kron_gen_ex(const void* L_kron_gen, const flo
     return mpb_softmax_update_ex(cost, x, mu, weights, nullptr, temp, step, nullptr, mu_out, P, S, H, D, stream);
 }
 
+// The same iteration with the sample rows kept DOF-MAJOR between the three kernels (x_dm: [P, S, dof, 2H]; see
+// sample_gp_kron_gen_dm.cu for why that layout halves the sampler's time): K1 writes them, K2 and K3 read them in place.
+// Samples, costs, weights and means are bit-identical to mpb_stoch_gpmp_iter_kron_gen_ex; only the memory order of x
+// differs (mpb_traj_from_dof_major gives the reference order back for `state_samples`).  Needs the structured precision
+// (the mat-vec warp) and mpb_cost_eval_dm_supported(robot, fields, n_fields, H).
+extern "C" int mpb_stoch_gpmp_iter_kron_gen_dm(const void* L_kron_gen, const float* Sigma_inv, const mpb_noise_desc* noise, float* mu,
+                                               float* x_dm, float* cost, float* weights, float* is_vec, uint8_t* free_flag,
+                                               float* mu_prev, float* mu_out, int P, int S, int H, const mpb_robot_desc* robot,
+                                               const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp, float temp,
+                                               float step, void* stream) {
+    MPB_REQUIRE(robot && L_kron_gen && noise && Sigma_inv, "mpb_stoch_gpmp_iter_kron_gen_dm: null robot / factor / precision / noise descriptor");
+    const int D = 2 * robot->q_dim;
+    int rc = mpb_sample_gp_kron_gen_dm(L_kron_gen, mu, noise, x_dm, P, S, H, robot->q_dim, Sigma_inv, is_vec, mu_prev, stream);
+    if (rc) return rc;
+    rc = mpb_cost_eval_dm(x_dm, P * S, H, robot, fields, n_fields, gp, is_vec, S, temp, cost, nullptr, free_flag, stream);
+    if (rc) return rc;
+    return mpb_softmax_update_dm(cost, x_dm, mu, weights, nullptr, temp, step, mu_out, P, S, H, D, stream);
+}
+
 // STOMP: `n_iters` whole iterations (stomp.py:137-160: sample -> cost -> importance-weighted update) enqueued from ONE
 // call -- sample_stomp (noise drawn in the kernel, draw counter noise->offset + it), cost_eval, softmax_update with Sigma_R.
 // The small STOMP configurations are bound by launch / host latency (BASELINE.json configs[0]: 64 samples), so the

@@ -49,6 +49,7 @@ struct CostArgs {
     mpb_extra_cost_desc ex;            // CostGPTrajectory / CostJointLimits (only read by the XF variant)
     float* jl_out;                     // [B] raw joint-limit term per trajectory
     CullTable ctab;                    // packed kernel: link-frame cull table (cost_eval_packed.cuh)
+    int x_dm;                          // packed kernel, 7 dofs, H = 64: the rows of x are dof-major (sample_gp_kron_gen_dm.cu)
     int k2_local;                      // packed kernel: sphere-only lists are culled in the link frame (MPB_K2_LOCAL=0: world frame)
 };
 
@@ -566,9 +567,9 @@ static cudaError_t launch(const CostArgs& a, int blocks_needed, size_t smem, cud
 
 namespace mpb {
 
-template <int DOF, int NW, int MINB, bool BOXES, bool SPH>
+template <int DOF, int NW, int MINB, bool BOXES, bool SPH, bool DM = false>
 static cudaError_t launch_chain2b(const CostArgs& a, size_t smem, cudaStream_t st) {
-    auto kern = cost_eval_chain2_kernel<DOF, NW, MINB, BOXES, SPH>;
+    auto kern = cost_eval_chain2_kernel<DOF, NW, MINB, BOXES, SPH, DM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -620,11 +621,44 @@ extern "C" int mpb_cost_eval(const float* x, int B, int H, const mpb_robot_desc*
                             free_flag, nullptr, nullptr, stream);
 }
 
+static int cost_eval_impl(const float* x, int B, int H, const mpb_robot_desc* robot,
+                          const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp,
+                          const float* is_vec, int samples_per_particle, float is_scale,
+                          float* cost, float* terms, uint8_t* free_flag,
+                          const mpb_extra_cost_desc* extra, float* jl_per_traj, int x_dm, void* stream);
+
 extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_desc* robot,
                                 const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp,
                                 const float* is_vec, int samples_per_particle, float is_scale,
                                 float* cost, float* terms, uint8_t* free_flag,
                                 const mpb_extra_cost_desc* extra, float* jl_per_traj, void* stream) {
+    return cost_eval_impl(x, B, H, robot, fields, n_fields, gp, is_vec, samples_per_particle, is_scale, cost, terms, free_flag, extra,
+                          jl_per_traj, 0, stream);
+}
+
+extern "C" int mpb_cost_eval_dm_supported(const mpb_robot_desc* robot, const mpb_field_desc* fields, int n_fields, int H) {
+    if (!robot || robot->kind != MPB_ROBOT_CHAIN || robot->q_dim != 7 || H != 64 || !mpb::packed_allowed()) return 0;
+    if (getenv("MPB_K2_CFG") || getenv("MPB_K2_LOCAL")) return 0;          // experiment shapes exist in the natural layout only
+    for (int i = 0; i < n_fields; ++i)
+        if (!fields || fields[i].kind != MPB_FIELD_PRIMITIVES) return 0;
+    return 1;
+}
+
+extern "C" int mpb_cost_eval_dm(const float* x_dm, int B, int H, const mpb_robot_desc* robot,
+                                const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp,
+                                const float* is_vec, int samples_per_particle, float is_scale,
+                                float* cost, float* terms, uint8_t* free_flag, void* stream) {
+    MPB_REQUIRE(mpb_cost_eval_dm_supported(robot, fields, n_fields, H),
+                "mpb_cost_eval_dm: dof-major rows need a 7-dof chain, H = 64 and primitive fields only");
+    return cost_eval_impl(x_dm, B, H, robot, fields, n_fields, gp, is_vec, samples_per_particle, is_scale, cost, terms, free_flag,
+                          nullptr, nullptr, 1, stream);
+}
+
+static int cost_eval_impl(const float* x, int B, int H, const mpb_robot_desc* robot,
+                          const mpb_field_desc* fields, int n_fields, const mpb_gp_desc* gp,
+                          const float* is_vec, int samples_per_particle, float is_scale,
+                          float* cost, float* terms, uint8_t* free_flag,
+                          const mpb_extra_cost_desc* extra, float* jl_per_traj, int x_dm, void* stream) {
     using namespace mpb;
     MPB_REQUIRE(B >= 0, "mpb_cost_eval: negative batch size %d", B);
     if (B == 0) return MPB_OK;
@@ -722,6 +756,9 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
     }
     a.sched = sched_slot();
     if (!a.sched) { set_error("mpb_cost_eval: could not allocate the scheduler counters"); return MPB_ECUDA; }
+    a.x_dm = x_dm;
+    MPB_REQUIRE(!x_dm || (packed && robot->q_dim == 7 && H == 64 && (cfg == 102 || cfg == 82 || cfg == 63)),
+                "mpb_cost_eval_dm: configuration has no dof-major instance");
     const int blocks_needed = (B + kWarps - 1) / kWarps;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
@@ -734,6 +771,13 @@ extern "C" int mpb_cost_eval_ex(const float* x, int B, int H, const mpb_robot_de
             case 6: e = launch_chain2<6, 8, 2>(a, smem, st); break;
             case 8: e = launch_chain2<8, 8, 2>(a, smem, st); break;
             default:
+                if (x_dm) {
+                    // dof-major rows: the three default instances only (cfg was chosen from the fields above)
+                    e = cfg == 102 ? launch_chain2b<7, 10, 2, false, true, true>(a, smem, st)
+                        : cfg == 63 ? launch_chain2b<7, 6, 3, true, false, true>(a, smem, st)
+                                    : launch_chain2b<7, 8, 2, true, true, true>(a, smem, st);
+                    break;
+                }
                 switch (cfg) {
                     case 83: e = launch_chain2<7, 8, 3>(a, smem, st); break;
                     case 45: e = launch_chain2<7, 4, 5>(a, smem, st); break;

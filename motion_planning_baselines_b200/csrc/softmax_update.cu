@@ -31,7 +31,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
     const float* __restrict__ cost, const float* __restrict__ x, float* __restrict__ mu, float* __restrict__ weights,
     float* __restrict__ grad, float temp, float step, const float* __restrict__ SigmaR, float* __restrict__ mu_copy, int S, int H,
-    int D) {
+    int D, int x_dm) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float red[32];
     const int M = H * D;
@@ -85,7 +85,35 @@ __global__ void __launch_bounds__(kUpdThreads) softmax_update_kernel(
     const float* xp = x + (size_t)p * S * M;
     float* mp = mu + (size_t)p * M;
     const bool vec = ((M & 3) == 0);
-    if (vec) {
+    if (x_dm) {
+        // The sample rows are DOF-MAJOR (column 2H j + 2 h + pv, sample_gp_kron_gen_dm.cu); mu / grad / mu_copy keep the
+        // reference layout (column D h + dof pv + j).  A thread still streams four consecutive floats of every listed row
+        // with one 128-bit load; they are (h, pos), (h, vel), (h + 1, pos), (h + 1, vel) of one dof.  Per element the same
+        // operations in the same sample order as below: bit-identical means.
+        const int dof = D >> 1, N2 = 2 * H;
+        for (int c = threadIdx.x * 4; c < M; c += blockDim.x * 4) {
+            const int j = c / N2, n = c - j * N2;
+            const int c0 = (n >> 1) * D + j;
+            const int col[4] = {c0, c0 + dof, c0 + D, c0 + D + dof};
+            float m4[4], g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m4[i] = mp[col[i]];
+            for (int k = 0; k < nnz; ++k) {
+                const int s = nzs[k];
+                const float w = ws[s];
+                const float4 v = __ldg(reinterpret_cast<const float4*>(xp + (size_t)s * M + c));
+                g[0] = fmaf(w, v.x - m4[0], g[0]); g[1] = fmaf(w, v.y - m4[1], g[1]);
+                g[2] = fmaf(w, v.z - m4[2], g[2]); g[3] = fmaf(w, v.w - m4[3], g[3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (grad) grad[(size_t)p * M + col[i]] = g[i];
+                const float o = fmaf(step, g[i], m4[i]);
+                mp[col[i]] = o;
+                if (mu_copy) mu_copy[(size_t)p * M + col[i]] = o;
+            }
+        }
+    } else if (vec) {
         for (int c = threadIdx.x * 4; c < M; c += blockDim.x * 4) {
             const float4 m4 = *reinterpret_cast<const float4*>(mp + c);
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -146,9 +174,24 @@ extern "C" int mpb_softmax_update(const float* cost, const float* x, float* mu, 
     return mpb_softmax_update_ex(cost, x, mu, weights, grad, temp, step, SigmaR, nullptr, P, S, H, D, stream);
 }
 
+static int softmax_update_impl(const float* cost, const float* x, float* mu, float* weights, float* grad, float temp, float step,
+                               const float* SigmaR, float* mu_copy, int P, int S, int H, int D, int x_dm, void* stream);
+
+// the same update reading DOF-MAJOR sample rows (sample_gp_kron_gen_dm.cu); mu / grad / mu_out in the reference layout
+extern "C" int mpb_softmax_update_dm(const float* cost, const float* x_dm, float* mu, float* weights, float* grad, float temp,
+                                     float step, float* mu_copy, int P, int S, int H, int D, void* stream) {
+    MPB_REQUIRE((D & 1) == 0 && ((2 * H) & 3) == 0, "mpb_softmax_update_dm: need an even state dimension and 2H a multiple of 4");
+    return softmax_update_impl(cost, x_dm, mu, weights, grad, temp, step, nullptr, mu_copy, P, S, H, D, 1, stream);
+}
+
 extern "C" int mpb_softmax_update_ex(const float* cost, const float* x, float* mu, float* weights, float* grad,
                                      float temp, float step, const float* SigmaR, float* mu_copy, int P, int S, int H, int D,
                                      void* stream) {
+    return softmax_update_impl(cost, x, mu, weights, grad, temp, step, SigmaR, mu_copy, P, S, H, D, 0, stream);
+}
+
+static int softmax_update_impl(const float* cost, const float* x, float* mu, float* weights, float* grad, float temp, float step,
+                               const float* SigmaR, float* mu_copy, int P, int S, int H, int D, int x_dm, void* stream) {
     using namespace mpb;
     MPB_REQUIRE(cost && x && mu && weights, "mpb_softmax_update: null pointer");
     MPB_REQUIRE(P >= 0 && S >= 1 && H >= 1 && D >= 1, "mpb_softmax_update: bad sizes");
@@ -159,7 +202,7 @@ extern "C" int mpb_softmax_update_ex(const float* cost, const float* x, float* m
     cudaError_t e = cudaFuncSetAttribute(softmax_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("mpb_softmax_update: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
     e = launch_pdl(softmax_update_kernel, dim3(P), dim3(kUpdThreads), smem, static_cast<cudaStream_t>(stream), cost, x, mu, weights, grad,
-                   temp, step, SigmaR, mu_copy, S, H, D);
+                   temp, step, SigmaR, mu_copy, S, H, D, x_dm);
     if (e != cudaSuccess) { set_error("mpb_softmax_update: %s", cudaGetErrorString(e)); return MPB_ECUDA; }
     return check_launch("mpb_softmax_update");
 }

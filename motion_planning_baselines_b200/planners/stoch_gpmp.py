@@ -50,6 +50,7 @@ class StochGPMP(OptimizationPlanner):
         self._weights = None
         self._sample_dist = None
         self._recent_state_particles = self._recent_control_particles = None
+        self._has_recent = False
         self.costs = None
         self.free_flags = None
 
@@ -115,12 +116,63 @@ class StochGPMP(OptimizationPlanner):
         self._sinv_structured = bool(ok.value)
         P, S, H, D = self.num_particles, self.num_samples, self.n_support_points, self.d_state_opt
         ta = self.tensor_args
+        self._x_dm = None               # dof-major sample rows of the fused iteration (allocated on first use)
+        self._x_dm_fresh = False        # True: _x_dm holds the latest samples and _state_samples has not been refreshed from it
         self.state_samples = torch.empty(P, S, H, D, **ta)
         self.costs = torch.empty(P, S, **ta)
         self._w_buf = torch.empty(P, S, **ta)
         self._is_vec = torch.empty(P, H * D, **ta)
         self.free_flags = torch.empty(P * S, device=ta['device'], dtype=torch.uint8)
         self.state_samples = self._sample_dist.sample(S, out=self.state_samples.view(P, S, H * D))
+
+    # The fused iteration of the 7-dof arm keeps its sample rows DOF-MAJOR between its three kernels (include/mpb.h,
+    # "dof-major sample rows"); the reference-layout [P, S, H, 2 dof] tensor is produced from them when somebody asks.
+    @property
+    def state_samples(self):
+        if self._x_dm_fresh:
+            P, S, H = self.num_particles, self.num_samples, self.n_support_points
+            _lib.check(_lib.lib().mpb_traj_from_dof_major(_lib.ptr(self._x_dm), _lib.ptr(self._state_samples), P * S, H, self.n_dof,
+                                                          _lib.stream_ptr()))
+            self._x_dm_fresh = False
+        return self._state_samples
+
+    @state_samples.setter
+    def state_samples(self, value):
+        self._state_samples = value
+        self._x_dm_fresh = False
+
+    @property
+    def _recent_control_samples(self):
+        return self.state_samples[..., -self.n_dof:] if self._has_recent else None
+
+    @_recent_control_samples.setter
+    def _recent_control_samples(self, value):
+        self._has_recent = value is not None
+
+    @property
+    def _recent_state_trajectories(self):
+        return self.state_samples[..., :self.n_dof] if self._has_recent else None
+
+    @_recent_state_trajectories.setter
+    def _recent_state_trajectories(self, value):
+        self._has_recent = value is not None
+
+    def _use_dof_major(self, fields, nf):
+        """The dof-major fused iteration: tcgen05 sampler with the mat-vec warp + a cost-kernel instance that reads the rows
+        in place (7-dof chain, H = 64, primitive fields).  Opt-in (MPB_X_DM=1): bit-identical to the reference-layout
+        iteration and, as measured on the B200, no faster -- both samplers are bound by the noise generation."""
+        import os
+        if os.environ.get('MPB_X_DM', '0') != '1':
+            return False
+        sd = self._sample_dist
+        return (sd.scale_tril_kron_gen is not None and self._sinv_structured
+                and bool(_lib.lib().mpb_cost_eval_dm_supported(C.byref(self.robot.desc), fields, nf, self.n_support_points)))
+
+    def _dm_rows(self):
+        if self._x_dm is None:
+            self._x_dm = torch.empty(self.num_particles, self.num_samples, self.n_support_points * self.d_state_opt,
+                                     **self.tensor_args)
+        return self._x_dm
 
     # ------------------------------------------------------------------ hot path
     def _get_costs(self, **observation):
@@ -185,6 +237,7 @@ class StochGPMP(OptimizationPlanner):
         pos_mean = vel_mean = None
         sd = self._sample_dist
         traj_out = None
+        use_dm = eps is None and self._use_dof_major(fields, nf)
         for it in range(opt_iters):
             last = it == opt_iters - 1
             gen_path = eps is None and sd.scale_tril_kron_gen is not None
@@ -198,6 +251,16 @@ class StochGPMP(OptimizationPlanner):
                 if sd.scale_tril_kron_gen is not None:      # default: Blackwell sampler, noise drawn inside K1
                     if last:
                         traj_out = torch.empty_like(self._particle_means)
+                    if use_dm:                              # sample rows stay dof-major between the three kernels
+                        _lib.check(lib.mpb_stoch_gpmp_iter_kron_gen_dm(
+                            _lib.ptr(sd.scale_tril_kron_gen), _lib.ptr(self.Sigma_inv), C.byref(nd),
+                            _lib.ptr(self._particle_means), _lib.ptr(self._dm_rows()), _lib.ptr(self.costs), _lib.ptr(self._w_buf),
+                            _lib.ptr(self._is_vec), _lib.ptr(self.free_flags), _lib.ptr(pre) if last else None,
+                            _lib.ptr(traj_out) if last else None, P, S, H,
+                            C.byref(self.robot.desc), fields, nf, C.byref(gp), self.temperature, self.step_size, _lib.stream_ptr()))
+                        self._x_dm_fresh = True
+                        continue
+                    self._x_dm_fresh = False
                     _lib.check(lib.mpb_stoch_gpmp_iter_kron_gen_ex(
                         _lib.ptr(sd.scale_tril_kron_gen), _lib.ptr(self.Sigma_inv), int(self._sinv_structured), C.byref(nd),
                         _lib.ptr(self._particle_means), _lib.ptr(self.state_samples), _lib.ptr(self.costs), _lib.ptr(self._w_buf),
@@ -217,6 +280,7 @@ class StochGPMP(OptimizationPlanner):
                 e = eps[it]
             _lib.require_f32(e)
             assert e.shape == (S, P, M) and e.is_contiguous()
+            self._x_dm_fresh = False
             if self._sample_dist.scale_tril_kron is not None:
                 _lib.check(lib.mpb_stoch_gpmp_iter_kron(
                     _lib.ptr(self._sample_dist.scale_tril_kron), _lib.ptr(self._sample_dist.scale_tril_kron_tc),
@@ -233,8 +297,7 @@ class StochGPMP(OptimizationPlanner):
                 C.byref(self.robot.desc), fields, nf, C.byref(gp), self.temperature, self.step_size, _lib.stream_ptr()))
         self._weights = self._w_buf.view(P, S, 1, 1)
         self._sample_dist.means = self._particle_means.view(P, -1)
-        self._recent_control_samples = self.state_samples[..., -self.n_dof:]
-        self._recent_state_trajectories = self.state_samples[..., :self.n_dof]
+        self._has_recent = True         # _recent_control_samples / _recent_state_trajectories: views of state_samples, on demand
         self._recent_control_particles = vel_mean
         self._recent_state_particles = pos_mean
         self._recent_weights = self._weights
@@ -265,6 +328,25 @@ class StochGPMP(OptimizationPlanner):
         rec(0)
         split = self._sample_dist.scale_tril_split
         mv_fused = False
+        if eps is None and self._use_dof_major(fields, nf):
+            # the three kernels of mpb_stoch_gpmp_iter_kron_gen_dm, one C call each
+            nd = self._sample_dist.noise.next()
+            xdm = self._dm_rows()
+            _lib.check(lib.mpb_sample_gp_kron_gen_dm(_lib.ptr(self._sample_dist.scale_tril_kron_gen), _lib.ptr(self._particle_means),
+                                                     C.byref(nd), _lib.ptr(xdm), P, S, H, self.n_dof,
+                                                     _lib.ptr(self.Sigma_inv), _lib.ptr(self._is_vec), None, st))
+            rec(1)
+            rec(2)
+            _lib.check(lib.mpb_cost_eval_dm(_lib.ptr(xdm), P * S, H, C.byref(self.robot.desc), fields, nf,
+                                            C.byref(gp), _lib.ptr(self._is_vec), S, self.temperature, _lib.ptr(self.costs), None,
+                                            _lib.ptr(self.free_flags), st))
+            rec(3)
+            _lib.check(lib.mpb_softmax_update_dm(_lib.ptr(self.costs), _lib.ptr(xdm), _lib.ptr(self._particle_means),
+                                                 _lib.ptr(self._w_buf), None, self.temperature, self.step_size, None, P, S, H, D, st))
+            rec(4)
+            self._x_dm_fresh = True
+            return
+        self._x_dm_fresh = False
         if eps is None and self._sample_dist.scale_tril_kron_gen is not None and self._sinv_structured:
             # the tcgen05 sampler computes Sigma^-1 mu on one extra warp per CTA (as mpb_stoch_gpmp_iter_kron_gen runs it)
             nd = self._sample_dist.noise.next()
