@@ -27,8 +27,9 @@
 //   warps 0-7    epilogue (TMEM lane quadrant x half of the columns): tcgen05.ld 32 columns, fma with mu, 32 coalesced stores
 //   warp 8       factor loader (one lane: eight 8 KiB bulk-async copies per dof, double buffered, mbarrier complete_tx)
 //   warp 9       MMA issuer (warp-uniform loop, one elected lane): 24 tcgen05.mma.kind::f16 (M128 x N64 x K16) per unit
-//   warps 10-25  noise producers: four Philox calls per thread and unit, 8-byte conflict-free stores into the canonical
-//                K-major (no swizzle) operand tiles of a 3-stage ring (a stage = the whole K = 128 of a unit, 32 KiB)
+//   warps 10-25  noise producers, two groups of eight filling alternate units: eight Philox calls per thread and unit,
+//                8-byte conflict-free stores into the canonical K-major (no swizzle) operand tiles of a 3-stage ring (a
+//                stage = the whole K = 128 of a unit, 32 KiB)
 //   warp 26      (optional) y_p = Sigma^-1 mu_p and the copy of mu, as in sample_gp_kron_gen_kernel
 #include <cuda_fp16.h>
 
@@ -51,7 +52,15 @@ struct GenDmCfg {
     static constexpr uint32_t B_STAGE = NKC * 2 * B_TILE;    // one unit: 32 KiB
     static constexpr uint32_t A_BUF = NKC * 2 * A_TILE;      // one dof: 64 KiB
     static constexpr uint32_t A_IMG_STAGE = DOF * 2 * A_TILE;    // stride between k-chunks in the host image (sample_gp_kron_gen.cu)
-    static constexpr int B_STAGES = 3, A_BUFS = 2, NSETS = 8;
+#ifndef MPB_DM_GROUPS
+#define MPB_DM_GROUPS 2
+#endif
+    // producer groups filling alternate units; 2 groups: 3-stage noise ring + double-buffered factor, 4 groups: 5-stage ring +
+    // one factor buffer (a dof switch then waits for the 64 KiB load once; the deeper ring keeps the producers busy meanwhile).
+    // Measured at C4 (profiles/r02_k1_dm.txt): 4 groups pace the units 8 % faster (3 340 vs 3 640 cycles) but take twice as
+    // long to fill the pipeline (first MMA after 16 500 instead of 7 000 cycles): 56.3 vs 55.2 us per launch -- 2 it is.
+    static constexpr int NGROUPS = MPB_DM_GROUPS;
+    static constexpr int B_STAGES = NGROUPS == 4 ? 5 : 3, A_BUFS = NGROUPS == 4 ? 1 : 2, NSETS = 8;
     static constexpr int EPI_WARPS = 8, LOAD_WARP = 8, MMA_WARP = 9, FIRST_PROD_WARP = 10, PROD_WARPS = 16;
     static constexpr int MV_WARP = FIRST_PROD_WARP + PROD_WARPS;
     static constexpr int THREADS = (MV_WARP + 1) * 32;
@@ -120,7 +129,7 @@ sample_gp_kron_gen_dm_kernel(const GenDmArgs a, const NoiseArgs noise) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
     uint64_t* a_full = bars;                           // [A_BUFS] factor of a dof landed
     uint64_t* a_empty = a_full + C::A_BUFS;            // [A_BUFS] the MMAs of the last unit that read it completed
-    uint64_t* b_full = a_empty + C::A_BUFS;            // [B_STAGES] noise of a unit written (PROD_WARPS arrivals)
+    uint64_t* b_full = a_empty + C::A_BUFS;            // [B_STAGES] noise of a unit written (PROD_WARPS / 2 arrivals: one group)
     uint64_t* b_empty = b_full + C::B_STAGES;          // [B_STAGES]
     uint64_t* acc_full = b_empty + C::B_STAGES;        // [NSETS] accumulator of a unit complete
     uint64_t* acc_empty = acc_full + C::NSETS;         // [NSETS] accumulator read by the eight epilogue warps
@@ -131,11 +140,11 @@ sample_gp_kron_gen_dm_kernel(const GenDmArgs a, const NoiseArgs noise) {
     const bool spin = (a.dbg & 64) != 0;
     auto WAIT = [&](uint64_t* bar, uint32_t parity) { if (spin) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity); };
     auto stamp = [&](int ordinal, int ev) {
-        if (a.trace && blockIdx.x == 0 && ordinal < 24) a.trace[8 * ordinal + ev] = clock64();
+        if (a.trace && blockIdx.x == 0 && ordinal < 24) a.trace[8 * ordinal + ev] = clock64();   // ev >= 128: second bank (slot + 24 * 8)
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::A_BUFS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], C::PROD_WARPS); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], C::PROD_WARPS / C::NGROUPS); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < C::NSETS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], C::EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -268,69 +277,65 @@ sample_gp_kron_gen_dm_kernel(const GenDmArgs a, const NoiseArgs noise) {
         }
     } else if (warp >= C::FIRST_PROD_WARP && warp < C::MV_WARP) {
         // ================================ noise producers ==============================
-        // thread = one sample row (8-sample group sgrp, row r8) x two k-chunks (kq) x the 4-k groups of parity par
+        // Two GROUPS of eight producer warps fill alternate units (group g: units u0 + g, u0 + g + 2, ...).  With one group
+        // of sixteen, all producers ran in lockstep through the per-unit overhead (barrier wait, index arithmetic, operand
+        // stores, arrive: ~1 400 of 3 700 cycles per unit, measured with the generation switched off) and every scheduler
+        // idled through it; two groups are half a unit out of phase, so one computes while the other is in its overhead,
+        // and the overhead is paid once per eight Philox calls of a thread instead of once per four.
+        // thread = one sample row (8-sample group sgrp, row r8) x four k-chunks (kh) x the 4-k groups of parity par
         const int pw = warp - C::FIRST_PROD_WARP;
+        constexpr int GW = C::PROD_WARPS / C::NGROUPS;            // warps per group: 8 or 4
+        constexpr int KH = GW / 4;                                // k-halves a group splits a unit into: 2 or 1
+        constexpr int NB = 4 / KH;                                // batches of four Philox calls per thread and unit: 2 or 4
+        const int grp = pw / GW, gw = pw % GW;
         const int r8 = lane & 7, par = (lane >> 3) & 1, g1 = lane >> 4;
-        const int sgrp = (pw & 3) * 2 + g1, kq = pw >> 2;
-        int bs = 0;
-        uint32_t bph = 0;
-        int j = u0 / a.ntiles, t = u0 - j * a.ntiles;
-        long long p = 0, s = 0;
-        bool fresh = true;                                        // (p, s) must be computed from the row index
-        uint2 hi[4], lo[4];
-        // the operand values of the thread's next unit (four Philox calls generated together: their dependency chains
-        // interleave); advances (j, t) to the unit after it
-        auto generate = [&]() {
-            if (t == a.ntiles) { t = 0; ++j; fresh = true; }
+        const int sgrp = (gw & 3) * 2 + g1, kh = gw >> 2;
+        for (int u = u0 + grp; u < u1; u += C::NGROUPS) {
+            const int ord = u - u0;
+            const int bs = ord % C::B_STAGES;
+            const uint32_t bph = (uint32_t)(ord / C::B_STAGES) & 1u;
+            const int j = u / a.ntiles, t = u - j * a.ntiles;
             long long n = (long long)t * C::TS + sgrp * 8 + r8;
-            if (fresh || n >= a.Ntot) {                           // rows past the end are never stored: clamp
-                if (n >= a.Ntot) n = a.Ntot - 1;
-                p = n / a.S;
-                s = n - p * a.S;
-                fresh = false;
-            } else {                                              // the next tile of the same dof: 64 rows further
-                s += C::TS;
-                while (s >= a.S) { s -= a.S; ++p; }
-            }
+            if (n >= a.Ntot) n = a.Ntot - 1;                      // rows past the end are never stored
+            const long long p = n / a.S, s = n - p * a.S;
             const unsigned long long grow = (unsigned long long)((((noise.s_off + s) * noise.P_glob + noise.p_off + p) * DOF + j) * (C::NOUT / 4));
-            if (!(a.dbg & 1)) {
-                float4 e[4];
+            const uint32_t stage = smem_u32(sm + C::OFF_B + bs * C::B_STAGE);
+            bool waited = false;
+#pragma unroll 1
+            for (int b = 0; b < NB; ++b) {                        // batches of four Philox calls (interleaved chains)
+                uint2 hi[4], lo[4];
+                if (!(a.dbg & 1)) {
+                    float4 e[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int kc = 2 * kq + (i >> 1), q = 2 * (i & 1) + par;
-                    e[i] = philox_normal4(grow + (unsigned)(kc * 4 + q), noise);
+                    for (int i = 0; i < 4; ++i) {
+                        const int kc = (8 / KH) * kh + 2 * b + (i >> 1), q = 2 * (i & 1) + par;
+                        e[i] = philox_normal4(grow + (unsigned)(kc * 4 + q), noise);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) split4_f16_dm(e[i], hi[i], lo[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) hi[i] = lo[i] = make_uint2(0u, 0u);
+                }
+                if (!waited) {
+                    if (gw == 0 && lane == 0) stamp(ord, 0);
+                    WAIT(&b_empty[bs], bph ^ 1);
+                    if (gw == 0 && lane == 0) stamp(ord, 6);
+                    waited = true;
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) split4_f16_dm(e[i], hi[i], lo[i]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) hi[i] = lo[i] = make_uint2(0u, 0u);
+                for (int i = 0; i < 4 && !(a.dbg & 8); ++i) {
+                    const int kc = (8 / KH) * kh + 2 * b + (i >> 1), q = 2 * (i & 1) + par;
+                    // (sample row, k) -> core matrix (row / 8, k / 8): 16-byte rows, K groups 128 B apart, row groups 256 B
+                    const uint32_t off = stage + (uint32_t)(kc * (2 * C::B_TILE)) + (uint32_t)(sgrp * 256 + (q >> 1) * 128 + r8 * 16 + (q & 1) * 8);
+                    st_shared_v2_dm(off, hi[i]);
+                    st_shared_v2_dm(off + C::B_TILE, lo[i]);
+                }
             }
-            ++t;
-        };
-        if (u0 < u1) generate();
-        for (int u = u0; u < u1; ++u) {
-            if (pw == 0 && lane == 0) stamp(u - u0, 0);
-            WAIT(&b_empty[bs], bph ^ 1);
-            if (pw == 0 && lane == 0) stamp(u - u0, 6);
-            const uint32_t stage = smem_u32(sm + C::OFF_B + bs * C::B_STAGE);
-#pragma unroll
-            for (int i = 0; i < 4 && !(a.dbg & 8); ++i) {
-                const int kc = 2 * kq + (i >> 1), q = 2 * (i & 1) + par;
-                // (sample row, k) -> core matrix (row / 8, k / 8): 16-byte rows, K groups 128 B apart, row groups 256 B
-                const uint32_t off = stage + (uint32_t)(kc * (2 * C::B_TILE)) + (uint32_t)(sgrp * 256 + (q >> 1) * 128 + r8 * 16 + (q & 1) * 8);
-                st_shared_v2_dm(off, hi[i]);
-                st_shared_v2_dm(off + C::B_TILE, lo[i]);
-            }
-            // The next unit's values are generated BEFORE this unit's stores are fenced and announced: the producer warps
-            // run in lockstep (one barrier per stage), and with the fence right behind the stores every scheduler sat idle
-            // for its latency once per unit.  The MMAs of this unit start one generation later -- the 3-stage ring covers it.
-            if (u + 1 < u1) generate();
             fence_async_proxy();
             __syncwarp();
             if (lane == 0) mbar_arrive(&b_full[bs]);
-            if (pw == 0 && lane == 0) stamp(u - u0, 1);
-            if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
+            if (gw == 0 && lane == 0) stamp(ord, 1);
         }
     } else if (warp == C::MV_WARP && a.y && !(a.dbg & 32)) {
         // ================================ Sigma^-1 mu ===================================

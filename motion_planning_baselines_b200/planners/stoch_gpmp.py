@@ -159,10 +159,10 @@ class StochGPMP(OptimizationPlanner):
 
     def _use_dof_major(self, fields, nf):
         """The dof-major fused iteration: tcgen05 sampler with the mat-vec warp + a cost-kernel instance that reads the rows
-        in place (7-dof chain, H = 64, primitive fields).  Opt-in (MPB_X_DM=1): bit-identical to the reference-layout
-        iteration and, as measured on the B200, no faster -- both samplers are bound by the noise generation."""
+        in place (7-dof chain, H = 64, primitive fields).  Bit-identical to the reference-layout iteration (tests/
+        test_gpu_dof_major.py); MPB_X_DM=0 keeps the reference layout (A/B timing, tests)."""
         import os
-        if os.environ.get('MPB_X_DM', '0') != '1':
+        if os.environ.get('MPB_X_DM', '1') == '0':
             return False
         sd = self._sample_dist
         return (sd.scale_tril_kron_gen is not None and self._sinv_structured

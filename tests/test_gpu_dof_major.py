@@ -95,7 +95,7 @@ def test_dm_iteration_is_bit_identical_to_the_natural_one(obstacles_of, P, dev, 
         pl._noise.offset = 0
         if mode == '1':
             gp, fields, nf, _ = pl.cost._build()
-            assert pl._use_dof_major(fields, nf), 'MPB_X_DM=1 must select the dof-major iteration for the 7-dof arm at H = 64'
+            assert pl._use_dof_major(fields, nf), 'the dof-major iteration must be the default for the 7-dof arm at H = 64'
         trajs = [pl.optimize(opt_iters=1).clone() for _ in range(3)]
         out[mode] = dict(trajs=trajs, costs=pl.costs.clone(), w=pl._w_buf.clone(), free=pl.free_flags.clone(),
                          x=pl.state_samples.clone(), mu=pl._particle_means.clone(), rec=[t.clone() for t in pl.get_recent_samples()])
