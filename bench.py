@@ -207,6 +207,9 @@ def workload_config(n):
                 noise='drawn inside the sampling kernel (Philox4x32-10 keyed on the global element index), as the reference '
                       'draws inside MultiMPPrior.sample; the injected-noise variant (8 rotating 117 MB buffers resident in HBM) '
                       'is reported under "injected_noise"',
+                sample_rows='kept dof-major ([dof][2H]) between the three kernels of the iteration, an internal layout with '
+                            'bit-identical values (tests/test_gpu_dof_major.py); planner.state_samples converts to the '
+                            "reference's [H][2 dof] on demand, outside the iteration (MPB_X_DM=0: reference layout throughout)",
                 l2='per-step outputs (117 MB of samples; 235 MB with injected noise) exceed / fill the 126 MB L2 and every '
                    'step overwrites them')
 
@@ -354,6 +357,7 @@ def main():
     mv_in_k1 = planner_uses_gen and planner._sinv_structured
     launches_per_step = 3 if mv_in_k1 else 4
     value = world * P * S * K / (ms_total * 1e-3)
+    dof_major = bool(getattr(planner, '_x_dm_fresh', False))      # the timed steps kept their sample rows dof-major (default for C4)
     free_frac = float(planner.free_flags.float().mean())
     # K3 reads only the sample rows whose weight is non-zero: count them (roofline on bytes actually needed)
     rows_nonzero = int((planner._w_buf != 0).sum())
@@ -498,7 +502,11 @@ def main():
         flop_k1 = DOF * (2 * H) * (2 * H + 1)       # 7 independent [128,128] triangular mat-vecs = 115,584 flop / sample
         bytes_k1 = M * 4 * (2 if k1_reads_eps else 1)
         gen = (not k1_reads_eps) and planner_uses_gen
-        k1_name = ('sample_gp_kron_gen_kernel<7,32> (K1: tcgen05 kind::f16 with the factor as the M = 128 operand, 32-sample tiles, two '
+        dm = gen and dof_major
+        k1_name = ('sample_gp_kron_gen_dm_kernel<7> (K1: tcgen05 kind::f16, work unit = 64 samples x ONE dof with the factor as the M = 128 '
+                   'operand, 8-deep accumulator ring in TMEM, factor of a dof bulk-loaded once per CTA, dof-major sample rows stored '
+                   'straight from registers, two groups of eight Philox producer warps, Sigma^-1 mu on an extra warp)' if dm else
+                   'sample_gp_kron_gen_kernel<7,32> (K1: tcgen05 kind::f16 with the factor as the M = 128 operand, 32-sample tiles, two '
                    'sets of 7 accumulators in TMEM (the epilogue of a tile overlaps the MMAs of the next), warp-specialised Philox '
                    'producers, bulk-async factor loads and row stores, Sigma^-1 mu on an extra warp)' if gen else
                    'sample_gp_kron_mma_kernel<7,64,%s> (K1: structured GP sampler, warp MMA fp16x2 split%s)'
@@ -508,7 +516,10 @@ def main():
                   algorithmic_bytes_per_sample=bytes_k1, algorithmic_flop_per_sample=flop_k1,
                   note='HBM floor = x written' + (' + eps read' if k1_reads_eps else '') + '; the factor decouples over the 7 dofs '
                        '(exact zeros, verified bit-exactly at setup): 115,584 flop / sample instead of the dense 803,712'
-                       + ('; measured limiters (profiles/r02_k1_gen_*.txt, DESIGN 4c): the MMAs themselves -- three fp16 MMAs per '
+                       + ('; measured limiter (profiles/r02_k1_dm.txt, DESIGN 4f): the noise generation on the CUDA cores -- 29.4 M '
+                          'normals, Philox4x32-10 + Box-Muller + fp16 split = ~35 instructions per normal on pipes that take a warp '
+                          'instruction every second cycle (issue floor 0.035 ms); the MMAs of a unit take 1 400 of its 3 600 cycles' if dm else
+                          '; measured limiters (profiles/r02_k1_gen_*.txt, DESIGN 4c): the MMAs themselves -- three fp16 MMAs per '
                           'k-step for the two-term split, each fetching its 4 KiB factor tile from shared memory (55 cycles per '
                           'M128 x N32 x K16 MMA: floor 0.047 ms) -- and the noise generation on the CUDA cores (29.4 M normals: '
                           'Philox4x32-10 + Box-Muller + fp16 split = ~110 instructions per 4: issue floor 0.023 ms)' if gen else ''))
@@ -522,8 +533,9 @@ def main():
         a2 = flop_k2 * n_samp / (stage[2] * 1e-3) / 1e12
         slots = ncu_issue_slots('cost_eval_chain2')
         issue_peak = 148 * 4 * sm_mhz_peak * 1e6            # warp instructions / s: 4 schedulers per SM, one issue per cycle
-        k2 = dict(kernel='cost_eval_chain2_kernel<7,10,2,false> (K2 packed: FK + collision + GP cost + IS dot, two waypoints per lane on '
-                         'FFMA2 / FADD2 / FMUL2; sphere-only instance with the link-frame cull)', ms=float(stage[2]), bound='fp32',
+        k2 = dict(kernel='cost_eval_chain2_kernel<7,10,2,false,true%s> (K2 packed: FK + collision + GP cost + IS dot, two waypoints per lane '
+                         'on FFMA2 / FADD2 / FMUL2; sphere-only instance with the link-frame cull%s)'
+                         % ((',DM', '; reads the dof-major rows in place') if dm else ('', '')), ms=float(stage[2]), bound='fp32',
                   achieved=a2, peak=fp32_measured, unit='TFLOP/s', frac=a2 / fp32_measured,
                   peak_nominal=fp32_nominal, frac_of_nominal=a2 / fp32_nominal, algorithmic_flop_per_sample=flop_k2,
                   hbm_gbs=M * 4 * n_samp / (stage[2] * 1e-3) / 1e9, hbm_frac=M * 4 * n_samp / (stage[2] * 1e-3) / 1e9 / pk['hbm'],
@@ -541,7 +553,7 @@ def main():
                                          'are counted twice; round 1 generic kernel: 9,467 warp instructions per sample')
         bytes_k3 = (rows_nonzero * M * 4 + 3 * P * M * 4 + 2 * n_samp * 4)
         a3 = bytes_k3 / (stage[3] * 1e-3) / 1e9
-        k3 = dict(kernel='softmax_update_kernel (K3)', ms=float(stage[3]), bound='latency', achieved=a3, peak=pk['hbm'], unit='GB/s',
+        k3 = dict(kernel='softmax_update_kernel (K3%s)' % (', dof-major rows' if dm else ''), ms=float(stage[3]), bound='latency', achieved=a3, peak=pk['hbm'], unit='GB/s',
                   frac=a3 / pk['hbm'], bytes_needed=bytes_k3, rows_with_nonzero_weight=rows_nonzero, rows_total=n_samp,
                   note='bytes actually needed: rows whose softmax weight is non-zero (nearly one-hot at T = 1) + means + costs / '
                        'weights; a 12 us launch + DRAM-latency chain, not a throughput kernel')
