@@ -59,9 +59,13 @@ struct GenDmCfg {
     // one factor buffer (a dof switch then waits for the 64 KiB load once; the deeper ring keeps the producers busy meanwhile).
     // Measured at C4 (profiles/r02_k1_dm.txt): 4 groups pace the units 8 % faster (3 340 vs 3 640 cycles) but take twice as
     // long to fill the pipeline (first MMA after 16 500 instead of 7 000 cycles): 56.3 vs 55.2 us per launch -- 2 it is.
+    // 3 groups of 8 (24 producer warps; the 1 024-thread CTA then leaves room for only 4 epilogue warps): the producers pace
+    // the units 21 % faster (2 870 cycles) but four epilogue warps need 3 500 per unit and become the bound: 68.2 us.
     static constexpr int NGROUPS = MPB_DM_GROUPS;
-    static constexpr int B_STAGES = NGROUPS == 4 ? 5 : 3, A_BUFS = NGROUPS == 4 ? 1 : 2, NSETS = 8;
-    static constexpr int EPI_WARPS = 8, LOAD_WARP = 8, MMA_WARP = 9, FIRST_PROD_WARP = 10, PROD_WARPS = 16;
+    static constexpr int B_STAGES = NGROUPS >= 3 ? 5 : 3, A_BUFS = NGROUPS >= 3 ? 1 : 2, NSETS = 8;
+    static constexpr int GW = NGROUPS == 4 ? 4 : 8;          // producer warps per group (3 groups: 24 producer warps, 4 epilogue warps)
+    static constexpr int EPI_WARPS = NGROUPS == 3 ? 4 : 8, LOAD_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1, FIRST_PROD_WARP = EPI_WARPS + 2;
+    static constexpr int PROD_WARPS = NGROUPS * GW;
     static constexpr int MV_WARP = FIRST_PROD_WARP + PROD_WARPS;
     static constexpr int THREADS = (MV_WARP + 1) * 32;
     static constexpr uint32_t OFF_A = 0;
@@ -222,7 +226,8 @@ sample_gp_kron_gen_dm_kernel(const GenDmArgs a, const NoiseArgs noise) {
     } else if (warp < C::EPI_WARPS) {
         // ================================ epilogue =====================================
         // warp (q4, half): TMEM lane quadrant q4, columns (= samples) 32 half .. 32 half + 31 of the unit's accumulator
-        const int q4 = warp & 3, half = warp >> 2;
+        constexpr int NH = 8 / C::EPI_WARPS;                    // halves (32 columns) a warp handles per unit: 1 or 2
+        const int q4 = warp & 3;
         const int n_out = 32 * q4 + lane;                       // TMEM lane = accumulator row = column inside the dof block
         const float* inv_scale_g = reinterpret_cast<const float*>(a.Limg + (size_t)C::NKC * C::A_IMG_STAGE);
         const bool one_particle = (a.S % C::TS) == 0;           // a tile never straddles two particles
@@ -231,9 +236,15 @@ sample_gp_kron_gen_dm_kernel(const GenDmArgs a, const NoiseArgs noise) {
         for (int u = u0; u < u1; ++u, ++ord) {
             const int j = u / a.ntiles, t = u - j * a.ntiles;
             const int set = ord % C::NSETS;
-            const long long row0 = (long long)t * C::TS + 32 * half;        // first row of this warp's half
             const float inv_scale = __ldg(inv_scale_g + j);
             const int mcol = DOF * n_out + j;                   // natural column of (row n, dof j)
+            WAIT(&acc_full[set], ((uint32_t)(ord / C::NSETS)) & 1u);
+            tc_fence_after();
+            if (threadIdx.x == 0) stamp(ord, 4);
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh) {
+            const int half = (warp >> 2) + hh;
+            const long long row0 = (long long)t * C::TS + 32 * half;        // first row of this half
             long long rows_ll = a.Ntot - row0;
             const int rows = rows_ll > 32 ? 32 : (int)rows_ll;  // may be <= 0 in the last tile
             // particle of the first row; it advances where a row index crosses a multiple of S (no division per row: the
@@ -241,9 +252,6 @@ sample_gp_kron_gen_dm_kernel(const GenDmArgs a, const NoiseArgs noise) {
             const long long rowc = rows > 0 ? row0 : a.Ntot - 1;
             int p = (int)(rowc / a.S), rem = (int)(rowc - (long long)p * a.S);
             float m = __ldg(a.mu + (size_t)p * C::M + mcol);
-            WAIT(&acc_full[set], ((uint32_t)(ord / C::NSETS)) & 1u);
-            tc_fence_after();
-            if (threadIdx.x == 0) stamp(ord, 4);
             const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * C::TS + 32 * half);
             float v[32];
             if (!(a.dbg & 16)) {
@@ -252,9 +260,11 @@ sample_gp_kron_gen_dm_kernel(const GenDmArgs a, const NoiseArgs noise) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) v[c] = 0.f;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[set]);        // the accumulator is in registers: hand it back before the stores
+            if (hh == NH - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[set]);    // the accumulator is in registers: hand it back before the stores
+            }
             float* xo = a.x + (size_t)row0 * C::M + (size_t)j * C::NOUT + n_out;
             if (one_particle && rows == 32) {
                 if (st_on) {
@@ -273,6 +283,7 @@ sample_gp_kron_gen_dm_kernel(const GenDmArgs a, const NoiseArgs noise) {
                     if (c < rows && st_on) xo[(size_t)c * C::M] = fmaf(v[c], inv_scale, m);
                 }
             }
+            }
             if (threadIdx.x == 0) stamp(ord, 5);
         }
     } else if (warp >= C::FIRST_PROD_WARP && warp < C::MV_WARP) {
@@ -284,7 +295,7 @@ sample_gp_kron_gen_dm_kernel(const GenDmArgs a, const NoiseArgs noise) {
         // and the overhead is paid once per eight Philox calls of a thread instead of once per four.
         // thread = one sample row (8-sample group sgrp, row r8) x four k-chunks (kh) x the 4-k groups of parity par
         const int pw = warp - C::FIRST_PROD_WARP;
-        constexpr int GW = C::PROD_WARPS / C::NGROUPS;            // warps per group: 8 or 4
+        constexpr int GW = C::GW;                                 // warps per group: 8 or 4
         constexpr int KH = GW / 4;                                // k-halves a group splits a unit into: 2 or 1
         constexpr int NB = 4 / KH;                                // batches of four Philox calls per thread and unit: 2 or 4
         const int grp = pw / GW, gw = pw % GW;
