@@ -71,21 +71,22 @@ def test_dm_sampler_mat_vec_warp(dev):
 
 
 def build_arm(obstacles_of, P, dev):
-    """The C4 Stoch-GPMP problem (Panda, 64 samples x 64 waypoints) against the obstacles of configuration `obstacles_of`."""
+    """The C4 Stoch-GPMP problem (Panda, 64 samples x 64 waypoints) against the obstacles of configuration `obstacles_of`
+    ('C4+C5': two fields, the C4 spheres and the C5 boxes -- the mixed sphere / box instance of the cost kernel)."""
     from motion_planning_baselines_b200 import configs
     from motion_planning_baselines_b200.fields import CollisionField
     from motion_planning_baselines_b200.planners import StochGPMP
     from motion_planning_baselines_b200.robots import Robot
     cfg = configs.config('C4')
     robot = Robot(cfg['robot'], dt=cfg['dt'], tensor_args=dev)
-    field = CollisionField(configs.config(obstacles_of)['obstacles'], tensor_args=dev)
+    fields = [CollisionField(configs.config(name)['obstacles'], tensor_args=dev) for name in obstacles_of.split('+')]
     torch.manual_seed(2024)
     return StochGPMP(robot=robot, n_dof=7, n_support_points=64, num_particles_per_goal=P, opt_iters=1, dt=cfg['dt'],
                      start_state=torch.tensor(cfg['start']).to(**dev), multi_goal_states=torch.tensor(cfg['goal']).to(**dev).unsqueeze(0),
-                     collision_fields=[field], tensor_args=dev, num_samples=64, **cfg['params'])
+                     collision_fields=fields, tensor_args=dev, num_samples=64, **cfg['params'])
 
 
-@pytest.mark.parametrize('obstacles_of,P', [('C4', 512), ('C5', 96), ('C4', 3)])
+@pytest.mark.parametrize('obstacles_of,P', [('C4', 512), ('C5', 96), ('C4', 3), ('C4+C5', 40)])
 def test_dm_iteration_is_bit_identical_to_the_natural_one(obstacles_of, P, dev, monkeypatch):
     """Three optimize() calls (C4: the bench shape, 16 spheres; C5: the table + shelf boxes), dof-major against MPB_X_DM=0."""
     out = {}
