@@ -402,6 +402,234 @@ sample_gp_kron_gen_dm_kernel(const GenDmArgs a, const NoiseArgs noise) {
     if (warp == C::MMA_WARP) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// ---- variant with 24 producer warps (the default; MPB_DM_VARIANT=2 selects the kernel above) ---------------------------------
+// Measured at C4: 55.0 us per launch against 57.1, step 0.2378 against 0.2401 ms (profiles/r02_k1_dm.txt).
+// The generation is bound by thread-level parallelism (three groups of eight producer warps pace the units 21 % faster than
+// two), but a CTA holds 32 warps: with a loader, an MMA and a mat-vec warp next to eight epilogue warps only 21 are left.
+// Here the dedicated warps are folded into the others: warps 0-7 are the epilogue (and share the Sigma^-1 mu rows at the
+// start), warps 8-31 are three producer groups; group g owns operand stage g; warp 0 of a group issues the MMAs of the
+// unit its group has just written (it waits for its group's arrivals, the accumulator and the factor, then one elected lane
+// issues the 24 MMAs); the factors of the CTA's (at most two) dofs are bulk-loaded at the start by the first producer warp.
+template <int DOF>
+struct GenDm3Cfg {
+    static constexpr int NOUT = 128, TS = 64, KC = 16, NKC = NOUT / KC, M = NOUT * DOF;
+    static constexpr uint32_t B_TILE = TS * KC * 2, A_TILE = NOUT * KC * 2;
+    static constexpr uint32_t B_STAGE = NKC * 2 * B_TILE, A_BUF = NKC * 2 * A_TILE, A_IMG_STAGE = DOF * 2 * A_TILE;
+    static constexpr int NGROUPS = 3, GW = 8, B_STAGES = NGROUPS, A_BUFS = 2, NSETS = 8;
+    static constexpr int EPI_WARPS = 8, FIRST_PROD_WARP = EPI_WARPS, PROD_WARPS = NGROUPS * GW;
+    static constexpr int THREADS = (EPI_WARPS + PROD_WARPS) * 32;
+    static constexpr uint32_t OFF_A = 0, OFF_B = OFF_A + A_BUFS * A_BUF, OFF_BAR = OFF_B + B_STAGES * B_STAGE;
+    static constexpr uint32_t SMEM = OFF_BAR + 256 + 128;
+    static constexpr uint32_t TMEM_COLS = 512;
+    static_assert(THREADS == 1024 && SMEM <= 227 * 1024, "one full CTA per SM");
+};
+
+template <int DOF>
+__global__ void __launch_bounds__(GenDm3Cfg<DOF>::THREADS, 1)
+sample_gp_kron_gen_dm3_kernel(const GenDmArgs a, const NoiseArgs noise) {
+    using C = GenDm3Cfg<DOF>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+    uint64_t* a_full = bars;                           // [A_BUFS] factor of the CTA's first / second dof landed (loaded once)
+    uint64_t* b_full = a_full + C::A_BUFS;             // [B_STAGES] noise of a unit written (GW arrivals: the stage's group)
+    uint64_t* b_empty = b_full + C::B_STAGES;          // [B_STAGES] the MMAs that read the stage completed
+    uint64_t* acc_full = b_empty + C::B_STAGES;        // [NSETS]
+    uint64_t* acc_empty = acc_full + C::NSETS;         // [NSETS] EPI_WARPS arrivals
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(acc_empty + C::NSETS);
+
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::A_BUFS; ++s) mbar_init(&a_full[s], 1);
+        for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], C::GW); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < C::NSETS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], C::EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_base_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+    pdl_wait();
+
+    const long long U = (long long)DOF * a.ntiles;
+    const int u0 = (int)(U * blockIdx.x / gridDim.x), u1 = (int)(U * (blockIdx.x + 1) / gridDim.x);
+    const int j0 = u0 / a.ntiles;                      // the range [u0, u1) holds dof j0 and possibly j0 + 1 (the host checks)
+
+    if (warp < C::EPI_WARPS) {
+        // ================================ Sigma^-1 mu, then the epilogue ================
+        if (a.y) {      // same arithmetic as the mat-vec warp of the other variants; the rows are shared by the eight warps
+            constexpr int MAXP = 4;
+            for (int pb = blockIdx.x; pb < a.P; pb += MAXP * gridDim.x) {
+                int np = 0;
+                const float* mrow[MAXP];
+#pragma unroll
+                for (int q = 0; q < MAXP; ++q) {
+                    const int p = pb + q * gridDim.x;
+                    mrow[q] = a.mu + (size_t)(p < a.P ? p : pb) * C::M;
+                    if (p < a.P) np = q + 1;
+                }
+#pragma unroll 1
+                for (int i = lane + 32 * warp; i < C::M; i += 32 * C::EPI_WARPS) {
+                    float sv[7];
+#pragma unroll
+                    for (int m = 0; m < 7; ++m) {
+                        const int jj = i + (m - 3) * DOF;
+                        sv[m] = (jj >= 0 && jj < C::M) ? __ldg(a.Sinv + (size_t)jj * C::M + i) : 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < MAXP; ++q) {
+                        float mv[7];
+#pragma unroll
+                        for (int m = 0; m < 7; ++m) {
+                            const int jj = i + (m - 3) * DOF;
+                            mv[m] = (jj >= 0 && jj < C::M) ? __ldg(mrow[q] + jj) : 0.f;
+                        }
+                        float hi = 0.f, lo = 0.f;
+#pragma unroll
+                        for (int m = 0; m < 7; ++m) {
+                            const float pr = __fmul_rn(sv[m], mv[m]);
+                            const float e = fmaf(sv[m], mv[m], -pr);
+                            const float t = __fadd_rn(hi, pr);
+                            const float z = __fsub_rn(t, hi);
+                            lo = __fadd_rn(lo, __fadd_rn(__fadd_rn(__fsub_rn(hi, __fsub_rn(t, z)), __fsub_rn(pr, z)), e));
+                            hi = t;
+                        }
+                        if (q < np) {
+                            a.y[(size_t)(pb + q * gridDim.x) * C::M + i] = __fadd_rn(hi, lo);
+                            if (a.mu_copy) a.mu_copy[(size_t)(pb + q * gridDim.x) * C::M + i] = mv[3];
+                        }
+                    }
+                }
+            }
+        }
+        const int q4 = warp & 3, half = warp >> 2;
+        const int n_out = 32 * q4 + lane;
+        const float* inv_scale_g = reinterpret_cast<const float*>(a.Limg + (size_t)C::NKC * C::A_IMG_STAGE);
+        const bool one_particle = (a.S % C::TS) == 0;
+        int ord = 0;
+        for (int u = u0; u < u1; ++u, ++ord) {
+            const int j = u / a.ntiles, t = u - j * a.ntiles;
+            const int set = ord % C::NSETS;
+            const long long row0 = (long long)t * C::TS + 32 * half;
+            const float inv_scale = __ldg(inv_scale_g + j);
+            const int mcol = DOF * n_out + j;
+            long long rows_ll = a.Ntot - row0;
+            const int rows = rows_ll > 32 ? 32 : (int)rows_ll;
+            const long long rowc = rows > 0 ? row0 : a.Ntot - 1;
+            int p = (int)(rowc / a.S), rem = (int)(rowc - (long long)p * a.S);
+            float m = __ldg(a.mu + (size_t)p * C::M + mcol);
+            mbar_wait(&acc_full[set], ((uint32_t)(ord / C::NSETS)) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * C::TS + 32 * half);
+            float v[32];
+            tmem_ld32(taddr, v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[set]);
+            float* xo = a.x + (size_t)row0 * C::M + (size_t)j * C::NOUT + n_out;
+            if (one_particle && rows == 32) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) xo[(size_t)c * C::M] = fmaf(v[c], inv_scale, m);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (rem == a.S) {
+                        rem = 0;
+                        ++p;
+                        if (p < a.P) m = __ldg(a.mu + (size_t)p * C::M + mcol);
+                    }
+                    ++rem;
+                    if (c < rows) xo[(size_t)c * C::M] = fmaf(v[c], inv_scale, m);
+                }
+            }
+        }
+    } else {
+        // ================================ noise producers (+ factor loads, MMA issue) ==
+        const int pw = warp - C::FIRST_PROD_WARP;
+        const int grp = pw / C::GW, gw = pw % C::GW;
+        if (pw == 0 && lane == 0 && u0 < u1) {          // the factors of the CTA's dofs, once
+            const int jl = (u1 - 1) / a.ntiles;
+            for (int b = 0; b <= jl - j0 && b < C::A_BUFS; ++b) {
+                mbar_expect_tx(&a_full[b], C::A_BUF);
+                for (int kc = 0; kc < C::NKC; ++kc)
+                    bulk_load(sm + C::OFF_A + b * C::A_BUF + kc * (2 * C::A_TILE),
+                              a.Limg + (size_t)kc * C::A_IMG_STAGE + (size_t)(j0 + b) * (2 * C::A_TILE), 2 * C::A_TILE, &a_full[b]);
+            }
+        }
+        const bool leader = elect_one_dm();
+        const uint32_t idesc = make_idesc_f16(C::NOUT, C::TS);
+        const uint64_t adesc0 = make_nosw_desc(smem_u32(sm + C::OFF_A), 128u, 256u);
+        const uint64_t bdesc0 = make_nosw_desc(smem_u32(sm + C::OFF_B), 128u, 256u);
+        const uint32_t adesc_lo = (uint32_t)adesc0, bdesc_lo = (uint32_t)bdesc0, desc_hi = (uint32_t)(adesc0 >> 32);
+        const int r8 = lane & 7, par = (lane >> 3) & 1, g1 = lane >> 4;
+        const int sgrp = (gw & 3) * 2 + g1, kh = gw >> 2;
+        const int bs = grp;                                       // a group owns its operand stage
+        const uint32_t stage = smem_u32(sm + C::OFF_B + bs * C::B_STAGE);
+        uint32_t it = 0;                                          // uses of the stage so far
+        for (int u = u0 + grp; u < u1; u += C::NGROUPS, ++it) {
+            const int ord = u - u0;
+            const int j = u / a.ntiles, t = u - j * a.ntiles;
+            long long n = (long long)t * C::TS + sgrp * 8 + r8;
+            if (n >= a.Ntot) n = a.Ntot - 1;
+            const long long p = n / a.S, s = n - p * a.S;
+            const unsigned long long grow = (unsigned long long)((((noise.s_off + s) * noise.P_glob + noise.p_off + p) * DOF + j) * (C::NOUT / 4));
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {
+                uint2 hi[4], lo[4];
+                float4 e[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int kc = 4 * kh + 2 * b + (i >> 1), q = 2 * (i & 1) + par;
+                    e[i] = philox_normal4(grow + (unsigned)(kc * 4 + q), noise);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split4_f16_dm(e[i], hi[i], lo[i]);
+                if (b == 0) mbar_wait(&b_empty[bs], (it & 1u) ^ 1u);      // the MMAs of this group's previous unit are done
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int kc = 4 * kh + 2 * b + (i >> 1), q = 2 * (i & 1) + par;
+                    const uint32_t off = stage + (uint32_t)(kc * (2 * C::B_TILE)) + (uint32_t)(sgrp * 256 + (q >> 1) * 128 + r8 * 16 + (q & 1) * 8);
+                    st_shared_v2_dm(off, hi[i]);
+                    st_shared_v2_dm(off + C::B_TILE, lo[i]);
+                }
+            }
+            fence_async_proxy();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_full[bs]);
+            if (gw == 0) {
+                // this warp issues the unit's MMAs once its group has written the stage
+                const int set = ord % C::NSETS;
+                const int abuf = j - j0;
+                mbar_wait(&b_full[bs], it & 1u);
+                mbar_wait(&acc_empty[set], (((uint32_t)(ord / C::NSETS)) & 1u) ^ 1u);
+                mbar_wait(&a_full[abuf], 0u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(set * C::TS);
+                const uint32_t a_w = adesc_lo + (uint32_t)((abuf * C::A_BUF) >> 4);
+                const uint32_t b_w = bdesc_lo + (uint32_t)((bs * C::B_STAGE) >> 4);
+                if (leader) {
+#pragma unroll
+                    for (int kc = 0; kc < C::NKC; ++kc) {
+                        const uint32_t ahi = a_w + (uint32_t)((kc * 2 * C::A_TILE) >> 4), alo = ahi + (C::A_TILE >> 4);
+                        const uint32_t bhi = b_w + (uint32_t)((kc * 2 * C::B_TILE) >> 4), blo = bhi + (C::B_TILE >> 4);
+                        umma_f16_dm(d, alo, bhi, desc_hi, idesc, kc == 0 ? 0u : 1u);
+                        umma_f16_dm(d, ahi, blo, desc_hi, idesc, 1u);
+                        umma_f16_dm(d, ahi, bhi, desc_hi, idesc, 1u);
+                    }
+                    umma_commit(&b_empty[bs]);
+                    umma_commit(&acc_full[set]);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
 // dof-major <-> natural rows (state_samples accessors, tests): one thread per element, coalesced on the output side
 __global__ void traj_from_dof_major_kernel(const float* __restrict__ xdm, float* __restrict__ x, long long B, int H, int dof, int to_dm) {
     const int M = 2 * H * dof;
@@ -425,6 +653,19 @@ static cudaError_t launch_kron_gen_dm(GenDmArgs& a, const NoiseArgs& noise, cuda
     a.ntiles = (int)((a.Ntot + C::TS - 1) / C::TS);
     const long long U = (long long)DOF * a.ntiles;
     const int grid = U < sm_count() ? (int)U : sm_count();
+    {
+        const char* v = getenv("MPB_DM_VARIANT");
+        // a CTA's range must hold at most two dofs (two factor buffers, loaded once): always true for grid = min(U, SMs >= 7)
+        // default: 24 producer warps with the roles folded (sample_gp_kron_gen_dm3_kernel); MPB_DM_VARIANT=2: the kernel with
+        // dedicated loader / MMA / mat-vec warps and the timing hooks (two producer groups)
+        if (!(v && atoi(v) == 2) && (U + grid - 1) / grid <= (long long)a.ntiles) {
+            using C3 = GenDm3Cfg<DOF>;
+            auto k3 = sample_gp_kron_gen_dm3_kernel<DOF>;
+            const cudaError_t e3 = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3::SMEM);
+            if (e3 != cudaSuccess) return e3;
+            return launch_pdl(k3, dim3(grid), dim3(C3::THREADS), C3::SMEM, st, a, noise);
+        }
+    }
     auto kern = sample_gp_kron_gen_dm_kernel<DOF>;
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;

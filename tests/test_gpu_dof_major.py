@@ -28,10 +28,15 @@ def to_natural(xdm, H, dof):
     return xdm.view(B, dof, H, 2).permute(0, 2, 3, 1).reshape(B, H, 2 * dof).contiguous()
 
 
+@pytest.mark.parametrize('variant', ['default', '2'])
 @pytest.mark.parametrize('d', [7, 3])
 @pytest.mark.parametrize('P,S', [(8, 64), (2, 128), (5, 24), (3, 7), (1, 1), (300, 64)])
-def test_dm_sampler_is_bit_identical_to_the_natural_one(P, S, d, dev):
+def test_dm_sampler_is_bit_identical_to_the_natural_one(P, S, d, variant, dev, monkeypatch):
+    """Both dof-major kernels (default: 24 producer warps, roles folded; MPB_DM_VARIANT=2: dedicated loader / MMA / mat-vec
+    warps) against the reference-layout tcgen05 sampler."""
     from test_gpu_sample_gen import make_prior
+    if variant != 'default':
+        monkeypatch.setenv('MPB_DM_VARIANT', variant)
     prior, means = make_prior(P, dev, d=d)
     assert prior.scale_tril_kron_gen is not None
     H, M = 64, 64 * 2 * d
@@ -51,8 +56,11 @@ def test_dm_sampler_is_bit_identical_to_the_natural_one(P, S, d, dev):
     assert torch.equal(again, xdm)
 
 
-def test_dm_sampler_mat_vec_warp(dev):
+@pytest.mark.parametrize('variant', ['default', '2'])
+def test_dm_sampler_mat_vec_warp(variant, dev, monkeypatch):
     from test_gpu_sample_gen import make_prior
+    if variant != 'default':
+        monkeypatch.setenv('MPB_DM_VARIANT', variant)
     P, S, d, H = 37, 64, 7, 64
     prior, means = make_prior(P, dev, d=d)
     lib, st = _lib.lib(), _lib.stream_ptr()
