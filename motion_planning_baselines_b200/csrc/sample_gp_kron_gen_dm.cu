@@ -18,12 +18,17 @@
 // per sample, no staging in shared memory, no bulk stores -- and the factor of a dof (64 KiB, hi + lo) is loaded into
 // shared memory ONCE per CTA and dof (units are dealt in dof-major order, so a CTA sees one or two dofs) instead of being
 // streamed once per tile: half the MMA time per sample, 1 / 50 of the factor traffic.  The kernel is then bound by the noise
-// generation (Philox4x32-10 + Box-Muller + fp16 split on the CUDA cores), which gets 16 producer warps.
+// generation (Philox4x32-10 + Box-Muller + fp16 split on the CUDA cores), which gets as many producer warps as a CTA can hold.
 //
 // Consumers: the cost kernel and the update kernel read dof-major rows directly (mpb_cost_eval_dm, mpb_softmax_update_dm);
 // mpb_traj_from_dof_major converts for everything else (state_samples accessors, tests).
 //
-// One persistent CTA per SM, warp-specialised (864 threads):
+// Two kernels share this pipeline (bit-identical results, tests/test_gpu_dof_major.py runs both):
+//   sample_gp_kron_gen_dm3_kernel (further down, the DEFAULT): 8 epilogue + 24 producer warps, the loader / MMA / mat-vec
+//                roles folded into them -- 55.0 us per launch at C4;
+//   sample_gp_kron_gen_dm_kernel (next, MPB_DM_VARIANT=2): dedicated loader / MMA / mat-vec warps, 16 producer warps, with the
+//                stage-disable and clock64 trace hooks the measurements in profiles/r02_k1_dm.txt were taken with -- 57.1 us.
+// sample_gp_kron_gen_dm_kernel: one persistent CTA per SM, warp-specialised (864 threads):
 //   warps 0-7    epilogue (TMEM lane quadrant x half of the columns): tcgen05.ld 32 columns, fma with mu, 32 coalesced stores
 //   warp 8       factor loader (one lane: eight 8 KiB bulk-async copies per dof, double buffered, mbarrier complete_tx)
 //   warp 9       MMA issuer (warp-uniform loop, one elected lane): 24 tcgen05.mma.kind::f16 (M128 x N64 x K16) per unit
