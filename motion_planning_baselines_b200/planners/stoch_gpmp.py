@@ -316,6 +316,32 @@ class StochGPMP(OptimizationPlanner):
         self._recent_weights = self._weights
         return self._get_traj()
 
+    def step_fused(self):
+        """One iteration on in-kernel noise as ONE C call (the three launches optimize() issues per iteration, without the
+        bookkeeping around them: no returned clone, no pre-update copy).  Falls back to step_staged() where the fused entry
+        points do not apply."""
+        sd = self._sample_dist
+        P, S, H = self.num_particles, self.num_samples, self.n_support_points
+        gp, fields, nf, _ = self.cost._build()
+        if sd.scale_tril_kron_gen is None or self.cost._extra is not None or S > self.SPLIT_THRESHOLD:
+            return self.step_staged(None)
+        lib, st = _lib.lib(), _lib.stream_ptr()
+        nd = sd.noise.next()
+        if self._use_dof_major(fields, nf):
+            _lib.check(lib.mpb_stoch_gpmp_iter_kron_gen_dm(
+                _lib.ptr(sd.scale_tril_kron_gen), _lib.ptr(self.Sigma_inv), C.byref(nd), _lib.ptr(self._particle_means),
+                _lib.ptr(self._dm_rows()), _lib.ptr(self.costs), _lib.ptr(self._w_buf), _lib.ptr(self._is_vec),
+                _lib.ptr(self.free_flags), None, None, P, S, H, C.byref(self.robot.desc), fields, nf, C.byref(gp),
+                self.temperature, self.step_size, st))
+            self._x_dm_fresh = True
+            return
+        self._x_dm_fresh = False
+        _lib.check(lib.mpb_stoch_gpmp_iter_kron_gen_ex(
+            _lib.ptr(sd.scale_tril_kron_gen), _lib.ptr(self.Sigma_inv), int(self._sinv_structured), C.byref(nd),
+            _lib.ptr(self._particle_means), _lib.ptr(self._state_samples), _lib.ptr(self.costs), _lib.ptr(self._w_buf),
+            _lib.ptr(self._is_vec), _lib.ptr(self.free_flags), None, None, P, S, H, C.byref(self.robot.desc), fields, nf,
+            C.byref(gp), self.temperature, self.step_size, st))
+
     def step_staged(self, eps=None, events=None):
         """One iteration as four separate C-ABI calls (same kernels as mpb_stoch_gpmp_iter*); ``events`` is an
         optional list of 5 torch.cuda.Event recorded around the stages (bench.py per-kernel timing).  ``eps`` None:
