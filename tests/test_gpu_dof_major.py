@@ -149,3 +149,17 @@ def test_dm_kernels_one_by_one(dev):
                                          _lib.ptr(o1), P, S, H, D, st))
     assert int((w0 != 0).sum()) > 4 * P
     assert torch.equal(w0, w1) and torch.equal(g0, g1) and torch.equal(mu0, mu1) and torch.equal(o0, o1)
+
+
+@pytest.mark.parametrize('mode', ['1', '0'])
+def test_step_fused_is_one_optimize_iteration(mode, dev, monkeypatch):
+    """StochGPMP.step_fused() (one C call, what bench.py times) against optimize(opt_iters=1) on the same draw of the noise stream."""
+    monkeypatch.setenv('MPB_X_DM', mode)
+    a, b = build_arm('C4', 24, dev), build_arm('C4', 24, dev)
+    a._noise.offset = b._noise.offset = 0
+    for _ in range(2):
+        traj = a.optimize(opt_iters=1)
+        b.step_fused()
+    assert torch.equal(traj, b._particle_means) and torch.equal(a._particle_means, b._particle_means)
+    assert torch.equal(a.costs, b.costs) and torch.equal(a._w_buf, b._w_buf) and torch.equal(a.free_flags, b.free_flags)
+    assert torch.equal(a.state_samples, b.state_samples)
